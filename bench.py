@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the pairwise-comparison hot path.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                   (the CPU reference arm, rank 0 only)
+
+Workload (BASELINE.json configs[1]): `-m n_high` all-vs-all over 20,000 synthetic SARS-CoV-2-length
+records (29,903 nt, 1% N / ambiguity codes / gaps).  A step = one pass of the hot path
+(pack_planes -> count tiles -> results) over that alignment.  For N>1 the run is WEAK-scaled: the
+alignment grows to n = round(20000 * sqrt(N)) records so every GPU keeps ~2.0e8 pairs per step;
+ranks own disjoint result panels (dg_run_part) and exchange nothing but the timing reductions.
+
+  value : pairs/s, whole job, inputs resident in HBM, device time from CUDA events on the library's
+          compute stream (dg_timings.run_ms), MAX over ranks.
+  e2e   : same metric through the C ABI with HOST buffers: H2D of the codes from pinned memory,
+          pack, tiles, D2H of every result panel into pinned memory and the sink callback, per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MEASURE = "n_high"
+BASE_N = 20000
+WIDTH = 29903
+SEED = 20251018 + 2
+# algorithmic 32-bit lane-ops per pair-site (4 LOP3 + 1 POPC + 1 IADD per 32 sites)
+OPS_PER_PAIR_SITE = {"n": 0.1875, "n_high": 0.1875, "raw": 0.28125, "jc69": 0.28125, "k80": 0.5, "tn93": 0.5}
+
+
+def load_json(path):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for ts, r in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.2)]
+        if not rows:
+            rows = [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(n: int):
+    from distance_b200 import synth
+    asc = synth.make_alignment(n, width=WIDTH, seed=SEED, ambiguity=True)
+    return synth.encode_ascii(asc)
+
+
+def cpu_baseline(codes, threads: int, budget_s: float):
+    """The oracle (C port of the reference's per-pair loops, -t = all host threads) on a bounded
+    sample: the first R major rows of the same all-vs-all, R sized for ~budget_s of CPU time."""
+    from oracle import oracle as orc
+    a = orc.Alignment(codes)
+    orc.prepare(MEASURE, [a])
+    n = a.n
+    probe_rows = max(threads, 8)
+    pairs, secs = orc.bench(MEASURE, "square", a, None, probe_rows, threads)
+    rate = pairs / max(secs, 1e-9)
+    rows = int(max(probe_rows, min(n - 1, budget_s * rate / n)))
+    rows = rows // threads * threads or threads
+    pairs, secs = orc.bench(MEASURE, "square", a, None, rows, threads)
+    return pairs / secs, pairs, secs, rows
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = int(round(BASE_N * math.sqrt(args.gpus))) if args.n is None else args.n
+    codes = make_workload(min(n, 4000))  # the sample only touches the first rows x all columns
+    threads = os.cpu_count() or 1
+    from oracle import oracle as orc
+    a = orc.Alignment(codes)
+    orc.prepare(MEASURE, [a])
+    # size one step for ~2 s so W+K steps end within a few minutes
+    pairs, secs = orc.bench(MEASURE, "square", a, None, threads, threads)
+    rows = max(threads, int(2.0 * (pairs / secs) / a.n) // threads * threads)
+    rows = min(rows, a.n - 1)
+    for _ in range(args.warmup):
+        orc.bench(MEASURE, "square", a, None, rows, threads)
+    tot_pairs, tot_s = 0, 0.0
+    for _ in range(args.steps):
+        p, s = orc.bench(MEASURE, "square", a, None, rows, threads)
+        tot_pairs += p; tot_s += s
+    value = tot_pairs / tot_s
+    sample = (f"first {rows} rows x {a.n} records of the synthetic alignment per step "
+              f"({tot_pairs // args.steps} pairs/step), oracle C port, {threads} pthreads")
+    line = {
+        "impl": "reference", "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
+        "pair_sites_per_s": value * WIDTH, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"config 2: -m {MEASURE} all-vs-all, 29,903 nt, 1% N/ambiguity/gaps (bounded CPU sample)",
+                   "measure": MEASURE, "width": WIDTH},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated reference (C oracle), not the Rust binary: no Rust toolchain in this image",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import distance_b200 as dg
+    from distance_b200 import api, dist
+
+    d = dist.Dist()
+    rank, world = d.rank, d.world
+    if args.gpus != world and world > 1:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
+    n = int(round(BASE_N * math.sqrt(world))) if args.n is None else args.n
+    dg.load_library()
+    if dg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (the library has no CPU fallback)")
+
+    codes = make_workload(n)
+    pinned = api.pinned_array(codes.shape, np.uint8)
+    pinned[...] = codes
+    plan = api.plan_panels(MEASURE, api.DG_MODE_SQUARE, n, n, args.panel_bytes)
+    my_pairs = sum(p[2] for p in dist.my_panels(plan, rank, world))
+    total_pairs = n * (n - 1) // 2
+
+    eng = dg.Engine(MEASURE, WIDTH, gpus=[d.local_rank])
+    eng.set_option(api.DG_OPT_PANEL_BYTES, args.panel_bytes)
+    eng.set_option(api.DG_OPT_KEEP_CODES, 1)
+    if args.tile_variant:
+        eng.set_option(api.DG_OPT_TILE_VARIANT, args.tile_variant)
+    eng.load(0, pinned)
+
+    def sync_all():
+        d.barrier()
+
+    # ---- warm-up ------------------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
+
+    sampler = ClockSampler(d.local_rank)
+    sampler.start()
+    time.sleep(0.3)
+
+    # ---- value: device-resident inputs, kernel-only, CUDA events --------------------------------
+    sync_all()
+    eng.reset_timings()
+    t_wall0 = time.time()
+    dev_ms = 0.0
+    for _ in range(args.steps):
+        eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
+        dev_ms += eng.timings()["run_ms"]
+    sync_all()
+    t_wall1 = time.time()
+    tm = eng.timings()
+    step_ms = d.max(dev_ms / args.steps)
+    wall_step_ms = d.max(1e3 * (t_wall1 - t_wall0) / args.steps)
+    value = total_pairs / (step_ms * 1e-3)
+    launches = int(d.sum(tm["pack_launches"] + tm["count_launches"]))
+    count_launch_ms = tm["count_ms"] / max(tm["count_launches"], 1)
+
+    # ---- e2e: host buffers through the C ABI ----------------------------------------------------
+    for _ in range(2):
+        eng.load(0, pinned)
+        eng.run_discard(api.DG_MODE_SQUARE, rank, world)
+    sync_all()
+    t0 = time.time()
+    for _ in range(args.steps):
+        eng.load(0, pinned)                                   # H2D from pinned host memory + pack
+        got = eng.run_discard(api.DG_MODE_SQUARE, rank, world)  # tiles + D2H + sink reads each panel
+        assert got == my_pairs
+    sync_all()
+    t1 = time.time()
+    e2e_step_ms = d.max(1e3 * (t1 - t0) / args.steps)
+    e2e_value = total_pairs / (e2e_step_ms * 1e-3)
+    clocks = sampler.stop(t_wall0, t1)
+
+    # ---- roofline of the dominant kernel (count_tile_kernel) ------------------------------------
+    # achieved = algorithmic lane-ops of this rank's launches / device time of those launches.
+    ops = my_pairs * WIDTH * OPS_PER_PAIR_SITE[MEASURE]
+    count_ms_step = tm["count_ms"] / args.steps
+    run_ms_step = dev_ms / args.steps
+    peaks = load_json(os.path.join(ROOT, "profiles", "int_peaks.json")) or {}
+    measured = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+    if "lop3_lane_ops_per_s" in peaks:
+        peak, peak_src = peaks["lop3_lane_ops_per_s"] / 1e12, "measured: tools/ubench_int LOP3 (profiles/int_peaks.json)"
+    else:
+        mhz = clocks.get("sm_mhz") or measured.get("sm_max_mhz", 1965.0)
+        peak, peak_src = 64 * 148 * mhz * 1e6 / 1e12, f"nominal 64 lanes/clk/SM x 148 SM x {mhz:.0f} MHz (no measured int peak yet)"
+    achieved = ops / (run_ms_step * 1e-3) / 1e12
+    roofline = {
+        "bound": "int_alu", "kernel": "count_tile_kernel<FAM_SNP>", "achieved": achieved, "peak": peak,
+        "unit": "Tlaneop/s", "frac": achieved / peak, "traffic": (peaks.get("count_kernel_dram_bytes_per_launch")),
+        "ops_per_pair_site": OPS_PER_PAIR_SITE[MEASURE], "peak_source": peak_src,
+        "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
+        "note": "the path is integer-issue bound, not HBM/tensor bound (SURVEY 8d); launches of consecutive "
+                "panels overlap on two streams, so achieved uses the device time of the whole step",
+    }
+    hbm = measured.get("hbm_gbs")
+    pack_ms_step = tm["pack_ms"] / args.steps
+    pack_bytes = n * WIDTH + n * math.ceil(WIDTH / 32) * 16  # read 1 B/site, write the 4 core planes
+    roofline_pack = {"bound": "hbm", "kernel": "pack_planes_kernel", "achieved": pack_bytes / (pack_ms_step * 1e-3) / 1e9,
+                     "peak": hbm, "unit": "GB/s", "frac": (pack_bytes / (pack_ms_step * 1e-3) / 1e9 / hbm) if hbm else None,
+                     "ms": pack_ms_step}
+
+    line = None
+    if rank == 0:
+        cb_value, cb_pairs, cb_secs, cb_rows = (None, 0, 0.0, 0)
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            cb_value, cb_pairs, cb_secs, cb_rows = cpu_baseline(codes, threads, args.cpu_budget)
+            cpu = {"value": cb_value, "unit": "pairs/s", "cores": threads, "kind": "port",
+                   "sample": f"first {cb_rows} rows x {n} records of the same alignment ({cb_pairs} pairs, {cb_secs:.1f} s), "
+                             f"oracle C port of measures.rs snp, {threads} pthreads"}
+        else:
+            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "skipped (N>1 or --no-cpu-baseline)"}
+        line = {
+            "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
+            "pair_sites_per_s": value * WIDTH, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32 bit-planes (popcount), u32 results", "data": "synthetic",
+            "config": {"workload": f"config 2: -m {MEASURE} all-vs-all, {n:,} x 29,903 nt, 1% N/ambiguity/gaps",
+                       "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
+                       "weak_scaling": "n = round(20000*sqrt(N)) so pairs per GPU stay ~2.0e8",
+                       "panel_bytes": args.panel_bytes, "panels": len(plan),
+                       "l2": "inputs larger than L2 (bit-planes %.0f MB vs 126 MB L2)" % (n * 936 * 16 / 1e6)},
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
+                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * 4)},
+            "gpu_launches": launches,
+            "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    eng.close()
+    d.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=None, help="override the record count (debug)")
+    ap.add_argument("--panel-bytes", type=int, default=128 << 20)
+    ap.add_argument("--tile-variant", type=int, default=0)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

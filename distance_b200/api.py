@@ -1,0 +1,336 @@
+"""ctypes binding of include/distance_gpu.h (libdistance_gpu.so).
+
+Mirrors the C ABI one to one; `Engine` is a convenience wrapper used by tests and bench.py.
+No computation happens in Python and there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB_PATH = os.path.join(_ROOT, "distance_b200", "_lib", "libdistance_gpu.so")
+
+MEASURES = {"n": 0, "n_high": 1, "raw": 2, "jc69": 3, "k80": 4, "tn93": 5}
+DG_INPUT_PARADIS, DG_INPUT_ASCII = 0, 1
+DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
+DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
+DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE = 1, 2, 3, 4
+DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
+          -4: "DG_ERR_INVALID_CODE", -5: "DG_ERR_SINK", -6: "DG_ERR_NOMEM"}
+
+# every symbol include/distance_gpu.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "dg_abi_version", "dg_device_count", "dg_create", "dg_destroy", "dg_last_error", "dg_set_option",
+    "dg_load_resident", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
+    "dg_stream_begin", "dg_stream_push", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
+    "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels",
+]
+
+
+class DistanceGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{DG_ERR.get(code, code)}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class Panel(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32),
+        ("result_kind", C.c_int32),
+        ("row_begin", C.c_uint64),
+        ("row_end", C.c_uint64),
+        ("n_cols", C.c_uint64),
+        ("n_results", C.c_uint64),
+        ("data", C.c_void_p),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("pack_ms", C.c_double), ("count_ms", C.c_double), ("h2d_ms", C.c_double),
+        ("total_ms", C.c_double), ("run_ms", C.c_double), ("pack_launches", C.c_uint64), ("count_launches", C.c_uint64),
+        ("pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+    ]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+SINK_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(Panel))
+
+_lib = None
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def build_library(force: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a build of the in-tree library (Makefile `lib`)."""
+    srcs = [os.path.join(_ROOT, "distance_b200", "csrc", f) for f in ("dg_api.cu", "kernels.cuh")]
+    srcs.append(os.path.join(_ROOT, "include", "distance_gpu.h"))
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", _ROOT, "lib"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+def load_library():
+    """Load libdistance_gpu.so.  Fails loudly if it is missing: there is no fallback path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise DistanceGpuError(-2, f"{_LIB_PATH} is missing: run `make lib` (or __graft_entry__.build())")
+    L = C.CDLL(_LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.dg_abi_version.restype = i32
+    L.dg_device_count.restype = i32
+    L.dg_create.argtypes = [C.POINTER(C.c_int), i32, i32, u64, C.POINTER(vp)]
+    L.dg_destroy.argtypes = [vp]
+    L.dg_destroy.restype = None
+    L.dg_last_error.argtypes = [vp]
+    L.dg_last_error.restype = C.c_char_p
+    L.dg_set_option.argtypes = [vp, i32, C.c_int64]
+    L.dg_load_resident.argtypes = [vp, i32, vp, u64, i32, vp]
+    L.dg_invalid_site.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_uint8)]
+    L.dg_run_square.argtypes = [vp, SINK_FN, vp, C.c_uint32]
+    L.dg_run_rect.argtypes = [vp, SINK_FN, vp, C.c_uint32]
+    L.dg_run_part.argtypes = [vp, i32, C.c_uint32, C.c_uint32, SINK_FN, vp, C.c_uint32]
+    L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
+    L.dg_stream_push.argtypes = [vp, vp, u64, i32, vp]
+    L.dg_stream_end.argtypes = [vp]
+    L.dg_debug_counts.argtypes = [vp, i32, i32, vp]
+    L.dg_debug_planes.argtypes = [vp, i32, vp, vp, vp, C.POINTER(u64)]
+    L.dg_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    L.dg_reset_timings.argtypes = [vp]
+    L.dg_alloc_pinned.argtypes = [C.c_size_t]
+    L.dg_alloc_pinned.restype = vp
+    L.dg_free_pinned.argtypes = [vp]
+    L.dg_free_pinned.restype = None
+    L.dg_plan_panels.argtypes = [i32, i32, u64, u64, u64, i32, vp, vp, vp, u64]
+    L.dg_plan_panels.restype = C.c_int64
+    for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_invalid_site", "dg_run_square",
+                 "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_end",
+                 "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return int(load_library().dg_device_count())
+
+
+_NULL_SINK = C.cast(None, SINK_FN)
+DEFAULT_PANEL_BYTES = 128 << 20
+
+
+def plan_panels(measure: str, mode: int, n_rows: int, n_cols: int, panel_bytes: int = DEFAULT_PANEL_BYTES,
+                tile_variant: int = 0):
+    """dg_plan_panels: [(row_begin, row_end, n_results)] -- host arithmetic only, needs no GPU."""
+    L = load_library()
+    n = L.dg_plan_panels(MEASURES[measure], mode, n_rows, n_cols, panel_bytes, tile_variant, None, None, None, 0)
+    if n < 0:
+        raise DistanceGpuError(int(n), "dg_plan_panels")
+    rb, re_, nr = (np.zeros(max(n, 1), dtype=np.uint64) for _ in range(3))
+    L.dg_plan_panels(MEASURES[measure], mode, n_rows, n_cols, panel_bytes, tile_variant,
+                     rb.ctypes.data_as(C.c_void_p), re_.ctypes.data_as(C.c_void_p),
+                     nr.ctypes.data_as(C.c_void_p), n)
+    return [(int(rb[k]), int(re_[k]), int(nr[k])) for k in range(n)]
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """A numpy array over page-locked memory from dg_alloc_pinned (freed with the process)."""
+    L = load_library()
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = L.dg_alloc_pinned(max(n, 1))
+    if not p:
+        raise DistanceGpuError(-6, "dg_alloc_pinned failed")
+    buf = (C.c_uint8 * max(n, 1)).from_address(p)
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+class Engine:
+    """One dg_ctx.  measure: 'n' | 'n_high' | 'raw' | 'jc69' | 'k80' | 'tn93'."""
+
+    def __init__(self, measure: str, width: int, gpus=None):
+        self.L = load_library()
+        self.measure = measure
+        self.width = int(width)
+        ids = list(gpus) if gpus is not None else [0]
+        arr = (C.c_int * len(ids))(*ids)
+        h = C.c_void_p()
+        rc = self.L.dg_create(arr, len(ids), MEASURES[measure], self.width, C.byref(h))
+        if rc != 0:
+            raise DistanceGpuError(rc, self.L.dg_last_error(None).decode())
+        self.h = h
+        self.is_int = measure in ("n", "n_high")
+        self._n = [0, 0]
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise DistanceGpuError(rc, self.L.dg_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.dg_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: int, value: int):
+        self._check(self.L.dg_set_option(self.h, key, value))
+
+    # -- inputs ----------------------------------------------------------------------------------
+    def load(self, which: int, codes: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        assert codes.ndim == 2 and codes.shape[1] == self.width
+        cnt = None if acgt is None else np.ascontiguousarray(acgt, dtype=np.uint64)
+        self._check(self.L.dg_load_resident(
+            self.h, which, codes.ctypes.data_as(C.c_void_p), codes.shape[0], input_kind,
+            None if cnt is None else cnt.ctypes.data_as(C.c_void_p)))
+        self._n[which] = codes.shape[0]
+
+    def invalid_site(self):
+        r, s, b = C.c_uint64(), C.c_uint64(), C.c_uint8()
+        self._check(self.L.dg_invalid_site(self.h, C.byref(r), C.byref(s), C.byref(b)))
+        return int(r.value), int(s.value), int(b.value)
+
+    # -- runs ------------------------------------------------------------------------------------
+    def _collect(self, total: int):
+        dtype = np.uint32 if self.is_int else np.float64
+        out = np.empty(total, dtype=dtype)
+        state = {"pos": 0, "panels": []}
+
+        def sink(user, pp):
+            p = pp.contents
+            n = int(p.n_results)
+            src = np.frombuffer((C.c_uint8 * (n * out.itemsize)).from_address(p.data), dtype=dtype, count=n)
+            out[state["pos"]:state["pos"] + n] = src
+            state["pos"] += n
+            state["panels"].append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), n))
+            return 0
+
+        return out, state, SINK_FN(sink)
+
+    def run_square(self, flags: int = 0):
+        n = self._n[0]
+        out, st, cb = self._collect(n * (n - 1) // 2)
+        self._check(self.L.dg_run_square(self.h, cb, None, flags))
+        assert st["pos"] == out.shape[0], (st["pos"], out.shape)
+        self.last_panels = st["panels"]
+        return out
+
+    def run_rect(self, flags: int = 0):
+        out, st, cb = self._collect(self._n[0] * self._n[1])
+        self._check(self.L.dg_run_rect(self.h, cb, None, flags))
+        assert st["pos"] == out.shape[0]
+        self.last_panels = st["panels"]
+        return out
+
+    def run_part(self, mode: int, part: int, n_parts: int, flags: int = 0):
+        """Returns [(row_begin, row_end, values)] for this part's panels."""
+        dtype = np.uint32 if self.is_int else np.float64
+        got = []
+
+        def sink(user, pp):
+            p = pp.contents
+            n = int(p.n_results)
+            src = np.frombuffer((C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(p.data),
+                                dtype=dtype, count=n)
+            got.append((int(p.row_begin), int(p.row_end), src.copy()))
+            return 0
+
+        self._check(self.L.dg_run_part(self.h, mode, part, n_parts, SINK_FN(sink), None, flags))
+        return got
+
+    def run_device_only(self, mode: int = DG_MODE_SQUARE, part: int = 0, n_parts: int = 1, repack: bool = False):
+        flags = DG_RUN_DEVICE_ONLY | (DG_RUN_REPACK if repack else 0)
+        self._check(self.L.dg_run_part(self.h, mode, part, n_parts, _NULL_SINK, None, flags))
+
+    def run_discard(self, mode: int = DG_MODE_SQUARE, part: int = 0, n_parts: int = 1, touch: bool = True):
+        """Full e2e run (D2H into pinned panels + sink) whose sink only reads one word per panel."""
+        state = {"n": 0, "acc": 0}
+
+        def sink(user, pp):
+            p = pp.contents
+            state["n"] += int(p.n_results)
+            if touch and p.n_results:
+                state["acc"] ^= C.c_uint32.from_address(p.data).value
+            return 0
+
+        self._check(self.L.dg_run_part(self.h, mode, part, n_parts, SINK_FN(sink), None, 0))
+        return state["n"]
+
+    def stream(self, batches, input_kind: int = DG_INPUT_PARADIS, max_batch: int = 1 << 20, acgt_batches=None):
+        """Stream an iterable of (n_b x width) uint8 arrays against alignment 0."""
+        dtype = np.uint32 if self.is_int else np.float64
+        chunks, panels = [], []
+
+        def sink(user, pp):
+            p = pp.contents
+            n = int(p.n_results)
+            src = np.frombuffer((C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(p.data),
+                                dtype=dtype, count=n)
+            chunks.append(src.copy())
+            panels.append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), n))
+            return 0
+
+        cb = SINK_FN(sink)
+        self._check(self.L.dg_stream_begin(self.h, cb, None, max_batch))
+        for k, b in enumerate(batches):
+            b = np.ascontiguousarray(b, dtype=np.uint8)
+            cnt = None
+            if acgt_batches is not None:
+                cnt = np.ascontiguousarray(acgt_batches[k], dtype=np.uint64)
+            self._check(self.L.dg_stream_push(
+                self.h, b.ctypes.data_as(C.c_void_p), b.shape[0], input_kind,
+                None if cnt is None else cnt.ctypes.data_as(C.c_void_p)))
+        self._check(self.L.dg_stream_end(self.h))
+        self.last_panels = panels
+        return np.concatenate(chunks) if chunks else np.zeros(0, dtype=dtype)
+
+    # -- debug / parity --------------------------------------------------------------------------
+    def debug_counts(self, which_a: int = 0, which_b: int = 0) -> np.ndarray:
+        out = np.zeros((self._n[which_a], self._n[which_b], 4), dtype=np.uint32)
+        self._check(self.L.dg_debug_counts(self.h, which_a, which_b, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def debug_planes(self, which: int = 0, want_aux: bool = True):
+        words = C.c_uint64()
+        self._check(self.L.dg_debug_planes(self.h, which, None, None, None, C.byref(words)))
+        n, w = self._n[which], int(words.value)
+        core = np.zeros((n, w, 4), dtype=np.uint32)
+        aux = np.zeros((n, w, 4), dtype=np.uint32) if want_aux else None
+        acgt = np.zeros((n, 4), dtype=np.uint64)
+        self._check(self.L.dg_debug_planes(
+            self.h, which, core.ctypes.data_as(C.c_void_p),
+            None if aux is None else aux.ctypes.data_as(C.c_void_p),
+            acgt.ctypes.data_as(C.c_void_p), C.byref(words)))
+        return core, aux, acgt
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self.L.dg_get_timings(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def reset_timings(self):
+        self._check(self.L.dg_reset_timings(self.h))

@@ -1,0 +1,902 @@
+// dg_api.cu -- host side of libdistance_gpu: context, plane residency, the panel / tile scheduler
+// that replaces the reference's thread + batch scheduler (lib.rs:269-596), -s streaming through
+// double-buffered pinned batches, and the extern "C" entry points of include/distance_gpu.h.
+//
+// No CPU fallback lives here: every compute entry point needs a CUDA device.
+#include "../../include/distance_gpu.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+using namespace dg;
+
+thread_local std::string g_create_error;
+
+double wall_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DgError {
+    int code;
+    std::string msg;
+};
+
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    throw DgError{code, buf};
+}
+
+#define CUDA_CHECK(expr)                                                                   \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            fail(e_ == cudaErrorMemoryAllocation ? DG_ERR_NOMEM : DG_ERR_CUDA,             \
+                 "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__,   \
+                 cudaGetErrorString(e_));                                                  \
+    } while (0)
+
+// ---- tile shapes -------------------------------------------------------------------------------
+struct TileShape { int tm, tn; };
+
+TileShape tile_shape(int fam, int variant) {
+    switch (fam) {
+    case FAM_SNP:  return variant == 1 ? TileShape{128, 64} : TileShape{128, 128};
+    case FAM_RAW:  return variant == 1 ? TileShape{64, 64} : TileShape{64, 128};
+    default:       return TileShape{64, 64};
+    }
+}
+
+template <int FAM, int RM, int RN, bool COUNTS, int MINB>
+void launch_tile(const CountParams& p, dim3 grid, cudaStream_t s) {
+    using Cfg = TileCfg<FAM, RM, RN>;
+    auto kern = count_tile_kernel<FAM, RM, RN, COUNTS, MINB>;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(p);
+    CUDA_CHECK(cudaGetLastError());
+}
+
+template <bool COUNTS>
+void launch_count(int fam, int variant, const CountParams& p, dim3 grid, cudaStream_t s) {
+    switch (fam) {
+    case FAM_SNP:
+        if (variant == 1) launch_tile<FAM_SNP, 8, 4, COUNTS, 2>(p, grid, s);
+        else launch_tile<FAM_SNP, 8, 8, COUNTS, 2>(p, grid, s);
+        break;
+    case FAM_RAW:
+        if (variant == 1) launch_tile<FAM_RAW, 4, 4, COUNTS, 2>(p, grid, s);
+        else launch_tile<FAM_RAW, 4, 8, COUNTS, 2>(p, grid, s);
+        break;
+    case FAM_K80: launch_tile<FAM_K80, 4, 4, COUNTS, 2>(p, grid, s); break;
+    default: launch_tile<FAM_TN93, 4, 4, COUNTS, 2>(p, grid, s); break;
+    }
+}
+
+// ---- per-device state --------------------------------------------------------------------------
+struct PlaneSet {  // one alignment packed on one device
+    uint64_t n = 0, n_pad = 0;
+    uint4* core = nullptr;
+    uint4* aux = nullptr;
+    uint32_t* acgt = nullptr;
+    uint8_t* codes = nullptr;  // kept only with DG_OPT_KEEP_CODES
+    int input_kind = 0;
+    bool acgt_from_host = false;
+};
+
+struct Slot {  // one stage of the result ring (and of the stream-input ring)
+    void* d_out = nullptr;
+    void* h_out = nullptr;
+    cudaEvent_t k_start = nullptr, k_stop = nullptr, copied = nullptr, in_ready = nullptr;
+    // stream mode staging
+    uint8_t* h_in = nullptr;
+    uint8_t* d_in = nullptr;
+    uint32_t* h_acgt = nullptr;
+    PlaneSet batch;
+    cudaEvent_t p_start = nullptr, p_stop = nullptr;
+};
+
+struct Device {
+    int id = 0;
+    // compute = stream of ring slot 0 (also packs / resident loads), compute2 = stream of ring slot 1:
+    // consecutive panels alternate streams so the tail wave of one launch overlaps the next launch.
+    cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr, copy_in = nullptr;
+    cudaStream_t cs(int slot) const { return slot ? compute2 : compute; }
+    PlaneSet set[2];
+    Slot slot[2];
+    size_t out_cap = 0;   // bytes of d_out / h_out
+    size_t in_cap = 0;    // records of stream staging
+    cudaEvent_t run_start = nullptr, run_stop = nullptr;
+    unsigned long long* d_invalid = nullptr;  // [3]: ring slot 0, ring slot 1, resident loads
+    unsigned long long* h_invalid = nullptr;  // [3] pinned mirror
+};
+
+struct Panel {
+    uint64_t row0, row1;   // major rows
+    uint64_t out_base;     // global index of the first result
+    uint64_t n_results;
+};
+
+struct InFlight {  // a panel / batch whose results have not been handed to the sink yet
+    int dev = 0, slot = 0;
+    dg_panel desc{};
+    bool pack_timed = false;
+    uint64_t pairs = 0;
+};
+
+}  // namespace
+
+struct dg_ctx {
+    int measure = 0, fam = 0;
+    uint64_t width = 0;
+    uint32_t wp = 0;
+    std::vector<Device> devs;
+    std::string err;
+    // options
+    size_t panel_bytes = (size_t)128 << 20;
+    bool keep_codes = false;
+    int tile_variant = 0;
+    int engine = 0;
+    // invalid-site report
+    bool have_invalid = false;
+    uint64_t inv_record = 0, inv_site = 0;
+    uint8_t inv_byte = 0;
+    dg_timings tm{};
+    // stream session
+    bool streaming = false;
+    dg_sink_fn s_sink = nullptr;
+    void* s_user = nullptr;
+    uint64_t s_max_batch = 0, s_rows_pushed = 0, s_batches = 0;
+    std::vector<InFlight> s_queue;  // FIFO of batches not yet sunk
+    double s_t0 = 0;
+
+    size_t elem_bytes() const { return measure <= 1 ? 4 : 8; }
+    int result_kind() const { return measure <= 1 ? DG_RESULT_U32 : DG_RESULT_F64; }
+};
+
+namespace {
+
+void free_set(PlaneSet& s) {
+    if (s.core) cudaFree(s.core);
+    if (s.aux) cudaFree(s.aux);
+    if (s.acgt) cudaFree(s.acgt);
+    if (s.codes) cudaFree(s.codes);
+    s = PlaneSet{};
+}
+
+void alloc_set(dg_ctx* c, PlaneSet& s, uint64_t n, bool with_codes) {
+    s.n = n;
+    s.n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+    const size_t plane_bytes = (size_t)s.n_pad * c->wp * sizeof(uint4);
+    CUDA_CHECK(cudaMalloc(&s.core, plane_bytes));
+    if (c->fam != FAM_SNP) CUDA_CHECK(cudaMalloc(&s.aux, plane_bytes));
+    CUDA_CHECK(cudaMalloc(&s.acgt, (size_t)s.n_pad * 4 * sizeof(uint32_t)));
+    if (with_codes) CUDA_CHECK(cudaMalloc(&s.codes, (size_t)std::max<uint64_t>(1, n * c->width)));
+}
+
+// Enqueue pack_planes for `n` records whose code bytes are at d_codes.
+void enqueue_pack(dg_ctx* c, unsigned long long* d_inv, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
+                  int input_kind, bool count_on_device, bool upper_ascii, cudaStream_t st) {
+    PackParams pp{};
+    pp.codes = d_codes;
+    pp.n = n;
+    pp.n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+    pp.width = c->width;
+    pp.wp = c->wp;
+    pp.core = s.core;
+    pp.aux = s.aux;
+    pp.acgt = count_on_device ? s.acgt : nullptr;
+    pp.count_upper_ascii = upper_ascii ? 1 : 0;
+    pp.invalid = d_inv;
+    if (count_on_device) CUDA_CHECK(cudaMemsetAsync(s.acgt, 0, (size_t)pp.n_pad * 4 * sizeof(uint32_t), st));
+    const uint64_t units = pp.n_pad * (c->wp / 4);
+    const uint64_t blocks = std::min<uint64_t>((units + 7) / 8, (uint64_t)148 * 16);
+    if (input_kind == DG_INPUT_ASCII)
+        pack_planes_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(pp);
+    else
+        pack_planes_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(pp);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.pack_launches++;
+}
+
+// After a sync: did pack_planes see an invalid byte?  `probe` fetches the byte for the report.
+void check_invalid(dg_ctx* c, Device& d, const uint8_t* host_codes, uint64_t row_offset) {
+    CUDA_CHECK(cudaMemcpy(d.h_invalid + 2, d.d_invalid + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const unsigned long long key = d.h_invalid[2];
+    if (key == ~0ull) return;
+    const unsigned long long reset = ~0ull;
+    CUDA_CHECK(cudaMemcpy(d.d_invalid + 2, &reset, sizeof reset, cudaMemcpyHostToDevice));
+    c->have_invalid = true;
+    c->inv_record = (key >> 32) + row_offset;
+    c->inv_site = key & 0xffffffffull;
+    c->inv_byte = host_codes ? host_codes[(key >> 32) * c->width + c->inv_site] : 0;
+    fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in record %llu at site %llu", c->inv_byte,
+         (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
+}
+
+void ensure_out_ring(dg_ctx* c, Device& d, size_t bytes) {
+    if (d.out_cap >= bytes) return;
+    for (auto& s : d.slot) {
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        s.d_out = s.h_out = nullptr;
+    }
+    d.out_cap = 0;
+    for (auto& s : d.slot) {
+        CUDA_CHECK(cudaMalloc(&s.d_out, bytes));
+        CUDA_CHECK(cudaHostAlloc(&s.h_out, bytes, cudaHostAllocDefault));
+    }
+    d.out_cap = bytes;
+}
+
+uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
+
+std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, uint64_t n_rows_total,
+                               uint64_t n_cols, int tm) {
+    // rows per panel: a multiple of the tile height sized so one panel's results ~ panel_bytes
+    std::vector<Panel> v;
+    const uint64_t rows_major = mode == DG_MODE_SQUARE ? (n_rows_total ? n_rows_total - 1 : 0) : n_rows_total;
+    if (rows_major == 0 || n_cols == 0) return v;
+    uint64_t per = panel_bytes / (elem_bytes * std::max<uint64_t>(1, n_cols));
+    per = std::min<uint64_t>(per, (uint64_t)tm * 32768);  // gridDim.y limit
+    per = std::max<uint64_t>(tm, per / tm * tm);
+    for (uint64_t r = 0; r < rows_major; r += per) {
+        Panel p;
+        p.row0 = r;
+        p.row1 = std::min(rows_major, r + per);
+        if (mode == DG_MODE_SQUARE) {
+            p.out_base = sq_off(n_rows_total, p.row0);
+            p.n_results = sq_off(n_rows_total, p.row1) - p.out_base;
+        } else {
+            p.out_base = p.row0 * n_cols;
+            p.n_results = (p.row1 - p.row0) * n_cols;
+        }
+        v.push_back(p);
+    }
+    return v;
+}
+
+// Enqueue the count tiles of one panel on d.compute, writing slot.d_out.
+template <bool COUNTS>
+void enqueue_panel_kernel(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode,
+                          const Panel& p, void* d_out, bool swap_roles, cudaStream_t st) {
+    const TileShape ts = tile_shape(c->fam, c->tile_variant);
+    CountParams cp{};
+    cp.a_core = A.core; cp.a_aux = A.aux; cp.a_acgt = A.acgt;
+    cp.b_core = B.core; cp.b_aux = B.aux; cp.b_acgt = B.acgt;
+    cp.n_b = (uint32_t)B.n;
+    cp.wp = c->wp;
+    cp.row0 = (uint32_t)p.row0;
+    cp.row_end = (uint32_t)p.row1;
+    cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
+    cp.swap_roles = swap_roles ? 1 : 0;
+    cp.n_total = A.n;
+    cp.out_base = COUNTS ? 0 : p.out_base;
+    cp.out = d_out;
+    cp.measure = c->measure;
+    cp.col_block0 = cp.square ? (uint32_t)((p.row0 + 1) / ts.tn) : 0;
+    const uint64_t col_blocks_total = (B.n + ts.tn - 1) / ts.tn;
+    dim3 grid((unsigned)(col_blocks_total - cp.col_block0), (unsigned)((p.row1 - p.row0 + ts.tm - 1) / ts.tm));
+    if (grid.x == 0 || grid.y == 0) return;
+    if (grid.y > 65535) fail(DG_ERR_INVALID_ARG, "panel too tall for one launch (%u row blocks)", grid.y);
+    launch_count<COUNTS>(c->fam, c->tile_variant, cp, grid, st);
+    c->tm.count_launches++;
+}
+
+void harvest_kernel_time(dg_ctx* c, Slot& s) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.k_start, s.k_stop) == cudaSuccess) c->tm.count_ms += ms;
+}
+
+// ---- square / rect runs ------------------------------------------------------------------------
+void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user,
+              uint32_t flags) {
+    if (c->streaming) fail(DG_ERR_STATE, "a stream session is open");
+    if (n_parts == 0 || part >= n_parts) fail(DG_ERR_INVALID_ARG, "bad part %u of %u", part, n_parts);
+    const int wb = mode == DG_MODE_SQUARE ? 0 : 1;
+    for (auto& d : c->devs) {
+        if (d.set[0].n == 0) fail(DG_ERR_STATE, "alignment 0 is not loaded");
+        if (d.set[wb].n == 0) fail(DG_ERR_STATE, "alignment %d is not loaded", wb);
+    }
+    const bool device_only = (flags & DG_RUN_DEVICE_ONLY) != 0;
+    if (!device_only && sink == nullptr) fail(DG_ERR_INVALID_ARG, "sink is NULL");
+    const double t0 = wall_ms();
+    const int ndev = (int)c->devs.size();
+    for (auto& d : c->devs) {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        CUDA_CHECK(cudaEventRecord(d.run_start, d.compute));
+        CUDA_CHECK(cudaStreamWaitEvent(d.compute2, d.run_start, 0));
+    }
+
+    if (flags & DG_RUN_REPACK) {
+        for (auto& d : c->devs) {
+            CUDA_CHECK(cudaSetDevice(d.id));
+            for (int w = 0; w <= wb; w++) {
+                PlaneSet& s = d.set[w];
+                if (!s.codes) fail(DG_ERR_STATE, "DG_RUN_REPACK needs DG_OPT_KEEP_CODES before loading");
+                CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
+                enqueue_pack(c, d.d_invalid + 2, s, s.codes, s.n, s.input_kind, !s.acgt_from_host, false, d.compute);
+                CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
+                CUDA_CHECK(cudaEventSynchronize(d.slot[0].p_stop));
+                float ms = 0;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
+                c->tm.pack_ms += ms;
+            }
+        }
+    }
+
+    const PlaneSet& A0 = c->devs[0].set[0];
+    const PlaneSet& B0 = c->devs[0].set[wb];
+    const TileShape ts = tile_shape(c->fam, c->tile_variant);
+    std::vector<Panel> all = make_panels(c->panel_bytes, c->elem_bytes(), mode, A0.n, B0.n, ts.tm);
+    std::vector<Panel> mine;
+    for (size_t k = 0; k < all.size(); k++)
+        if (k % n_parts == part) mine.push_back(all[k]);
+    size_t max_bytes = 0;
+    for (auto& p : mine) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
+    for (auto& d : c->devs) {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
+    }
+
+    const int K = (int)mine.size();
+    const int lookahead = 2 * ndev;
+    for (int k = 0; k < K + lookahead; k++) {
+        const int h = k - lookahead;  // panel to hand to the sink
+        if (h >= 0) {
+            Device& d = c->devs[h % ndev];
+            Slot& s = d.slot[(h / ndev) & 1];
+            CUDA_CHECK(cudaSetDevice(d.id));
+            CUDA_CHECK(cudaEventSynchronize(device_only ? s.k_stop : s.copied));
+            harvest_kernel_time(c, s);
+            const Panel& p = mine[h];
+            c->tm.pairs += p.n_results;
+            if (!device_only) {
+                dg_panel desc{};
+                desc.mode = mode;
+                desc.result_kind = c->result_kind();
+                desc.row_begin = p.row0;
+                desc.row_end = p.row1;
+                desc.n_cols = mode == DG_MODE_SQUARE ? A0.n : B0.n;
+                desc.n_results = p.n_results;
+                desc.data = s.h_out;
+                c->tm.d2h_bytes += p.n_results * c->elem_bytes();
+                if (sink(user, &desc) != 0) {
+                    for (auto& dd : c->devs) { cudaSetDevice(dd.id); cudaDeviceSynchronize(); }
+                    fail(DG_ERR_SINK, "sink aborted the run at panel %d", h);
+                }
+            }
+        }
+        if (k < K) {
+            Device& d = c->devs[k % ndev];
+            const int si = (k / ndev) & 1;
+            Slot& s = d.slot[si];
+            CUDA_CHECK(cudaSetDevice(d.id));
+            const Panel& p = mine[k];
+            CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
+            enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
+            CUDA_CHECK(cudaEventRecord(s.k_stop, d.cs(si)));
+            if (!device_only) {
+                CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
+                CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(),
+                                           cudaMemcpyDeviceToHost, d.copy));
+                CUDA_CHECK(cudaEventRecord(s.copied, d.copy));
+            }
+        }
+    }
+    c->tm.run_ms = 0;
+    for (auto& d : c->devs) {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        CUDA_CHECK(cudaEventRecord(d.slot[1].in_ready, d.compute2));
+        CUDA_CHECK(cudaStreamWaitEvent(d.compute, d.slot[1].in_ready, 0));
+        CUDA_CHECK(cudaEventRecord(d.run_stop, d.compute));
+        CUDA_CHECK(cudaEventSynchronize(d.run_stop));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, d.run_start, d.run_stop));
+        c->tm.run_ms = std::max<double>(c->tm.run_ms, ms);
+    }
+    c->tm.total_ms = wall_ms() - t0;
+}
+
+// ---- stream session ----------------------------------------------------------------------------
+void stream_sink_front(dg_ctx* c) {
+    InFlight f = c->s_queue.front();
+    Device& d = c->devs[f.dev];
+    Slot& s = d.slot[f.slot];
+    CUDA_CHECK(cudaSetDevice(d.id));
+    CUDA_CHECK(cudaEventSynchronize(s.copied));
+    // an invalid byte in this batch?
+    if (d.h_invalid[f.slot] != ~0ull) {
+        const unsigned long long key = d.h_invalid[f.slot];
+        c->have_invalid = true;
+        c->inv_record = (key >> 32) + f.desc.row_begin;
+        c->inv_site = key & 0xffffffffull;
+        c->inv_byte = s.h_in[(key >> 32) * c->width + c->inv_site];
+        fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in streamed record %llu at site %llu",
+             c->inv_byte, (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
+    }
+    harvest_kernel_time(c, s);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.p_start, s.p_stop) == cudaSuccess) c->tm.pack_ms += ms;
+    c->tm.pairs += f.pairs;
+    c->tm.d2h_bytes += f.desc.n_results * c->elem_bytes();
+    f.desc.data = s.h_out;
+    c->s_queue.erase(c->s_queue.begin());
+    if (c->s_sink(c->s_user, &f.desc) != 0) fail(DG_ERR_SINK, "sink aborted the stream");
+}
+
+void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
+    if (c->streaming) fail(DG_ERR_STATE, "a stream session is already open");
+    if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
+    if (max_batch == 0) fail(DG_ERR_INVALID_ARG, "max_batch is 0");
+    for (auto& d : c->devs)
+        if (d.set[0].n == 0) fail(DG_ERR_STATE, "alignment 0 is not loaded");
+    const uint64_t n_res = c->devs[0].set[0].n;
+    // keep one batch's results within the panel budget
+    const uint64_t cap_rows = std::max<uint64_t>(1, c->panel_bytes / (c->elem_bytes() * n_res));
+    const TileShape ts = tile_shape(c->fam, c->tile_variant);
+    uint64_t mb = std::min(max_batch, std::max<uint64_t>(cap_rows / ts.tm * ts.tm, ts.tm));
+    c->s_max_batch = mb;
+    for (auto& d : c->devs) {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
+        if (d.in_cap < mb) {
+            for (auto& s : d.slot) {
+                if (s.h_in) cudaFreeHost(s.h_in);
+                if (s.d_in) cudaFree(s.d_in);
+                if (s.h_acgt) cudaFreeHost(s.h_acgt);
+                free_set(s.batch);
+                s.h_in = s.d_in = nullptr; s.h_acgt = nullptr;
+                CUDA_CHECK(cudaHostAlloc(&s.h_in, (size_t)mb * c->width, cudaHostAllocDefault));
+                CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)mb * c->width));
+                CUDA_CHECK(cudaHostAlloc(&s.h_acgt, (size_t)mb * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+                alloc_set(c, s.batch, mb, false);
+            }
+            d.in_cap = mb;
+        }
+    }
+    c->streaming = true;
+    c->s_sink = sink;
+    c->s_user = user;
+    c->s_rows_pushed = 0;
+    c->s_batches = 0;
+    c->s_queue.clear();
+    c->s_t0 = wall_ms();
+}
+
+void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kind, const uint64_t* acgt) {
+    const int ndev = (int)c->devs.size();
+    // the ring slot of this batch must have been sunk: keep at most 2*ndev batches in flight
+    while ((int)c->s_queue.size() >= 2 * ndev) stream_sink_front(c);
+    const uint64_t bi = c->s_batches++;
+    Device& d = c->devs[bi % ndev];
+    const int si = (int)((bi / ndev) & 1);
+    Slot& s = d.slot[si];
+    CUDA_CHECK(cudaSetDevice(d.id));
+    const double th = wall_ms();
+    std::memcpy(s.h_in, codes, (size_t)nb * c->width);
+    const bool host_counts = acgt != nullptr && c->fam == FAM_TN93;
+    if (host_counts)
+        for (uint64_t i = 0; i < nb * 4; i++) s.h_acgt[i] = (uint32_t)acgt[i];
+    CUDA_CHECK(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)nb * c->width, cudaMemcpyHostToDevice, d.copy_in));
+    if (host_counts)
+        CUDA_CHECK(cudaMemcpyAsync(s.batch.acgt, s.h_acgt, (size_t)nb * 4 * sizeof(uint32_t),
+                                   cudaMemcpyHostToDevice, d.copy_in));
+    CUDA_CHECK(cudaEventRecord(s.in_ready, d.copy_in));
+    c->tm.h2d_ms += wall_ms() - th;
+    c->tm.h2d_bytes += nb * c->width;
+    cudaStream_t cst = d.cs(si);
+    CUDA_CHECK(cudaStreamWaitEvent(cst, s.in_ready, 0));
+    s.batch.n = nb;
+    CUDA_CHECK(cudaEventRecord(s.p_start, cst));
+    // fastaio.rs:250-254: the streamed tn93 records count raw upper-case chars only (:139-142)
+    enqueue_pack(c, d.d_invalid + si, s.batch, s.d_in, nb, input_kind, !host_counts, input_kind == DG_INPUT_ASCII, cst);
+    CUDA_CHECK(cudaEventRecord(s.p_stop, cst));
+    Panel p;
+    p.row0 = 0; p.row1 = nb; p.out_base = 0;
+    p.n_results = nb * d.set[0].n;
+    CUDA_CHECK(cudaEventRecord(s.k_start, cst));
+    enqueue_panel_kernel<false>(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, true, cst);
+    CUDA_CHECK(cudaEventRecord(s.k_stop, cst));
+    CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(),
+                               cudaMemcpyDeviceToHost, d.copy));
+    CUDA_CHECK(cudaMemcpyAsync(d.h_invalid + si, d.d_invalid + si, sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, d.copy));
+    CUDA_CHECK(cudaEventRecord(s.copied, d.copy));
+    InFlight f;
+    f.dev = (int)(bi % ndev);
+    f.slot = si;
+    f.pairs = p.n_results;
+    f.desc.mode = DG_MODE_STREAM;
+    f.desc.result_kind = c->result_kind();
+    f.desc.row_begin = c->s_rows_pushed;
+    f.desc.row_end = c->s_rows_pushed + nb;
+    f.desc.n_cols = d.set[0].n;
+    f.desc.n_results = p.n_results;
+    c->s_queue.push_back(f);
+    c->s_rows_pushed += nb;
+}
+
+void stream_abort(dg_ctx* c) {
+    for (auto& d : c->devs) {
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        cudaMemset(d.d_invalid, 0xff, 3 * sizeof(unsigned long long));
+        for (int i = 0; i < 3; i++) d.h_invalid[i] = ~0ull;
+    }
+    c->s_queue.clear();
+    c->streaming = false;
+}
+
+template <typename F>
+int guarded(dg_ctx* c, F&& f) {
+    if (!c) return DG_ERR_INVALID_ARG;
+    try {
+        f();
+        return DG_OK;
+    } catch (const DgError& e) {
+        c->err = e.msg;
+        return e.code;
+    } catch (const std::exception& e) {
+        c->err = e.what();
+        return DG_ERR_NOMEM;
+    }
+}
+
+void destroy_device(Device& d) {
+    cudaSetDevice(d.id);
+    cudaDeviceSynchronize();
+    for (auto& s : d.set) free_set(s);
+    for (auto& s : d.slot) {
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.h_acgt) cudaFreeHost(s.h_acgt);
+        free_set(s.batch);
+        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop})
+            if (e) cudaEventDestroy(e);
+    }
+    if (d.run_start) cudaEventDestroy(d.run_start);
+    if (d.run_stop) cudaEventDestroy(d.run_stop);
+    if (d.d_invalid) cudaFree(d.d_invalid);
+    if (d.h_invalid) cudaFreeHost(d.h_invalid);
+    if (d.compute) cudaStreamDestroy(d.compute);
+    if (d.compute2) cudaStreamDestroy(d.compute2);
+    if (d.copy) cudaStreamDestroy(d.copy);
+    if (d.copy_in) cudaStreamDestroy(d.copy_in);
+}
+
+void host_lut(uint8_t lut[256], uint32_t valid[8]) {
+    // encoding.rs:7-38
+    std::memset(lut, 0, 256);
+    const char* letters = "AGCTRMWSKYVHDBN";
+    const uint8_t codes[15] = {136, 72, 40, 24, 192, 160, 144, 96, 80, 48, 224, 176, 208, 112, 240};
+    for (int i = 0; i < 15; i++) {
+        lut[(uint8_t)letters[i]] = codes[i];
+        lut[(uint8_t)(letters[i] + 32)] = codes[i];
+    }
+    lut[(uint8_t)'-'] = 244;
+    lut[(uint8_t)'?'] = 242;
+    std::memset(valid, 0, 32);
+    for (int i = 0; i < 256; i++)
+        if (lut[i]) valid[lut[i] >> 5] |= 1u << (lut[i] & 31);
+}
+
+}  // namespace
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+extern "C" {
+
+int dg_abi_version(void) { return DG_ABI_VERSION; }
+
+int dg_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return DG_ERR_CUDA;
+    }
+    return n;
+}
+
+const char* dg_last_error(const dg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ctx** out) {
+    if (!out) { g_create_error = "out is NULL"; return DG_ERR_INVALID_ARG; }
+    *out = nullptr;
+    if (measure < 0 || measure > 5) { g_create_error = "unknown measure"; return DG_ERR_INVALID_ARG; }
+    if (width == 0 || width >= (1ull << 31)) { g_create_error = "width must be in [1, 2^31)"; return DG_ERR_INVALID_ARG; }
+    if (n_gpus < 1) { g_create_error = "n_gpus must be >= 1"; return DG_ERR_INVALID_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device available (this library has no CPU fallback)";
+        return DG_ERR_CUDA;
+    }
+    dg_ctx* c = new dg_ctx();
+    c->measure = measure;
+    c->fam = family_of(measure);
+    c->width = width;
+    c->wp = (uint32_t)(((width + 31) / 32 + KC - 1) / KC * KC);
+    int rc = DG_OK;
+    try {
+        uint8_t lut[256];
+        uint32_t valid[8];
+        host_lut(lut, valid);
+        for (int i = 0; i < n_gpus; i++) {
+            Device d;
+            d.id = gpu_ids ? gpu_ids[i] : i;
+            if (d.id < 0 || d.id >= ndev) fail(DG_ERR_INVALID_ARG, "GPU id %d out of range (have %d)", d.id, ndev);
+            CUDA_CHECK(cudaSetDevice(d.id));
+            cudaDeviceProp prop{};
+            CUDA_CHECK(cudaGetDeviceProperties(&prop, d.id));
+            if (prop.major != 10)
+                fail(DG_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", d.id, prop.major, prop.minor);
+            CUDA_CHECK(cudaStreamCreateWithFlags(&d.compute, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&d.compute2, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy_in, cudaStreamNonBlocking));
+            for (auto& s : d.slot)
+                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.in_ready, &s.p_start, &s.p_stop})
+                    CUDA_CHECK(cudaEventCreate(e));
+            CUDA_CHECK(cudaEventCreate(&d.run_start));
+            CUDA_CHECK(cudaEventCreate(&d.run_stop));
+            CUDA_CHECK(cudaMemcpyToSymbol(c_ascii_lut, lut, 256));
+            CUDA_CHECK(cudaMemcpyToSymbol(c_valid_code, valid, 32));
+            CUDA_CHECK(cudaMalloc(&d.d_invalid, 3 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaHostAlloc(&d.h_invalid, 3 * sizeof(unsigned long long), cudaHostAllocDefault));
+            for (int k = 0; k < 3; k++) d.h_invalid[k] = ~0ull;
+            CUDA_CHECK(cudaMemset(d.d_invalid, 0xff, 3 * sizeof(unsigned long long)));
+            c->devs.push_back(d);
+        }
+    } catch (const DgError& e) {
+        g_create_error = e.msg;
+        rc = e.code;
+    }
+    if (rc != DG_OK) {
+        for (auto& d : c->devs) destroy_device(d);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return DG_OK;
+}
+
+void dg_destroy(dg_ctx* ctx) {
+    if (!ctx) return;
+    for (auto& d : ctx->devs) destroy_device(d);
+    delete ctx;
+}
+
+int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
+    return guarded(ctx, [&] {
+        switch (key) {
+        case DG_OPT_PANEL_BYTES:
+            if (value < 4096) fail(DG_ERR_INVALID_ARG, "panel bytes too small");
+            ctx->panel_bytes = (size_t)value;
+            break;
+        case DG_OPT_KEEP_CODES: ctx->keep_codes = value != 0; break;
+        case DG_OPT_TILE_VARIANT: ctx->tile_variant = (int)value; break;
+        case DG_OPT_ENGINE:
+            if (value != 0 && value != 1) fail(DG_ERR_INVALID_ARG, "engine %lld is not built in this version", (long long)value);
+            ctx->engine = (int)value;
+            break;
+        default: fail(DG_ERR_INVALID_ARG, "unknown option %d", key);
+        }
+    });
+}
+
+int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, int input_kind,
+                     const uint64_t* acgt_counts) {
+    return guarded(ctx, [&] {
+        if (which < 0 || which > 1) fail(DG_ERR_INVALID_ARG, "which must be 0 or 1");
+        if (!codes || n == 0) fail(DG_ERR_INVALID_ARG, "empty alignment");
+        if (n >= (1ull << 31)) fail(DG_ERR_INVALID_ARG, "too many records");
+        if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+        if (ctx->streaming) fail(DG_ERR_STATE, "a stream session is open");
+        ctx->have_invalid = false;
+        std::vector<uint32_t> c32;
+        if (acgt_counts) {
+            c32.resize(n * 4);
+            for (uint64_t i = 0; i < n * 4; i++) c32[i] = (uint32_t)acgt_counts[i];
+        }
+        for (auto& d : ctx->devs) {
+            CUDA_CHECK(cudaSetDevice(d.id));
+            PlaneSet& s = d.set[which];
+            free_set(s);
+            alloc_set(ctx, s, n, true);
+            s.input_kind = input_kind;
+            s.acgt_from_host = acgt_counts != nullptr;
+            const double th = wall_ms();
+            CUDA_CHECK(cudaMemcpyAsync(s.codes, codes, (size_t)n * ctx->width, cudaMemcpyHostToDevice, d.compute));
+            CUDA_CHECK(cudaStreamSynchronize(d.compute));
+            ctx->tm.h2d_ms += wall_ms() - th;
+            ctx->tm.h2d_bytes += n * ctx->width;
+            CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
+            enqueue_pack(ctx, d.d_invalid + 2, s, s.codes, n, input_kind, acgt_counts == nullptr, false, d.compute);
+            CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
+            if (acgt_counts) {
+                CUDA_CHECK(cudaMemsetAsync(s.acgt, 0, (size_t)s.n_pad * 16, d.compute));
+                CUDA_CHECK(cudaMemcpyAsync(s.acgt, c32.data(), (size_t)n * 16, cudaMemcpyHostToDevice, d.compute));
+            }
+            CUDA_CHECK(cudaStreamSynchronize(d.compute));
+            float ms = 0;
+            CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
+            ctx->tm.pack_ms += ms;
+            if (!ctx->keep_codes) { cudaFree(s.codes); s.codes = nullptr; }
+            try {
+                check_invalid(ctx, d, codes, 0);
+            } catch (...) {
+                free_set(s);
+                throw;
+            }
+        }
+    });
+}
+
+int dg_invalid_site(const dg_ctx* ctx, uint64_t* record, uint64_t* site, uint8_t* byte) {
+    if (!ctx || !ctx->have_invalid) return DG_ERR_STATE;
+    if (record) *record = ctx->inv_record;
+    if (site) *site = ctx->inv_site;
+    if (byte) *byte = ctx->inv_byte;
+    return DG_OK;
+}
+
+int dg_run_square(dg_ctx* ctx, dg_sink_fn sink, void* user, uint32_t flags) {
+    return guarded(ctx, [&] { run_mode(ctx, DG_MODE_SQUARE, 0, 1, sink, user, flags); });
+}
+
+int dg_run_rect(dg_ctx* ctx, dg_sink_fn sink, void* user, uint32_t flags) {
+    return guarded(ctx, [&] { run_mode(ctx, DG_MODE_RECT, 0, 1, sink, user, flags); });
+}
+
+int dg_run_part(dg_ctx* ctx, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user,
+                uint32_t flags) {
+    return guarded(ctx, [&] {
+        if (mode != DG_MODE_SQUARE && mode != DG_MODE_RECT) fail(DG_ERR_INVALID_ARG, "mode must be SQUARE or RECT");
+        run_mode(ctx, mode, part, n_parts, sink, user, flags);
+    });
+}
+
+int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n_cols, uint64_t panel_bytes,
+                       int tile_variant, uint64_t* row_begin, uint64_t* row_end, uint64_t* n_results,
+                       uint64_t cap) {
+    if (measure < 0 || measure > 5 || (mode != DG_MODE_SQUARE && mode != DG_MODE_RECT) || panel_bytes < 4096)
+        return DG_ERR_INVALID_ARG;
+    const TileShape ts = tile_shape(family_of(measure), tile_variant);
+    const std::vector<Panel> v = make_panels(panel_bytes, measure <= 1 ? 4 : 8, mode, n_rows,
+                                             mode == DG_MODE_SQUARE ? n_rows : n_cols, ts.tm);
+    for (size_t k = 0; k < v.size() && k < cap; k++) {
+        if (row_begin) row_begin[k] = v[k].row0;
+        if (row_end) row_end[k] = v[k].row1;
+        if (n_results) n_results[k] = v[k].n_results;
+    }
+    return (int64_t)v.size();
+}
+
+int dg_stream_begin(dg_ctx* ctx, dg_sink_fn sink, void* user, uint64_t max_batch) {
+    return guarded(ctx, [&] { stream_begin(ctx, sink, user, max_batch); });
+}
+
+int dg_stream_push(dg_ctx* ctx, const uint8_t* codes, uint64_t n_batch, int input_kind,
+                   const uint64_t* acgt_counts) {
+    int rc = guarded(ctx, [&] {
+        if (!ctx->streaming) fail(DG_ERR_STATE, "no stream session is open");
+        if (!codes && n_batch) fail(DG_ERR_INVALID_ARG, "codes is NULL");
+        if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+        for (uint64_t off = 0; off < n_batch; off += ctx->s_max_batch) {
+            const uint64_t nb = std::min(ctx->s_max_batch, n_batch - off);
+            stream_push_one(ctx, codes + off * ctx->width, nb, input_kind,
+                            acgt_counts ? acgt_counts + off * 4 : nullptr);
+        }
+    });
+    if (rc != DG_OK && ctx && ctx->streaming) stream_abort(ctx);
+    return rc;
+}
+
+int dg_stream_end(dg_ctx* ctx) {
+    int rc = guarded(ctx, [&] {
+        if (!ctx->streaming) fail(DG_ERR_STATE, "no stream session is open");
+        while (!ctx->s_queue.empty()) stream_sink_front(ctx);
+        ctx->streaming = false;
+        ctx->tm.total_ms = wall_ms() - ctx->s_t0;
+    });
+    if (rc != DG_OK && ctx && ctx->streaming) stream_abort(ctx);
+    return rc;
+}
+
+int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
+    return guarded(ctx, [&] {
+        if (which_a < 0 || which_a > 1 || which_b < 0 || which_b > 1 || !out) fail(DG_ERR_INVALID_ARG, "bad arguments");
+        Device& d = ctx->devs[0];
+        CUDA_CHECK(cudaSetDevice(d.id));
+        const PlaneSet& A = d.set[which_a];
+        const PlaneSet& B = d.set[which_b];
+        if (A.n == 0 || B.n == 0) fail(DG_ERR_STATE, "alignment not loaded");
+        const size_t bytes = (size_t)A.n * B.n * 16;
+        uint4* dbuf = nullptr;
+        CUDA_CHECK(cudaMalloc(&dbuf, bytes));
+        try {
+            Panel p;
+            p.row0 = 0; p.row1 = A.n; p.out_base = 0; p.n_results = A.n * B.n;
+            // tall alignments: split into launches of <= 65535 row blocks
+            const TileShape ts = tile_shape(ctx->fam, ctx->tile_variant);
+            const uint64_t step = (uint64_t)ts.tm * 32768;
+            for (uint64_t r = 0; r < A.n; r += step) {
+                Panel q = p;
+                q.row0 = r; q.row1 = std::min<uint64_t>(A.n, r + step);
+                enqueue_panel_kernel<true>(ctx, d, A, B, DG_MODE_RECT, q, dbuf + r * B.n, false, d.compute);
+            }
+            CUDA_CHECK(cudaStreamSynchronize(d.compute));
+            CUDA_CHECK(cudaMemcpy(out, dbuf, bytes, cudaMemcpyDeviceToHost));
+        } catch (...) {
+            cudaFree(dbuf);
+            throw;
+        }
+        cudaFree(dbuf);
+    });
+}
+
+int dg_debug_planes(dg_ctx* ctx, int which, uint32_t* core, uint32_t* aux, uint64_t* acgt, uint64_t* words_out) {
+    return guarded(ctx, [&] {
+        if (which < 0 || which > 1) fail(DG_ERR_INVALID_ARG, "which must be 0 or 1");
+        Device& d = ctx->devs[0];
+        CUDA_CHECK(cudaSetDevice(d.id));
+        const PlaneSet& s = d.set[which];
+        if (s.n == 0) fail(DG_ERR_STATE, "alignment not loaded");
+        if (words_out) *words_out = ctx->wp;
+        const size_t bytes = (size_t)s.n * ctx->wp * 16;
+        if (core) CUDA_CHECK(cudaMemcpy(core, s.core, bytes, cudaMemcpyDeviceToHost));
+        if (aux) {
+            if (!s.aux) fail(DG_ERR_STATE, "this measure family keeps no aux planes");
+            CUDA_CHECK(cudaMemcpy(aux, s.aux, bytes, cudaMemcpyDeviceToHost));
+        }
+        if (acgt) {
+            std::vector<uint32_t> tmp(s.n * 4);
+            CUDA_CHECK(cudaMemcpy(tmp.data(), s.acgt, tmp.size() * 4, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < tmp.size(); i++) acgt[i] = tmp[i];
+        }
+    });
+}
+
+int dg_get_timings(const dg_ctx* ctx, dg_timings* out) {
+    if (!ctx || !out) return DG_ERR_INVALID_ARG;
+    *out = ctx->tm;
+    return DG_OK;
+}
+
+int dg_reset_timings(dg_ctx* ctx) {
+    if (!ctx) return DG_ERR_INVALID_ARG;
+    ctx->tm = dg_timings{};
+    return DG_OK;
+}
+
+void* dg_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void dg_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""CPU-side checks (no GPU, no compute calls): the C-ABI library loads and exports every symbol the
+header declares, refuses to run without a device, and the panel plan shards a run completely."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from distance_b200 import api as a
+    a.build_library()
+    a.load_library()
+    return a
+
+
+def test_header_symbols_are_exported(api):
+    hdr = open(os.path.join(ROOT, "include", "distance_gpu.h")).read()
+    declared = sorted(set(re.findall(r"DG_API[^;(]*?\b(dg_[a-z0-9_]+)\s*\(", hdr)))
+    assert declared == sorted(api.ABI_SYMBOLS)
+    lib = api.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.dg_abi_version() == 1
+
+
+def test_no_cpu_fallback(api):
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.DistanceGpuError) as ei:
+        api.Engine("raw", 100)
+    assert ei.value.code == -2 and "no CPU fallback" in ei.value.msg
+
+
+def test_product_does_not_touch_the_oracle():
+    """Nothing under distance_b200/ may import, link or load anything under oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "distance_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "liboracle" not in txt and "distance_oracle" not in txt, f
+                assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+@pytest.mark.parametrize("measure,mode,n_rows,n_cols", [
+    ("n_high", 0, 20000, 20000), ("jc69", 0, 100000, 100000), ("tn93", 1, 10000, 10000),
+    ("raw", 0, 1000, 1000), ("k80", 0, 2, 2), ("raw", 0, 1, 1), ("n", 1, 3, 70000)])
+def test_plan_covers_every_pair_once(api, measure, mode, n_rows, n_cols):
+    plan = api.plan_panels(measure, mode, n_rows, n_cols)
+    total = n_rows * (n_rows - 1) // 2 if mode == 0 else n_rows * n_cols
+    assert sum(p[2] for p in plan) == total
+    rows = n_rows - 1 if mode == 0 else n_rows
+    if total:
+        assert plan[0][0] == 0 and plan[-1][1] == rows
+        assert all(plan[k][1] == plan[k + 1][0] for k in range(len(plan) - 1))
+    else:
+        assert plan == []
+    for rb, re_, nr in plan:
+        want = sum(n_rows - 1 - i for i in range(rb, re_)) if mode == 0 else (re_ - rb) * n_cols
+        assert nr == want
+
+
+def _rank_main(rank, world, port, q):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank),
+                      MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    from distance_b200 import api, dist
+    d = dist.Dist(backend="gloo")
+    plan = api.plan_panels("n_high", 0, 20000, 20000, panel_bytes=16 << 20)
+    mine = dist.my_panels(plan, d.rank, d.world)
+    d.barrier()
+    pairs = d.sum(sum(p[2] for p in mine))
+    slowest = d.max(10.0 * (rank + 1))
+    q.put((rank, len(mine), pairs, slowest))
+    d.close()
+
+
+def test_two_rank_sharding_over_gloo(api):
+    """world_size 2 over gloo: ranks take disjoint panels (no data-path collective); the bench
+    protocol's SUM of pairs equals the whole triangle and MAX picks the slowest rank."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 300
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    total = 20000 * 19999 // 2
+    assert out[0][2] == total and out[1][2] == total
+    assert out[0][3] == 20.0 and out[1][3] == 20.0
+    n_panels = len(api.plan_panels("n_high", 0, 20000, 20000, panel_bytes=16 << 20))
+    assert out[0][1] + out[1][1] == n_panels and abs(out[0][1] - out[1][1]) <= 1
