@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, no GPU needed) into the few numbers the roofline uses.
+usage: ncu_summary.py <report.ncu-rep> [kernel-regex]   -> markdown on stdout"""
+import csv, io, re, subprocess, sys
+
+rep = sys.argv[1]
+pat = re.compile(sys.argv[2]) if len(sys.argv) > 2 else None
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, data = rows[0], rows[1], rows[2:]
+col = {k: i for i, k in enumerate(hdr)}
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("launch__grid_size", "grid"), ("launch__registers_per_thread", "regs/thread"),
+    ("launch__waves_per_multiprocessor", "waves/SM"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe % (LOP3)"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe % (POPC)"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % (IMAD.IADD)"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue slots busy %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+    ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+    ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall short_scoreboard"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall wait"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall long_scoreboard"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+]
+name_col = col.get("Kernel Name", 4)
+print(f"# ncu summary of `{rep.split('/')[-1]}`\n")
+for r in data:
+    name = r[name_col]
+    if pat and not pat.search(name):
+        continue
+    print(f"## {name[:110]}\n")
+    print("| metric | value | unit |\n|---|---|---|")
+    for k, label in KEYS:
+        if k in col and r[col[k]] not in ("", "n/a"):
+            print(f"| {label} (`{k}`) | {r[col[k]]} | {units[col[k]]} |")
+    print()
