@@ -230,19 +230,34 @@ def run_ours(args):
     run_ms_step = dev_ms / args.steps
     peaks = load_json(os.path.join(ROOT, "profiles", "int_peaks.json")) or {}
     measured = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json")) or {}
+    achieved = ops / (run_ms_step * 1e-3) / 1e12
+    ops_per_word = OPS_PER_PAIR_SITE[MEASURE] * 32
     if "lop3_lane_ops_per_s" in peaks:
-        peak, peak_src = peaks["lop3_lane_ops_per_s"] / 1e12, "measured: tools/ubench_int LOP3 (profiles/int_peaks.json)"
+        # Issue ceiling of this instruction mix from the MEASURED per-pipe peaks: LOP3 issues on the ALU
+        # pipe, POPC on the XU pipe, the accumulate (IMAD.IADD) on the FMA pipe; the slowest pipe bounds
+        # the word-pair rate, and peak = that rate x the algorithmic ops per word.
+        mix = peaks["per_word"][MEASURE]
+        words_per_s = min(peaks["lop3_lane_ops_per_s"] / mix["lop3"], peaks["popc_lane_ops_per_s"] / mix["popc"],
+                          peaks["imad_lane_ops_per_s"] / mix["iadd"])
+        peak = words_per_s * ops_per_word / 1e12
+        peak_src = ("measured (tools/ubench_int, profiles/int_peaks.json): min over pipes of "
+                    "LOP3 1.85e13/4, POPC 4.39e12/1, IMAD 3.68e13/1 word-pairs/s x 6 algorithmic ops/word")
+        frac_lop3 = achieved * 1e12 / peaks["lop3_lane_ops_per_s"]
     else:
         mhz = clocks.get("sm_mhz") or measured.get("sm_max_mhz", 1965.0)
-        peak, peak_src = 64 * 148 * mhz * 1e6 / 1e12, f"nominal 64 lanes/clk/SM x 148 SM x {mhz:.0f} MHz (no measured int peak yet)"
-    achieved = ops / (run_ms_step * 1e-3) / 1e12
+        peak = 16 * 148 * mhz * 1e6 * ops_per_word / 1e12
+        peak_src = f"nominal 16 word-pairs/clk/SM x 148 SM x {mhz:.0f} MHz (no measured int peaks file)"
+        frac_lop3 = achieved / (64 * 148 * mhz * 1e6 / 1e12)
     roofline = {
-        "bound": "int_alu", "kernel": "count_tile_kernel<FAM_SNP>", "achieved": achieved, "peak": peak,
-        "unit": "Tlaneop/s", "frac": achieved / peak, "traffic": (peaks.get("count_kernel_dram_bytes_per_launch")),
+        "bound": "int_issue", "kernel": "count_tile_kernel<FAM_SNP>", "achieved": achieved, "peak": peak,
+        "unit": "Tlaneop/s", "frac": achieved / peak, "traffic": peaks.get("count_kernel_dram_bytes_per_launch"),
         "ops_per_pair_site": OPS_PER_PAIR_SITE[MEASURE], "peak_source": peak_src,
+        "frac_vs_lop3_peak_alone": frac_lop3,
+        "word_pairs_per_clk_per_sm": my_pairs * math.ceil(WIDTH / 32) / (run_ms_step * 1e-3) / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e6),
         "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
-        "note": "the path is integer-issue bound, not HBM/tensor bound (SURVEY 8d); launches of consecutive "
-                "panels overlap on two streams, so achieved uses the device time of the whole step",
+        "note": "integer-issue bound (LOP3 on the ALU pipe and POPC on the XU pipe saturate together), not HBM or "
+                "tensor bound (SURVEY 8d); consecutive panel launches overlap on two streams, so achieved uses "
+                "the device time of the whole step; traffic = DRAM bytes of one profiled launch (see profiles/)",
     }
     hbm = measured.get("hbm_gbs")
     pack_ms_step = tm["pack_ms"] / args.steps

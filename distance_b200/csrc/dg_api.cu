@@ -53,7 +53,7 @@ struct TileShape { int tm, tn; };
 
 TileShape tile_shape(int fam, int variant) {
     switch (fam) {
-    case FAM_SNP:  return variant == 1 ? TileShape{128, 64} : TileShape{128, 128};
+    case FAM_SNP:  return variant == 1 ? TileShape{128, 128} : TileShape{128, 64};
     case FAM_RAW:  return variant == 1 ? TileShape{64, 64} : TileShape{64, 128};
     default:       return TileShape{64, 64};
     }
@@ -72,8 +72,8 @@ template <bool COUNTS>
 void launch_count(int fam, int variant, const CountParams& p, dim3 grid, cudaStream_t s) {
     switch (fam) {
     case FAM_SNP:
-        if (variant == 1) launch_tile<FAM_SNP, 8, 4, COUNTS, 2>(p, grid, s);
-        else launch_tile<FAM_SNP, 8, 8, COUNTS, 2>(p, grid, s);
+        if (variant == 1) launch_tile<FAM_SNP, 8, 8, COUNTS, 2>(p, grid, s);
+        else launch_tile<FAM_SNP, 8, 4, COUNTS, 2>(p, grid, s);  // measured faster on B200 (profiles/)
         break;
     case FAM_RAW:
         if (variant == 1) launch_tile<FAM_RAW, 4, 4, COUNTS, 2>(p, grid, s);
