@@ -7,7 +7,7 @@ LIBDIR := distance_b200/_lib
 LIB := $(LIBDIR)/libdistance_gpu.so
 CSRC := distance_b200/csrc
 
-all: lib oracle
+all: lib cli oracle
 
 lib: $(LIB)
 
@@ -15,10 +15,23 @@ $(LIB): $(CSRC)/dg_api.cu $(CSRC)/kernels.cuh include/distance_gpu.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) $(PTXAS_V) -shared -o $@ $(CSRC)/dg_api.cu
 
+# The `distance` command line (C++ host over the C ABI; the image has no Rust toolchain).
+CXX ?= g++
+BINDIR := distance_b200/_bin
+CLI := $(BINDIR)/distance
+HOST := $(CSRC)/host
+
+cli: $(CLI)
+
+$(CLI): $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp $(HOST)/fasta.hpp $(HOST)/tsv.hpp include/distance_gpu.h $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CXX) -O2 -std=c++17 -Wall -Wextra -pthread -o $@ $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp \
+		-L$(LIBDIR) -ldistance_gpu -Wl,-rpath,'$$ORIGIN/../_lib'
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -rf $(LIBDIR) && $(MAKE) -C oracle clean
+	rm -rf $(LIBDIR) $(BINDIR) && $(MAKE) -C oracle clean
 
-.PHONY: all lib oracle clean
+.PHONY: all lib cli oracle clean

@@ -1,0 +1,74 @@
+// fasta.hpp -- FASTA tokeniser + record validation for the `distance` host.
+//
+// Replaces fastaio.rs:174-286 (load_fasta / load_fastas / stream_fasta) and the part of rust-bio's
+// bio::io::fasta::Reader (bio 1.6.0, Cargo.lock:216-217; source not in /root/reference) that those
+// call.  rust-bio semantics restated from its published behaviour:
+//   * a record starts at a line beginning with '>'; anything else where a header is expected is the
+//     io error "Expected > at record start."
+//   * id = header text after '>' up to the first whitespace, desc = the rest (trailing whitespace cut)
+//   * seq = the following lines up to the next '>' line or EOF, each with trailing whitespace (incl.
+//     '\r') removed and concatenated; blank lines inside a record are skipped by that rule
+//   * iteration ends at EOF or at a completely empty record
+// The reference's own tests only pin two-line, LF, upper-case records (fastaio.rs:344-350,
+// lib.rs:906-914); multi-line / CRLF behaviour is "parity unpinned" (SURVEY.md 8c).
+//
+// Sequence bytes are validated against the table of encoding.rs:4-41 while they are copied, so the
+// reference's error order is kept (fastaio.rs:111-113 before :188-190 when loading; :246-248 before
+// :250-254 when streaming).  The bytes stay ASCII: the LUT itself runs on the device
+// (DG_INPUT_ASCII), which also reproduces the stream-mode tn93 upper-case count quirk
+// (fastaio.rs:139-142).
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace host {
+
+// Mirrors DistanceError (lib.rs:21-39) as far as the process exit text goes: main prints
+// `Error: <Debug of the variant>` and exits 1 (main.rs:4-15).
+struct DistanceError : std::runtime_error {
+    explicit DistanceError(const std::string& debug_text) : std::runtime_error(debug_text) {}
+};
+DistanceError message_error(const std::string& msg);            // Message("...")
+DistanceError io_error_custom(const std::string& msg);          // IOError(Custom { kind: Other, error: "..." })
+DistanceError io_error_os(int err);                             // IOError(Os { code, kind, message })
+
+struct Alignment {
+    std::vector<std::string> ids;
+    std::vector<uint8_t> seqs;  // n x width raw ASCII bytes (validated)
+    uint64_t width = 0;
+    uint64_t n() const { return ids.size(); }
+};
+
+class FastaReader {
+public:
+    // validate = false: bytes are copied unchecked (stream mode checks the width first, fastaio.rs:246-254)
+    explicit FastaReader(int fd, bool validate = true);
+    // Reads the next record: id into `id`, sequence bytes APPENDED to `seq`.  Returns false at the
+    // end of the input.  Throws DistanceError on malformed input or an invalid nucleotide.
+    bool next(std::string& id, std::vector<uint8_t>& seq);
+
+private:
+    bool read_line();  // fills line_ (without the '\n'); false at EOF with nothing read
+    bool fill();
+    int fd_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, end_ = 0;
+    bool eof_ = false;
+    std::string line_;
+    bool have_line_ = false;
+    bool validate_ = true;
+};
+
+// load_fasta (fastaio.rs:174-200)
+Alignment load_fasta(int fd);
+// the cross-file width check of load_fastas (fastaio.rs:202-212)
+void check_same_width(const Alignment& a, const Alignment& b);
+
+bool valid_nucleotide(uint8_t c);
+// Throws the Message error of fastaio.rs:89-91 for the first invalid byte of seq[0..len), if any.
+void validate_record(const std::string& id, const uint8_t* seq, uint64_t len);
+
+}  // namespace host

@@ -1,0 +1,348 @@
+// main.cpp -- the `distance` command line on top of libdistance_gpu (C ABI, include/distance_gpu.h).
+//
+// Same flags, defaults, mutual-exclusion rules, output text and exit codes as the reference CLI
+// (lib.rs:68-131 get_cli_arguments, lib.rs:162-267 set_up, lib.rs:490-498 run, main.rs:4-16); the
+// pairwise work between "records are parsed" and "ordered results reach the writer" goes to the GPU
+// through dg_load_resident / dg_run_square / dg_run_rect / dg_stream_*.  The host is C++ because the
+// build image has no Rust toolchain; INTEGRATION.md shows the Rust binding of the same ABI.
+//
+//   -t  = threads formatting TSV text (the reference's worker count; results never depended on it)
+//   -b  = accepted and validated, otherwise unused (the reference's pair batch size)
+//   DISTANCE_GPUS=<k> or DISTANCE_GPUS=0,2,3 chooses the devices (default: device 0); there is no flag
+//   for it so the CLI surface stays the reference's.
+#include <cerrno>
+#include <csignal>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fcntl.h>
+#include <string>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+#include "../../../include/distance_gpu.h"
+#include "fasta.hpp"
+#include "tsv.hpp"
+
+using namespace host;
+
+namespace {
+
+const char* kVersion = "0.3.1";  // Cargo.toml:3
+const char* kMeasures[] = {"n", "n_high", "raw", "jc69", "k80", "tn93"};
+
+const char* kHelp =
+    "Calculate genetic distances within/between fasta-format alignments of DNA sequences\n"
+    "\n"
+    "Usage: All sequences across all input files must be the same length.\n"
+    "\n"
+    "       distance alignment.fasta\n"
+    "       cat alignment.fasta | distance\n"
+    "       distance alignment.fasta -o distances.tsv\n"
+    "       distance -t 8 -m jc69 alignment.fasta -o jc69.tsv\n"
+    "       distance alignment1.fasta alignment2.fasta > distances2.tsv\n"
+    "       distance -i smallAlignment.fasta -s bigAlignment.fasta -o distances3.tsv\n"
+    "       cat bigAlignment.fasta | distance smallAlignment.fasta -s - > distances3.tsv\n"
+    "\n"
+    "Options:\n"
+    "  -i, --input [<input>...]     One or two input alignment files in fasta format. Loaded into memory. This flag can be omitted and the files passed as positional arguments\n"
+    "  -s, --stream <stream>        One input alignment file in fasta format. Streamed from disk (or stdin using \"-s -\"). Requires exactly one file also be loaded\n"
+    "  -m, --measure <measure>      Which distance measure to use [default: raw] [possible values: n, n_high, raw, jc69, k80, tn93]\n"
+    "  -o, --output <output>        Output file in tab-separated-value format. Omit this option to print to stdout\n"
+    "  -t, --threads <threads>      How many threads to spin up for pairwise comparisons. Omitting this option spins up the number of available CPUs\n"
+    "  -b, --batchsize <batchsize>  Try setting this >(>) 1 to tune the workload per thread [default: 1]\n"
+    "  -l, --licenses               Print licence information and exit\n"
+    "  -h, --help                   Print help\n"
+    "  -V, --version                Print version\n";
+
+const char* kLicences =
+    "\ndistance (B200 host) follows the reference program's licensing: the reference `distance` is\n"
+    "Copyright 2022 Ben Jackson, GNU LIBRARY GENERAL PUBLIC LICENSE Version 2; its FASTA reading\n"
+    "derives from Rust-Bio (MIT licence, Copyright (c) 2016 Johannes Koester, the Rust-Bio team,\n"
+    "Google Inc.).  See the LICENSE file of the reference distribution for the full texts.\n";
+
+struct Args {
+    std::vector<std::string> flag_inputs, pos_inputs;
+    bool have_stream = false;
+    std::string stream;
+    std::string measure = "raw";
+    bool have_output = false;
+    std::string output;
+    bool have_threads = false;
+    uint64_t threads = 0;
+    uint64_t batchsize = 1;
+    bool licenses = false;
+};
+
+[[noreturn]] void clap_error(const std::string& msg) {  // clap prints to stderr and exits 2
+    fprintf(stderr, "error: %s\n\nFor more information, try '--help'.\n", msg.c_str());
+    std::exit(2);
+}
+
+bool parse_usize(const std::string& s, uint64_t* out) {
+    if (s.empty()) return false;
+    size_t i = 0;
+    if (s[0] == '+') i = 1;
+    if (i >= s.size()) return false;
+    uint64_t v = 0;
+    for (; i < s.size(); i++) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        const uint64_t nv = v * 10 + (uint64_t)(s[i] - '0');
+        if (nv < v) return false;
+        v = nv;
+    }
+    *out = v;
+    return true;
+}
+
+Args parse_args(int argc, char** argv) {
+    Args a;
+    bool only_positional = false;
+    for (int k = 1; k < argc; k++) {
+        std::string t = argv[k];
+        auto value = [&](const std::string& name, bool inline_ok, const std::string& inline_val) -> std::string {
+            if (inline_ok) return inline_val;
+            if (k + 1 >= argc) clap_error("a value is required for '" + name + "' but none was supplied");
+            return argv[++k];
+        };
+        if (only_positional || t == "-" || t.empty() || t[0] != '-') {
+            if (a.pos_inputs.size() >= 2) clap_error("unexpected argument '" + t + "' found");
+            a.pos_inputs.push_back(t);
+            continue;
+        }
+        if (t == "--") { only_positional = true; continue; }
+        std::string key = t, inl;
+        bool has_inl = false;
+        if (t.rfind("--", 0) == 0) {
+            const size_t eq = t.find('=');
+            if (eq != std::string::npos) { key = t.substr(0, eq); inl = t.substr(eq + 1); has_inl = true; }
+        } else if (t.size() > 2) {  // -m=jc69 / -mjc69
+            key = t.substr(0, 2);
+            inl = t.substr(t[2] == '=' ? 3 : 2);
+            has_inl = true;
+        }
+        if (key == "-h" || key == "--help") { fputs(kHelp, stdout); std::exit(0); }
+        if (key == "-V" || key == "--version") { printf("distance %s\n", kVersion); std::exit(0); }
+        if (key == "-l" || key == "--licenses") { a.licenses = true; continue; }
+        if (key == "-i" || key == "--input") {  // num_args(0..=2), lib.rs:89
+            if (has_inl) a.flag_inputs.push_back(inl);
+            while (a.flag_inputs.size() < 2 && k + 1 < argc && (argv[k + 1][0] != '-' || !strcmp(argv[k + 1], "-")))
+                a.flag_inputs.push_back(argv[++k]);
+            continue;
+        }
+        if (key == "-s" || key == "--stream") { a.stream = value("--stream <stream>", has_inl, inl); a.have_stream = true; continue; }
+        if (key == "-m" || key == "--measure") {
+            a.measure = value("--measure <measure>", has_inl, inl);
+            bool ok = false;
+            for (const char* m : kMeasures) ok |= a.measure == m;
+            if (!ok)
+                clap_error("invalid value '" + a.measure + "' for '--measure <measure>'\n  [possible values: n, n_high, raw, jc69, k80, tn93]");
+            continue;
+        }
+        if (key == "-o" || key == "--output") { a.output = value("--output <output>", has_inl, inl); a.have_output = true; continue; }
+        if (key == "-t" || key == "--threads") {
+            const std::string v = value("--threads <threads>", has_inl, inl);
+            if (!parse_usize(v, &a.threads)) clap_error("invalid value '" + v + "' for '--threads <threads>': invalid digit found in string");
+            a.have_threads = true;
+            continue;
+        }
+        if (key == "-b" || key == "--batchsize") {
+            const std::string v = value("--batchsize <batchsize>", has_inl, inl);
+            if (!parse_usize(v, &a.batchsize)) clap_error("invalid value '" + v + "' for '--batchsize <batchsize>': invalid digit found in string");
+            continue;
+        }
+        clap_error("unexpected argument '" + t + "' found");
+    }
+    return a;
+}
+
+int open_read(const std::string& path) {
+    int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw io_error_os(errno);  // File::open(path)? (lib.rs:193, 206)
+    return fd;
+}
+
+int measure_id(const std::string& m) {
+    for (int i = 0; i < 6; i++)
+        if (m == kMeasures[i]) return i;
+    return -1;
+}
+
+std::vector<int> gpu_list() {
+    std::vector<int> ids;
+    const char* e = std::getenv("DISTANCE_GPUS");
+    if (!e || !*e) return {0};
+    std::string s = e;
+    if (s.find(',') == std::string::npos) {
+        const int k = std::atoi(s.c_str());
+        for (int i = 0; i < std::max(1, k); i++) ids.push_back(i);
+        return ids;
+    }
+    size_t p = 0;
+    while (p <= s.size()) {
+        const size_t q = s.find(',', p);
+        const std::string tok = s.substr(p, q == std::string::npos ? std::string::npos : q - p);
+        if (!tok.empty()) ids.push_back(std::atoi(tok.c_str()));
+        if (q == std::string::npos) break;
+        p = q + 1;
+    }
+    return ids.empty() ? std::vector<int>{0} : ids;
+}
+
+struct SinkState {
+    TsvWriter* w;
+    std::string error;
+};
+
+int sink_cb(void* user, const dg_panel* p) {
+    SinkState* st = static_cast<SinkState*>(user);
+    try {
+        st->w->write_panel(*p);
+        return 0;
+    } catch (const DistanceError& e) {
+        st->error = e.what();
+        return 1;
+    }
+}
+
+void gpu_check(dg_ctx* ctx, int rc, SinkState* st = nullptr) {
+    if (rc == DG_OK) return;
+    if (rc == DG_ERR_SINK && st && !st->error.empty()) throw DistanceError(st->error);
+    throw message_error(std::string("GPU engine: ") + dg_last_error(ctx));
+}
+
+int run(const Args& a) {
+    // ---- set_up (lib.rs:162-267), same order of checks -------------------------------------------
+    if (!a.pos_inputs.empty() && !a.flag_inputs.empty())  // lib.rs:182-184
+        throw message_error("For loading input files, don't use both positional arguments and the -i/--input flag");
+    std::vector<std::string> inputs = a.flag_inputs;
+    inputs.insert(inputs.end(), a.pos_inputs.begin(), a.pos_inputs.end());
+    std::vector<int> fds;
+    if (inputs.empty()) fds.push_back(0);              // stdin, lib.rs:189-191
+    for (const auto& p : inputs) fds.push_back(open_read(p));
+    int stream_fd = -1;
+    if (a.have_stream) {
+        if (inputs.size() != 1)  // lib.rs:196-199
+            throw message_error("If you stream one file, you must also provide exactly one other file to be loaded");
+        stream_fd = a.stream == "-" ? 0 : open_read(a.stream);  // lib.rs:200-207
+    }
+    std::vector<Alignment> loaded;
+    for (size_t k = 0; k < fds.size(); k++) {
+        loaded.push_back(load_fasta(fds[k]));
+        if (k == 1) check_same_width(loaded[0], loaded[1]);
+        if (fds[k] != 0) ::close(fds[k]);
+    }
+    int out_fd = 1;
+    if (a.have_output) {
+        out_fd = ::open(a.output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);  // File::create, lib.rs:248-250
+        if (out_fd < 0) throw io_error_os(errno);
+    }
+    uint64_t threads = a.have_threads ? std::max<uint64_t>(1, a.threads)  // lib.rs:252-264
+                                      : std::max(1u, std::thread::hardware_concurrency());
+
+    // ---- run (lib.rs:490-498) ----------------------------------------------------------------------
+    const uint64_t width = loaded[0].width;
+    TsvWriter writer(out_fd, (int)std::min<uint64_t>(threads, 256));
+    SinkState st{&writer, {}};
+    const std::vector<int> gpus = gpu_list();
+    dg_ctx* ctx = nullptr;
+    int rc = dg_create(gpus.data(), (int)gpus.size(), measure_id(a.measure), width, &ctx);
+    if (rc != DG_OK) throw message_error(std::string("GPU engine: ") + dg_last_error(nullptr));
+    struct Guard { dg_ctx* c; ~Guard() { dg_destroy(c); } } guard{ctx};
+
+    for (size_t k = 0; k < loaded.size(); k++)
+        gpu_check(ctx, dg_load_resident(ctx, (int)k, loaded[k].seqs.data(), loaded[k].n(), DG_INPUT_ASCII, nullptr));
+
+    writer.write_header();  // gather_write writes the header before anything arrives (lib.rs:613)
+    if (stream_fd >= 0) {
+        // stream() (lib.rs:269-365) + stream_fasta (fastaio.rs:215-286)
+        std::vector<std::string> streamed_ids;
+        writer.set_ids(&loaded[0].ids, &streamed_ids);
+        const uint64_t batch = std::max<uint64_t>(64, std::min<uint64_t>(8192, (64ull << 20) / std::max<uint64_t>(1, width)));
+        gpu_check(ctx, dg_stream_begin(ctx, sink_cb, &st, batch), &st);
+        FastaReader rd(stream_fd, /*validate=*/false);
+        std::vector<uint8_t> buf;
+        buf.reserve(batch * width);
+        std::string id;
+        uint64_t in_batch = 0, records = 0;
+        for (;;) {
+            const size_t before = buf.size();
+            if (!rd.next(id, buf)) break;
+            records++;
+            const uint64_t len = buf.size() - before;
+            if (len != width)  // fastaio.rs:246-248
+                throw message_error("Different length sequences in alignment(s): " + std::to_string(len) + " vs " + std::to_string(width));
+            validate_record(id, buf.data() + before, len);  // fastaio.rs:250-254 -> :111-113
+            streamed_ids.push_back(id);
+            if (++in_batch == batch) {
+                gpu_check(ctx, dg_stream_push(ctx, buf.data(), in_batch, DG_INPUT_ASCII, nullptr), &st);
+                buf.clear();
+                in_batch = 0;
+            }
+        }
+        if (in_batch) gpu_check(ctx, dg_stream_push(ctx, buf.data(), in_batch, DG_INPUT_ASCII, nullptr), &st);
+        gpu_check(ctx, dg_stream_end(ctx), &st);
+        if (records == 0) throw message_error("Empty FASTA file");  // fastaio.rs:281-283 (after the header was written)
+    } else if (loaded.size() == 1) {
+        writer.set_ids(&loaded[0].ids, &loaded[0].ids);
+        gpu_check(ctx, dg_run_square(ctx, sink_cb, &st, 0), &st);
+    } else {
+        writer.set_ids(&loaded[0].ids, &loaded[1].ids);
+        gpu_check(ctx, dg_run_rect(ctx, sink_cb, &st, 0), &st);
+    }
+    writer.flush();
+    if (out_fd != 1) ::close(out_fd);
+    return 0;
+}
+
+}  // namespace
+
+// Hidden developer check (not part of the reference CLI): the exact `{:.12}` formatter against the C
+// library's exact %.12f on N pseudo-random doubles plus edge cases.  `distance --selftest-format N`.
+int selftest_format(uint64_t n) {
+    uint64_t x = 0x9E3779B97F4A7C15ull, bad = 0;
+    auto check = [&](double d) {
+        std::string got;
+        format_float12(d, got);
+        char want[512];
+        if (d != d) snprintf(want, sizeof want, "NaN");
+        else if (d == 1.0 / 0.0) snprintf(want, sizeof want, "inf");
+        else if (d == -1.0 / 0.0) snprintf(want, sizeof want, "-inf");
+        else snprintf(want, sizeof want, "%.12f", d);
+        if (got != want) { if (bad++ < 10) fprintf(stderr, "MISMATCH %a: got %s want %s\n", d, got.c_str(), want); }
+    };
+    const double edge[] = {0.0, -0.0, 0.5e-12, 1.5e-12, 2.5e-12, 0.9999999999995, 0.1333333333333333, 1.0, 123456.789,
+                           1e-300, 4.9e-324, 1e22, 2147483648.0, 0.0000000000005, 0.00000000000049999, 1.0 / 0.0, -1.0 / 0.0, 0.0 / 0.0};
+    for (double d : edge) { check(d); check(-d); }
+    for (uint64_t i = 0; i < n; i++) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        double d;
+        if (i % 3 == 0) {  // raw bit patterns: every exponent
+            uint64_t b = x; std::memcpy(&d, &b, 8);
+        } else if (i % 3 == 1) {  // distances: [0, 4)
+            d = (double)(x >> 11) / 9007199254740992.0 * 4.0;
+        } else {  // ties at the 12th place: k / 2^j
+            d = (double)(x >> 40) / (double)(1ull << (20 + (x & 31)));
+        }
+        check(d);
+    }
+    printf("selftest-format: %llu values, %llu mismatches\n", (unsigned long long)(n + 36), (unsigned long long)bad);
+    return bad ? 1 : 0;
+}
+
+int main(int argc, char** argv) {
+    std::signal(SIGPIPE, SIG_IGN);  // a closed pipe shows up as EPIPE -> exit 0 (lib.rs:598-608)
+    if (argc == 3 && !strcmp(argv[1], "--selftest-format")) return selftest_format(strtoull(argv[2], nullptr, 10));
+    const Args a = parse_args(argc, argv);
+    if (a.licenses) {  // main.rs:7-10
+        printf("%s\n", kLicences);
+        return 0;
+    }
+    try {
+        return run(a);
+    } catch (const DistanceError& e) {
+        fprintf(stderr, "Error: %s\n", e.what());  // Debug form of the returned Err (main.rs:4-15)
+        return 1;
+    }
+}
