@@ -338,3 +338,27 @@ def test_config2_full_size_properties(dg, oracle):
     for ii in (0, 64, 127):
         i = 100 + ii
         assert np.array_equal(got[off(i) + (15000 - i - 1): off(i) + (15100 - i - 1)], rect[:, ii])
+
+
+def test_multi_gpu_single_process_matches_oracle(dg, oracle):
+    """One process driving every visible device: planes replicated, panels dealt round-robin, the sink
+    still sees them in global order.  Skipped on a one-GPU box."""
+    from distance_b200 import api, synth
+    ndev = dg.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rng = np.random.default_rng(21)
+    n, width = 900, 700
+    codes = synth.random_codes(rng, n, width, p_ambig=0.1)
+    for measure in ("n_high", "tn93"):
+        want = oracle_run(oracle, measure, "square", codes)
+        with dg.Engine(measure, width, gpus=list(range(ndev))) as e:
+            e.set_option(api.DG_OPT_PANEL_BYTES, 128 * n * (4 if measure == "n_high" else 8))
+            e.load(0, codes)
+            got = e.run_square()
+            assert len(e.last_panels) >= 2 * ndev
+            check(measure, got, want)
+            loaded, streamed = codes[:40], codes[40:400]
+            e.load(0, loaded)
+            got = e.stream([streamed[i:i + 50] for i in range(0, 360, 50)], max_batch=64)
+        check(measure, got, oracle_run(oracle, measure, "stream", loaded, streamed))
