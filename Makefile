@@ -11,7 +11,7 @@ all: lib cli oracle
 
 lib: $(LIB)
 
-$(LIB): $(CSRC)/dg_api.cu $(CSRC)/kernels.cuh include/distance_gpu.h
+$(LIB): $(CSRC)/dg_api.cu $(CSRC)/kernels.cuh $(CSRC)/tc_engine.cuh include/distance_gpu.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) $(PTXAS_V) -shared -o $@ $(CSRC)/dg_api.cu
 

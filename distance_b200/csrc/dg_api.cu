@@ -5,11 +5,13 @@
 // No CPU fallback lives here: every compute entry point needs a CUDA device.
 #include "../../include/distance_gpu.h"
 #include "kernels.cuh"
+#include "tc_engine.cuh"
 
 #include <algorithm>
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -93,6 +95,12 @@ struct PlaneSet {  // one alignment packed on one device
     uint8_t* codes = nullptr;  // kept only with DG_OPT_KEEP_CODES
     int input_kind = 0;
     bool acgt_from_host = false;
+    // tcgen05 engine (DG_OPT_ENGINE = 2): int8 one-hot operand planes, N-like counts, partial-code index
+    int8_t* tc_ops = nullptr;
+    uint32_t* tc_nN = nullptr;
+    uint64_t tc_wp8 = 0;
+    tc::PpIndex pp;
+    CUtensorMap map_a{}, map_b{};  // box 128 rows / box 256 rows over tc_ops
 };
 
 struct Slot {  // one stage of the result ring (and of the stream-input ring)
@@ -168,6 +176,10 @@ struct dg_ctx {
 namespace {
 
 void free_set(PlaneSet& s) {
+    if (s.tc_ops) cudaFree(s.tc_ops);
+    if (s.tc_nN) cudaFree(s.tc_nN);
+    if (s.pp.entries) cudaFree(s.pp.entries);
+    if (s.pp.site_off) cudaFree(s.pp.site_off);
     if (s.core) cudaFree(s.core);
     if (s.aux) cudaFree(s.aux);
     if (s.acgt) cudaFree(s.acgt);
@@ -238,6 +250,124 @@ void ensure_out_ring(dg_ctx* c, Device& d, size_t bytes) {
         CUDA_CHECK(cudaHostAlloc(&s.h_out, bytes, cudaHostAllocDefault));
     }
     d.out_cap = bytes;
+}
+
+
+// ---- tcgen05 engine: host side ------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+        if (qres != cudaDriverEntryPointSuccess || !ptr) fail(DG_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D map over ops[n_pad][6 * wp8] bytes: box = 128 bytes (one swizzle atom of K) x `box_rows` records.
+void make_ops_map(CUtensorMap* map, void* base, uint64_t row_bytes, uint64_t rows, uint32_t box_rows) {
+    const cuuint64_t dims[2] = {row_bytes, rows};
+    const cuuint64_t strides[1] = {row_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::KB, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) fail(DG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+}
+
+// Build the int8 operand planes, the N-like counts and the partial-code index of one alignment.
+void build_tc_operands(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
+    const uint64_t wp8 = (c->width + tc::KB - 1) / tc::KB * tc::KB;
+    s.tc_wp8 = wp8;
+    const size_t ops_bytes = (size_t)s.n_pad * tc::NPLANES_STORED * wp8;
+    CUDA_CHECK(cudaMalloc(&s.tc_ops, ops_bytes));
+    CUDA_CHECK(cudaMalloc(&s.tc_nN, (size_t)s.n_pad * 4));
+    CUDA_CHECK(cudaMemsetAsync(s.tc_nN, 0, (size_t)s.n_pad * 4, st));
+    tc::PackI8Params pp{};
+    pp.codes = d_codes; pp.n = s.n; pp.n_pad = s.n_pad; pp.width = c->width; pp.wp8 = wp8;
+    pp.ops = s.tc_ops; pp.nN = s.tc_nN; pp.ascii = s.input_kind == DG_INPUT_ASCII;
+    const uint64_t total = s.n_pad * (wp8 / 16);
+    tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32), 256, 0, st>>>(pp);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.pack_launches++;
+    // inverted index of the partial ambiguity codes (counting sort by site)
+    uint32_t *cnt = nullptr, *cursor = nullptr;
+    double* d_work = nullptr;
+    CUDA_CHECK(cudaMalloc(&cnt, (size_t)c->width * 4));
+    CUDA_CHECK(cudaMalloc(&cursor, (size_t)c->width * 4));
+    CUDA_CHECK(cudaMalloc(&d_work, 8));
+    CUDA_CHECK(cudaMalloc(&s.pp.site_off, (size_t)(c->width + 1) * 4));
+    CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)c->width * 4, st));
+    const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
+    tc::pp_count_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, pp.ascii, cnt);
+    tc::pp_scan_kernel<<<1, 1024, 0, st>>>(cnt, c->width, s.pp.site_off, cursor, d_work);
+    CUDA_CHECK(cudaGetLastError());
+    uint32_t total_entries = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&total_entries, s.pp.site_off + c->width, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&s.pp.pair_work, d_work, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    s.pp.n_entries = total_entries;
+    CUDA_CHECK(cudaMalloc(&s.pp.entries, (size_t)std::max<uint32_t>(1, total_entries) * 8));
+    if (total_entries) {
+        tc::pp_fill_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, pp.ascii, cursor, s.pp.entries);
+        CUDA_CHECK(cudaGetLastError());
+    }
+    c->tm.pack_launches += 3;
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaFree(cnt); cudaFree(cursor); cudaFree(d_work);
+    const uint64_t row_bytes = (uint64_t)tc::NPLANES_STORED * wp8;
+    make_ops_map(&s.map_a, s.tc_ops, row_bytes, s.n_pad, tc::TM);
+    make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, tc::TN);
+}
+
+int g_num_sms(int dev) {
+    int v = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+}
+
+// tcgen05 variant of enqueue_panel_kernel (n / n_high): GEMM tiles, then the both-partial correction.
+void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
+                      void* d_out, cudaStream_t st) {
+    if (!A.tc_ops || !B.tc_ops) fail(DG_ERR_STATE, "tensor-engine operands were not built (set DG_OPT_ENGINE before loading)");
+    tc::TcParams tp{};
+    tp.a_nN = A.tc_nN; tp.b_nN = B.tc_nN;
+    tp.n_b = (uint32_t)B.n;
+    tp.row0 = (uint32_t)p.row0; tp.row_end = (uint32_t)p.row1;
+    tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
+    tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tc::TN) : 0;
+    tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
+    tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM - 1) / tc::TM);
+    tp.n_total = A.n; tp.out_base = p.out_base;
+    tp.out = static_cast<uint32_t*>(d_out);
+    tp.width = (uint32_t)c->width; tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
+    if (tp.gx == 0 || tp.gy == 0) return;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_snp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)tp.gx * tp.gy, (uint64_t)g_num_sms(d.id));
+    tc::tc_snp_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_b, tp);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.count_launches++;
+    if (A.pp.n_entries && B.pp.n_entries) {
+        tc::PpCorrParams cp{};
+        cp.a_entries = A.pp.entries; cp.a_n = A.pp.n_entries;
+        cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
+        cp.row0 = tp.row0; cp.row_end = tp.row_end; cp.n_b = tp.n_b; cp.square = tp.square;
+        cp.n_total = tp.n_total; cp.out_base = tp.out_base; cp.out = tp.out;
+        tc::pp_correct_kernel<<<(A.pp.n_entries + 255) / 256, 256, 0, st>>>(cp);
+        CUDA_CHECK(cudaGetLastError());
+        c->tm.count_launches++;
+    }
 }
 
 uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
@@ -385,7 +515,8 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
             CUDA_CHECK(cudaSetDevice(d.id));
             const Panel& p = mine[k];
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
-            enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
+            if (c->engine == 2) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, d.cs(si));
+            else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
             CUDA_CHECK(cudaEventRecord(s.k_stop, d.cs(si)));
             if (!device_only) {
                 CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
@@ -438,6 +569,7 @@ void stream_sink_front(dg_ctx* c) {
 
 void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     if (c->streaming) fail(DG_ERR_STATE, "a stream session is already open");
+    if (c->engine == 2) fail(DG_ERR_INVALID_ARG, "the tcgen05 engine does not cover -s streaming yet; use engine 0/1");
     if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
     if (max_batch == 0) fail(DG_ERR_INVALID_ARG, "max_batch is 0");
     for (auto& d : c->devs)
@@ -673,6 +805,10 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
         delete c;
         return rc;
     }
+    if (const char* e = std::getenv("DG_ENGINE")) {  // developer override: 1 = LOP3+POPC tiles, 2 = tcgen05 int8 GEMM
+        const int v = std::atoi(e);
+        if (v == 1 || (v == 2 && c->fam == FAM_SNP)) c->engine = v;
+    }
     *out = c;
     return DG_OK;
 }
@@ -693,7 +829,9 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
         case DG_OPT_KEEP_CODES: ctx->keep_codes = value != 0; break;
         case DG_OPT_TILE_VARIANT: ctx->tile_variant = (int)value; break;
         case DG_OPT_ENGINE:
-            if (value != 0 && value != 1) fail(DG_ERR_INVALID_ARG, "engine %lld is not built in this version", (long long)value);
+            if (value < 0 || value > 2) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
+            if (value == 2 && ctx->fam != FAM_SNP)
+                fail(DG_ERR_INVALID_ARG, "the tcgen05 engine currently covers n / n_high only");
             ctx->engine = (int)value;
             break;
         default: fail(DG_ERR_INVALID_ARG, "unknown option %d", key);
@@ -738,9 +876,15 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
             float ms = 0;
             CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
             ctx->tm.pack_ms += ms;
-            if (!ctx->keep_codes) { cudaFree(s.codes); s.codes = nullptr; }
             try {
                 check_invalid(ctx, d, codes, 0);
+                if (ctx->engine == 2) build_tc_operands(ctx, s, s.codes, d.compute);
+            } catch (...) {
+                free_set(s);
+                throw;
+            }
+            if (!ctx->keep_codes) { cudaFree(s.codes); s.codes = nullptr; }
+            try {
             } catch (...) {
                 free_set(s);
                 throw;

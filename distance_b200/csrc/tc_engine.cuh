@@ -1,0 +1,386 @@
+// tc_engine.cuh -- tcgen05 `kind::i8` one-hot GEMM variant of the count kernel (north_star item 2).
+//
+// The per-pair counts are a dense contraction over sites, so they can run on the 5th-gen tensor
+// cores with exact int32 accumulation in TMEM.  Operand planes are int8, K-major:
+//
+//   ops[record][plane][site]   plane 0..3 = m_A, m_G, m_C, m_T : possibility bit of the base, but 0 for
+//                                           N-like codes (N, '-', '?')
+//                              plane 4    = +Nl  (1 where the code is N-like)          -- A operand
+//                              plane 5    = -Nl                                        -- B operand
+//
+// For a pair (q, t):  acc = sum_sites [ sum_b m_b(q) m_b(t)  -  Nl(q) Nl(t) ]            (5 MAC / site)
+//   * q, t known            : 1 iff same base
+//   * one known, one partial: 1 iff the base is in the ambiguity set   (overlap indicator, exact)
+//   * anything vs N-like    : the m-part is 0; N-like sites are added back from per-record counts:
+//                             overlap = acc + nN(q) + nN(t)   [the -Nl*Nl term removes the double count]
+//   * both partial          : sum_b = |Sq ^ St| which over-counts by (|X|-1) when the two ambiguity sets
+//                             share >= 2 bases; fixed exactly by pp_correct_kernel from a per-site
+//                             inverted index of the (rare) partial codes.
+// DIFF = width - overlap  <=>  #sites with (q & t) < 16  (measures.rs:14-23).
+//
+// Kernel: persistent, warp-specialised CTA of 192 threads per SM.
+//   warp 0     : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
+//   warp 1     : TMEM allocator + MMA issuer (one elected lane, tcgen05.mma.cta_group::1.kind::i8,
+//                M=128 N=256 K=32, accumulators 2 x 256 TMEM columns, tcgen05.commit -> mbarriers)
+//   warps 2..5 : epilogue (tcgen05.ld 32x32b.x32 -> DIFF -> global store in reference order)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dg {
+namespace tc {
+
+constexpr int TM = 128;          // tile rows    (UMMA M)
+constexpr int TN = 256;          // tile columns (UMMA N)
+constexpr int KB = 128;          // K bytes per stage = one 128B swizzle atom = 128 sites of one plane
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TM * KB;
+constexpr int B_BYTES = TN * KB;
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int THREADS = 192;
+constexpr int NPLANES_STORED = 6;
+constexpr int NPLANES_K = 5;
+constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel traps instead of hanging
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (!done && ++spins > SPIN_LIMIT) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32
+__device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128B-swizzled operand tile whose rows are 128 B: 8-row groups are 1024 B apart (SBO),
+// LBO = 1 (unused for swizzled K-major), descriptor version 1 (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    return ((uint64_t)hi << 32) | lo;
+}
+// kind::i8 instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 256, M = 128.
+constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ---- operand packing ------------------------------------------------------------------------------
+struct PackI8Params {
+    const uint8_t* codes;  // n x width
+    uint64_t n, n_pad, width;
+    uint64_t wp8;          // bytes per plane (width rounded up to 128)
+    int8_t* ops;           // n_pad x 6 x wp8
+    uint32_t* nN;          // n_pad: N-like sites per record (zeroed by the caller)
+    int ascii;
+};
+
+// One thread per (record, 16-site group): 16 byte loads -> six 16-byte stores.
+__global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
+    const uint64_t groups = p.wp8 / 16;
+    const uint64_t total = p.n_pad * groups;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t seq = u / groups;
+        const uint64_t s0 = (u % groups) * 16;
+        uint32_t w[6][4];
+#pragma unroll
+        for (int pl = 0; pl < 6; pl++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) w[pl][k] = 0;
+        uint32_t nn = 0;
+        if (seq < p.n) {
+            const uint8_t* row = p.codes + seq * p.width;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const uint64_t s = s0 + k;
+                if (s >= p.width) break;
+                uint32_t c = row[s];
+                if (p.ascii) c = c_ascii_lut[c];
+                const bool nl = (c & 0xF0u) == 0xF0u;  // N 240, '-' 244, '?' 242
+                const int sh = (k & 3) * 8;
+                if (nl) {
+                    w[4][k >> 2] |= 1u << sh;
+                    w[5][k >> 2] |= 0xFFu << sh;  // -1
+                    nn++;
+                } else {
+                    w[0][k >> 2] |= ((c >> 7) & 1u) << sh;
+                    w[1][k >> 2] |= ((c >> 6) & 1u) << sh;
+                    w[2][k >> 2] |= ((c >> 5) & 1u) << sh;
+                    w[3][k >> 2] |= ((c >> 4) & 1u) << sh;
+                }
+            }
+        }
+        int8_t* base = p.ops + (seq * NPLANES_STORED) * p.wp8 + s0;
+#pragma unroll
+        for (int pl = 0; pl < 6; pl++)
+            *reinterpret_cast<uint4*>(base + pl * p.wp8) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
+        if (nn) atomicAdd(p.nN + seq, nn);
+    }
+}
+
+// ---- inverted index of partial ambiguity codes (R Y M W S K V H D B) -----------------------------------
+// entry = site << 36 | record << 4 | possibility nibble
+struct PpIndex {
+    uint64_t* entries = nullptr;   // sorted by site (order inside a site is arbitrary)
+    uint32_t* site_off = nullptr;  // width + 1 offsets
+    uint32_t n_entries = 0;
+    double pair_work = 0;          // sum over sites of |L_s|^2 (cost of the correction)
+};
+
+__device__ __forceinline__ bool is_partial(uint32_t c) { return (c & 8u) == 0u && (c & 0xF0u) != 0xF0u; }
+
+__global__ void pp_count_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* site_cnt) {
+    const uint64_t total = n * width;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c = codes[u];
+        if (ascii) c = c_ascii_lut[c];
+        if (is_partial(c)) atomicAdd(site_cnt + (u % width), 1u);
+    }
+}
+// single-block exclusive scan over `width` site counts; also sum of squares
+__global__ void pp_scan_kernel(const uint32_t* site_cnt, uint64_t width, uint32_t* site_off, uint32_t* cursor, double* work) {
+    __shared__ uint32_t part[1024];
+    __shared__ double wpart[1024];
+    const uint64_t per = (width + 1023) / 1024;
+    const uint64_t b = threadIdx.x * per, e = min(width, b + per);
+    uint32_t s = 0; double w = 0;
+    for (uint64_t i = b; i < e; i++) { s += site_cnt[i]; w += (double)site_cnt[i] * site_cnt[i]; }
+    part[threadIdx.x] = s; wpart[threadIdx.x] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0; double tw = 0;
+        for (int i = 0; i < 1024; i++) { const uint32_t t = part[i]; part[i] = run; run += t; tw += wpart[i]; }
+        site_off[width] = run;
+        *work = tw;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; i++) { site_off[i] = run; cursor[i] = run; run += site_cnt[i]; }
+}
+__global__ void pp_fill_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* cursor, uint64_t* entries) {
+    const uint64_t total = n * width;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t c = codes[u];
+        if (ascii) c = c_ascii_lut[c];
+        if (is_partial(c)) {
+            const uint64_t site = u % width, rec = u / width;
+            const uint32_t pos = atomicAdd(cursor + site, 1u);
+            entries[pos] = (site << 36) | (rec << 4) | (uint64_t)(c >> 4);
+        }
+    }
+}
+
+struct PpCorrParams {
+    const uint64_t* a_entries; uint32_t a_n;          // row alignment's entries
+    const uint64_t* b_entries; const uint32_t* b_off; // column alignment's index
+    uint32_t row0, row_end, n_b;
+    int square;
+    uint64_t n_total, out_base;
+    uint32_t* out;                                    // DIFF counts of the panel
+};
+// Both-partial sites whose ambiguity sets share x >= 2 bases were counted x times as overlap: add x-1 back to DIFF.
+__global__ void pp_correct_kernel(PpCorrParams p) {
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < p.a_n; e += gridDim.x * blockDim.x) {
+        const uint64_t ea = p.a_entries[e];
+        const uint32_t row = (uint32_t)((ea >> 4) & 0xFFFFFFFFull);
+        if (row < p.row0 || row >= p.row_end) continue;
+        const uint32_t site = (uint32_t)(ea >> 36), ma = (uint32_t)(ea & 15);
+        uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
+                                     : (uint64_t)(row - p.row0) * p.n_b;
+        for (uint32_t k = p.b_off[site]; k < p.b_off[site + 1]; k++) {
+            const uint64_t eb = p.b_entries[k];
+            const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
+            if (p.square && col <= row) continue;
+            const int x = __popc(ma & (uint32_t)(eb & 15));
+            if (x >= 2) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), (uint32_t)(x - 1));
+        }
+    }
+}
+
+// ---- the GEMM kernel ----------------------------------------------------------------------------------
+struct TcParams {
+    const uint32_t* a_nN; const uint32_t* b_nN;
+    uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of TN
+    uint32_t gx, gy;                           // tiles: gx column blocks x gy row blocks
+    int square;
+    uint64_t n_total, out_base;
+    uint32_t* out;
+    uint32_t width;        // valid sites
+    uint32_t wp8;          // bytes per plane
+    uint32_t nsb;          // wp8 / KB
+};
+
+__device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t& rowA0, uint32_t& rowB0) {
+    const uint32_t by = t / p.gx, bx = t % p.gx;
+    rowA0 = p.row0 + by * TM;
+    rowB0 = (p.col_block0 + bx) * TN;
+    if (rowA0 >= p.row_end) return false;
+    if (p.square && rowB0 + TN <= rowA0 + 1) return false;
+    return true;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle needs 1024-byte aligned tiles
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* full = bars;               // [STAGES]
+    uint64_t* empty = bars + STAGES;     // [STAGES]
+    uint64_t* tfull = bars + 2 * STAGES; // [2]
+    uint64_t* tempty = tfull + 2;        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t ntiles = p.gx * p.gy;
+    const uint32_t KT = NPLANES_K * p.nsb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                uint32_t rowA0, rowB0;
+                if (!tile_live(p, t, rowA0, rowB0)) continue;
+                for (uint32_t kt = 0; kt < KT; kt++) {
+                    mbar_wait(empty + stage, phase ^ 1);
+                    mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
+                    const uint32_t plane = kt / p.nsb, sb = kt - plane * p.nsb;
+                    const uint32_t plane_b = plane < 4 ? plane : 5;
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, (int)(plane * p.wp8 + sb * KB), (int)rowA0, full + stage);
+                    tma_load_2d(sa + A_BYTES, &tmB, (int)(plane_b * p.wp8 + sb * KB), (int)rowB0, full + stage);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, it = 0;
+            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                uint32_t rowA0, rowB0;
+                if (!tile_live(p, t, rowA0, rowB0)) continue;
+                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                mbar_wait(tempty + ab, aphase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + ab * TN;
+                for (uint32_t kt = 0; kt < KT; kt++) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+#pragma unroll
+                    for (uint32_t k4 = 0; k4 < KB / 32; k4++)
+                        tc_mma_i8(d_tmem, da + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
+                    tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(tfull + ab);         // accumulator ready for the epilogue
+                it++;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> DIFF -> global, reference order =====
+        const uint32_t quad = warp & 3;  // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
+        uint32_t it = 0;
+        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            uint32_t rowA0, rowB0;
+            if (!tile_live(p, t, rowA0, rowB0)) continue;
+            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+            mbar_wait(tfull + ab, aphase);
+            tc_fence_after();
+            const uint32_t row = rowA0 + quad * 32 + lane;
+            const bool row_ok = row < p.row_end;
+            const uint32_t nq = row_ok ? p.a_nN[row] : 0;
+            const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
+                                               : (uint64_t)(row - p.row0) * p.n_b;
+#pragma unroll 1
+            for (uint32_t c = 0; c < TN / 32; c++) {
+                uint32_t v[32];
+                tc_ld32(tmem_base + ((quad * 32u) << 16) + ab * TN + c * 32, v);
+                if (row_ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t col = rowB0 + c * 32 + j;
+                        if (col >= p.n_b) break;
+                        if (p.square && col <= row) continue;
+                        const uint32_t overlap = v[j] + nq + p.b_nN[col];
+                        p.out[p.square ? row_base + (col - row - 1) : row_base + col] = p.width - overlap;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty + ab);
+            it++;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace dg
