@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -106,6 +107,8 @@ struct PlaneSet {  // one alignment packed on one device
 struct Slot {  // one stage of the result ring (and of the stream-input ring)
     void* d_out = nullptr;
     void* h_out = nullptr;
+    uint32_t* d_scratch = nullptr;  // tcgen05 engine: raw int32 sums, [accumulator][panel pair]
+    size_t scratch_cap = 0;
     cudaEvent_t k_start = nullptr, k_stop = nullptr, copied = nullptr, in_ready = nullptr;
     // stream mode staging
     uint8_t* h_in = nullptr;
@@ -155,7 +158,8 @@ struct dg_ctx {
     size_t panel_bytes = (size_t)128 << 20;
     bool keep_codes = false;
     int tile_variant = 0;
-    int engine = 0;
+    int engine = 0;       // DG_OPT_ENGINE
+    int last_engine = 0;  // engine the last run used (1 LOP3, 2 tcgen05)
     // invalid-site report
     bool have_invalid = false;
     uint64_t inv_record = 0, inv_site = 0;
@@ -163,6 +167,7 @@ struct dg_ctx {
     dg_timings tm{};
     // stream session
     bool streaming = false;
+    bool s_tc = false;  // this stream session runs its batches on the tcgen05 engine
     dg_sink_fn s_sink = nullptr;
     void* s_user = nullptr;
     uint64_t s_max_batch = 0, s_rows_pushed = 0, s_batches = 0;
@@ -270,7 +275,7 @@ EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 
-// 2-D map over ops[n_pad][6 * wp8] bytes: box = 128 bytes (one swizzle atom of K) x `box_rows` records.
+// 2-D map over ops[n_pad][nplanes * wp8] bytes: box = 128 bytes (one swizzle atom of K) x `box_rows` records.
 void make_ops_map(CUtensorMap* map, void* base, uint64_t row_bytes, uint64_t rows, uint32_t box_rows) {
     const cuuint64_t dims[2] = {row_bytes, rows};
     const cuuint64_t strides[1] = {row_bytes};
@@ -282,31 +287,70 @@ void make_ops_map(CUtensorMap* map, void* base, uint64_t row_bytes, uint64_t row
     if (r != CUDA_SUCCESS) fail(DG_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
 }
 
-// Build the int8 operand planes, the N-like counts and the partial-code index of one alignment.
-void build_tc_operands(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
+// Which int8 planes a family stores and which plane pairs each accumulator sums (see tc_engine.cuh).
+struct TcSchedule {
+    int nplanes;
+    uint8_t plane_id[tc::MAX_PLANES];
+    int nacc;
+    int npairs[5];
+    uint8_t pa[5][8], pb[5][8];
+    bool needs_pp;  // the n/n_high sum needs the both-partial correction
+};
+
+const TcSchedule& tc_schedule(int fam) {
+    using namespace tc;
+    static const TcSchedule snp = {6, {P_MA, P_MG, P_MC, P_MT, P_NL, P_NEG_NL}, 1, {5},
+                                   {{0, 1, 2, 3, 4}}, {{0, 1, 2, 3, 5}}, true};
+    static const TcSchedule raw = {10, {P_MA, P_MG, P_MC, P_MT, P_NL, P_NEG_NL, P_KA, P_KG, P_KC, P_KT}, 2, {5, 4},
+                                   {{0, 1, 2, 3, 4}, {6, 7, 8, 9}}, {{0, 1, 2, 3, 5}, {6, 7, 8, 9}}, true};
+    static const TcSchedule k80 = {8, {P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_PURC, P_PYRC}, 3, {4, 2, 2},
+                                   {{0, 1, 2, 3}, {4, 5}, {6, 7}}, {{0, 1, 2, 3}, {4, 5}, {7, 6}}, false};
+    static const TcSchedule tn93 = {7, {P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_K}, 5, {1, 1, 1, 2, 2},
+                                    {{6}, {4}, {5}, {0, 1}, {2, 3}}, {{6}, {4}, {5}, {0, 1}, {2, 3}}, false};
+    return fam == FAM_SNP ? snp : (fam == FAM_RAW ? raw : (fam == FAM_K80 ? k80 : tn93));
+}
+
+void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
+    const TcSchedule& sch = tc_schedule(c->fam);
     const uint64_t wp8 = (c->width + tc::KB - 1) / tc::KB * tc::KB;
     s.tc_wp8 = wp8;
-    const size_t ops_bytes = (size_t)s.n_pad * tc::NPLANES_STORED * wp8;
-    CUDA_CHECK(cudaMalloc(&s.tc_ops, ops_bytes));
+    CUDA_CHECK(cudaMalloc(&s.tc_ops, (size_t)s.n_pad * sch.nplanes * wp8));
     CUDA_CHECK(cudaMalloc(&s.tc_nN, (size_t)s.n_pad * 4));
-    CUDA_CHECK(cudaMemsetAsync(s.tc_nN, 0, (size_t)s.n_pad * 4, st));
+    const uint64_t row_bytes = (uint64_t)sch.nplanes * wp8;
+    make_ops_map(&s.map_a, s.tc_ops, row_bytes, s.n_pad, tc::TM);
+    make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, tc::TN);
+}
+
+// Enqueue (no sync) the int8 operand planes + N-like counts of the first `n` records of the set.
+void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, cudaStream_t st) {
+    const TcSchedule& sch = tc_schedule(c->fam);
+    const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+    CUDA_CHECK(cudaMemsetAsync(s.tc_nN, 0, (size_t)n_pad * 4, st));
     tc::PackI8Params pp{};
-    pp.codes = d_codes; pp.n = s.n; pp.n_pad = s.n_pad; pp.width = c->width; pp.wp8 = wp8;
-    pp.ops = s.tc_ops; pp.nN = s.tc_nN; pp.ascii = s.input_kind == DG_INPUT_ASCII;
-    const uint64_t total = s.n_pad * (wp8 / 16);
+    pp.codes = d_codes; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
+    pp.ops = s.tc_ops; pp.nN = s.tc_nN; pp.ascii = input_kind == DG_INPUT_ASCII;
+    pp.nplanes = sch.nplanes;
+    for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
+    const uint64_t total = n_pad * (s.tc_wp8 / 16);
     tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32), 256, 0, st>>>(pp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.pack_launches++;
-    // inverted index of the partial ambiguity codes (counting sort by site)
+}
+
+// Inverted index of the partial ambiguity codes of a resident alignment (counting sort by site; syncs).
+void build_pp_index(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
+    if (s.pp.entries) { cudaFree(s.pp.entries); s.pp.entries = nullptr; }
+    if (s.pp.site_off) { cudaFree(s.pp.site_off); s.pp.site_off = nullptr; }
     uint32_t *cnt = nullptr, *cursor = nullptr;
     double* d_work = nullptr;
+    const int ascii = s.input_kind == DG_INPUT_ASCII;
     CUDA_CHECK(cudaMalloc(&cnt, (size_t)c->width * 4));
     CUDA_CHECK(cudaMalloc(&cursor, (size_t)c->width * 4));
     CUDA_CHECK(cudaMalloc(&d_work, 8));
     CUDA_CHECK(cudaMalloc(&s.pp.site_off, (size_t)(c->width + 1) * 4));
     CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)c->width * 4, st));
     const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
-    tc::pp_count_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, pp.ascii, cnt);
+    tc::pp_count_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, ascii, cnt);
     tc::pp_scan_kernel<<<1, 1024, 0, st>>>(cnt, c->width, s.pp.site_off, cursor, d_work);
     CUDA_CHECK(cudaGetLastError());
     uint32_t total_entries = 0;
@@ -316,15 +360,19 @@ void build_tc_operands(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStrea
     s.pp.n_entries = total_entries;
     CUDA_CHECK(cudaMalloc(&s.pp.entries, (size_t)std::max<uint32_t>(1, total_entries) * 8));
     if (total_entries) {
-        tc::pp_fill_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, pp.ascii, cursor, s.pp.entries);
+        tc::pp_fill_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, ascii, cursor, s.pp.entries);
         CUDA_CHECK(cudaGetLastError());
     }
     c->tm.pack_launches += 3;
     CUDA_CHECK(cudaStreamSynchronize(st));
     cudaFree(cnt); cudaFree(cursor); cudaFree(d_work);
-    const uint64_t row_bytes = (uint64_t)tc::NPLANES_STORED * wp8;
-    make_ops_map(&s.map_a, s.tc_ops, row_bytes, s.n_pad, tc::TM);
-    make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, tc::TN);
+}
+
+void build_tc_operands(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
+    alloc_tc_operands(c, s);
+    enqueue_tc_pack(c, s, d_codes, s.n, s.input_kind, st);
+    if (tc_schedule(c->fam).needs_pp) build_pp_index(c, s, d_codes, st);
+    CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
 int g_num_sms(int dev) {
@@ -333,10 +381,24 @@ int g_num_sms(int dev) {
     return v;
 }
 
-// tcgen05 variant of enqueue_panel_kernel (n / n_high): GEMM tiles, then the both-partial correction.
-void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                      void* d_out, cudaStream_t st) {
-    if (!A.tc_ops || !B.tc_ops) fail(DG_ERR_STATE, "tensor-engine operands were not built (set DG_OPT_ENGINE before loading)");
+// Engine choice for one run (DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC tiles, 2 tcgen05 int8 GEMM).
+// auto -> tensor cores when the operands exist and the both-partial correction is cheap relative to the
+// GEMM (adversarially ambiguous alignments stay on the LOP3 tiles, which need no correction).
+bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
+    if (c->engine == 1) return false;
+    if (!A.tc_ops || !B.tc_ops) {
+        if (c->engine == 2) fail(DG_ERR_STATE, "tensor-engine operands were not built (set DG_OPT_ENGINE before loading)");
+        return false;
+    }
+    if (c->engine == 2) return true;
+    if (!tc_schedule(c->fam).needs_pp) return true;
+    const double work = std::sqrt(A.pp.pair_work * B.pp.pair_work);
+    return work <= 2.0 * (double)A.n * (double)B.n;
+}
+
+void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
+                    int acc, bool raw_sums, uint32_t* out, cudaStream_t st) {
+    const TcSchedule& sch = tc_schedule(c->fam);
     tc::TcParams tp{};
     tp.a_nN = A.tc_nN; tp.b_nN = B.tc_nN;
     tp.n_b = (uint32_t)B.n;
@@ -346,28 +408,65 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
     tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
     tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM - 1) / tc::TM);
     tp.n_total = A.n; tp.out_base = p.out_base;
-    tp.out = static_cast<uint32_t*>(d_out);
+    tp.out = out;
     tp.width = (uint32_t)c->width; tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
+    tp.npairs = (uint32_t)sch.npairs[acc];
+    for (int i = 0; i < sch.npairs[acc]; i++) { tp.pa[i] = sch.pa[acc][i]; tp.pb[i] = sch.pb[acc][i]; }
+    tp.raw_sums = raw_sums ? 1 : 0;
     if (tp.gx == 0 || tp.gy == 0) return;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_snp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        attr_set = true;
-    }
+    CUDA_CHECK(cudaFuncSetAttribute(tc::tc_snp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)tp.gx * tp.gy, (uint64_t)g_num_sms(d.id));
     tc::tc_snp_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_b, tp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.count_launches++;
-    if (A.pp.n_entries && B.pp.n_entries) {
+    if (acc == 0 && sch.needs_pp && A.pp.n_entries && B.pp.n_entries) {
         tc::PpCorrParams cp{};
         cp.a_entries = A.pp.entries; cp.a_n = A.pp.n_entries;
         cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
         cp.row0 = tp.row0; cp.row_end = tp.row_end; cp.n_b = tp.n_b; cp.square = tp.square;
-        cp.n_total = tp.n_total; cp.out_base = tp.out_base; cp.out = tp.out;
+        cp.n_total = tp.n_total; cp.out_base = tp.out_base; cp.out = out;
+        cp.sign = raw_sums ? -1 : 1;
         tc::pp_correct_kernel<<<(A.pp.n_entries + 255) / 256, 256, 0, st>>>(cp);
         CUDA_CHECK(cudaGetLastError());
         c->tm.count_launches++;
     }
+}
+
+// tcgen05 variant of enqueue_panel_kernel.  n / n_high: one GEMM writes the result directly.  Other
+// families (and the debug counts): one GEMM per accumulator into `scratch`, then tc_combine_kernel.
+void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
+                      void* d_out, uint32_t* scratch, bool swap_roles, bool counts, cudaStream_t st) {
+    const TcSchedule& sch = tc_schedule(c->fam);
+    if (c->fam == FAM_SNP && !counts) {
+        launch_tc_gemm(c, d, A, B, mode, p, 0, false, static_cast<uint32_t*>(d_out), st);
+        return;
+    }
+    if (!scratch) fail(DG_ERR_STATE, "tensor engine: no scratch buffer");
+    const uint64_t stride = p.n_results;
+    for (int a = 0; a < sch.nacc; a++) launch_tc_gemm(c, d, A, B, mode, p, a, true, scratch + (size_t)a * stride, st);
+    tc::CombineParams cp{};
+    cp.acc = scratch; cp.acc_stride = stride;
+    cp.a_nN = A.tc_nN; cp.b_nN = B.tc_nN; cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
+    cp.n_b = (uint32_t)B.n; cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
+    cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
+    cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
+    cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam; cp.counts = counts ? 1 : 0;
+    cp.n_total = A.n; cp.out_base = p.out_base; cp.width = (uint32_t)c->width; cp.out = d_out;
+    dim3 grid((unsigned)((B.n - cp.col0 + 255) / 256), (unsigned)(p.row1 - p.row0));
+    if (grid.x == 0 || grid.y == 0) return;
+    if (grid.y > 65535) fail(DG_ERR_INVALID_ARG, "panel too tall for the combine kernel");
+    tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.count_launches++;
+}
+
+void ensure_scratch(dg_ctx* c, Slot& s, size_t pairs) {
+    const size_t bytes = pairs * 4 * (size_t)tc_schedule(c->fam).nacc;
+    if (s.scratch_cap >= bytes) return;
+    if (s.d_scratch) cudaFree(s.d_scratch);
+    s.d_scratch = nullptr; s.scratch_cap = 0;
+    CUDA_CHECK(cudaMalloc(&s.d_scratch, bytes));
+    s.scratch_cap = bytes;
 }
 
 uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
@@ -457,6 +556,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
                 if (!s.codes) fail(DG_ERR_STATE, "DG_RUN_REPACK needs DG_OPT_KEEP_CODES before loading");
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
                 enqueue_pack(c, d.d_invalid + 2, s, s.codes, s.n, s.input_kind, !s.acgt_from_host, false, d.compute);
+                if (s.tc_ops) enqueue_tc_pack(c, s, s.codes, s.n, s.input_kind, d.compute);
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
                 CUDA_CHECK(cudaEventSynchronize(d.slot[0].p_stop));
                 float ms = 0;
@@ -475,9 +575,13 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         if (k % n_parts == part) mine.push_back(all[k]);
     size_t max_bytes = 0;
     for (auto& p : mine) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
+    const bool tc_run = use_tc(c, c->devs[0].set[0], c->devs[0].set[wb]);
+    c->last_engine = tc_run ? 2 : 1;
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
+        if (tc_run && c->fam != FAM_SNP)
+            for (auto& sl : d.slot) ensure_scratch(c, sl, std::max<size_t>(max_bytes / c->elem_bytes(), 64));
     }
 
     const int K = (int)mine.size();
@@ -515,7 +619,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
             CUDA_CHECK(cudaSetDevice(d.id));
             const Panel& p = mine[k];
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
-            if (c->engine == 2) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, d.cs(si));
+            if (tc_run) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si));
             else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
             CUDA_CHECK(cudaEventRecord(s.k_stop, d.cs(si)));
             if (!device_only) {
@@ -569,7 +673,6 @@ void stream_sink_front(dg_ctx* c) {
 
 void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     if (c->streaming) fail(DG_ERR_STATE, "a stream session is already open");
-    if (c->engine == 2) fail(DG_ERR_INVALID_ARG, "the tcgen05 engine does not cover -s streaming yet; use engine 0/1");
     if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
     if (max_batch == 0) fail(DG_ERR_INVALID_ARG, "max_batch is 0");
     for (auto& d : c->devs)
@@ -580,10 +683,18 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     const TileShape ts = tile_shape(c->fam, c->tile_variant);
     uint64_t mb = std::min(max_batch, std::max<uint64_t>(cap_rows / ts.tm * ts.tm, ts.tm));
     c->s_max_batch = mb;
+    // Streamed batches run on the tensor cores for k80 / tn93 (no ambiguity correction needed); the
+    // n / n_high / raw / jc69 batches stay on the LOP3 tiles (their correction index is per alignment).
+    const bool needs_pp = tc_schedule(c->fam).needs_pp;
+    if (c->engine == 2 && needs_pp)
+        fail(DG_ERR_INVALID_ARG, "engine 2 covers -s streaming for k80 / tn93 only; use engine 0 or 1 for this measure");
+    const bool s_tc = c->engine != 1 && !needs_pp && c->devs[0].set[0].tc_ops != nullptr;
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
-        if (d.in_cap < mb) {
+        if (s_tc)
+            for (auto& sl : d.slot) ensure_scratch(c, sl, (size_t)mb * n_res);
+        if (d.in_cap < mb || (s_tc && !d.slot[0].batch.tc_ops)) {
             for (auto& s : d.slot) {
                 if (s.h_in) cudaFreeHost(s.h_in);
                 if (s.d_in) cudaFree(s.d_in);
@@ -594,11 +705,14 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
                 CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)mb * c->width));
                 CUDA_CHECK(cudaHostAlloc(&s.h_acgt, (size_t)mb * 4 * sizeof(uint32_t), cudaHostAllocDefault));
                 alloc_set(c, s.batch, mb, false);
+                if (s_tc) alloc_tc_operands(c, s.batch);
             }
             d.in_cap = mb;
         }
     }
     c->streaming = true;
+    c->s_tc = s_tc;
+    c->last_engine = s_tc ? 2 : 1;
     c->s_sink = sink;
     c->s_user = user;
     c->s_rows_pushed = 0;
@@ -638,8 +752,10 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     Panel p;
     p.row0 = 0; p.row1 = nb; p.out_base = 0;
     p.n_results = nb * d.set[0].n;
+    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, cst);
     CUDA_CHECK(cudaEventRecord(s.k_start, cst));
-    enqueue_panel_kernel<false>(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, true, cst);
+    if (c->s_tc) enqueue_panel_tc(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, s.d_scratch, true, false, cst);
+    else enqueue_panel_kernel<false>(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, true, cst);
     CUDA_CHECK(cudaEventRecord(s.k_stop, cst));
     CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
     CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(),
@@ -693,6 +809,7 @@ void destroy_device(Device& d) {
     for (auto& s : d.set) free_set(s);
     for (auto& s : d.slot) {
         if (s.d_out) cudaFree(s.d_out);
+        if (s.d_scratch) cudaFree(s.d_scratch);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.d_in) cudaFree(s.d_in);
@@ -807,7 +924,7 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
     }
     if (const char* e = std::getenv("DG_ENGINE")) {  // developer override: 1 = LOP3+POPC tiles, 2 = tcgen05 int8 GEMM
         const int v = std::atoi(e);
-        if (v == 1 || (v == 2 && c->fam == FAM_SNP)) c->engine = v;
+        if (v >= 0 && v <= 2) c->engine = v;
     }
     *out = c;
     return DG_OK;
@@ -830,8 +947,6 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
         case DG_OPT_TILE_VARIANT: ctx->tile_variant = (int)value; break;
         case DG_OPT_ENGINE:
             if (value < 0 || value > 2) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
-            if (value == 2 && ctx->fam != FAM_SNP)
-                fail(DG_ERR_INVALID_ARG, "the tcgen05 engine currently covers n / n_high only");
             ctx->engine = (int)value;
             break;
         default: fail(DG_ERR_INVALID_ARG, "unknown option %d", key);
@@ -878,7 +993,7 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
             ctx->tm.pack_ms += ms;
             try {
                 check_invalid(ctx, d, codes, 0);
-                if (ctx->engine == 2) build_tc_operands(ctx, s, s.codes, d.compute);
+                if (ctx->engine != 1) build_tc_operands(ctx, s, s.codes, d.compute);
             } catch (...) {
                 free_set(s);
                 throw;
@@ -981,6 +1096,22 @@ int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
             // tall alignments: split into launches of <= 65535 row blocks
             const TileShape ts = tile_shape(ctx->fam, ctx->tile_variant);
             const uint64_t step = (uint64_t)ts.tm * 32768;
+            if (use_tc(ctx, A, B)) {
+                // tensor engine: raw sums of every accumulator -> the same canonical counts
+                uint32_t* scratch = nullptr;
+                const uint64_t rows_step = std::min<uint64_t>(A.n, 32768);
+                CUDA_CHECK(cudaMalloc(&scratch, (size_t)rows_step * B.n * 4 * tc_schedule(ctx->fam).nacc));
+                try {
+                    for (uint64_t r = 0; r < A.n; r += rows_step) {
+                        Panel q = p;
+                        q.row0 = r; q.row1 = std::min<uint64_t>(A.n, r + rows_step);
+                        q.out_base = 0; q.n_results = (q.row1 - q.row0) * B.n;
+                        enqueue_panel_tc(ctx, d, A, B, DG_MODE_RECT, q, dbuf + r * B.n, scratch, false, true, d.compute);
+                        CUDA_CHECK(cudaStreamSynchronize(d.compute));
+                    }
+                } catch (...) { cudaFree(scratch); throw; }
+                cudaFree(scratch);
+            } else
             for (uint64_t r = 0; r < A.n; r += step) {
                 Panel q = p;
                 q.row0 = r; q.row1 = std::min<uint64_t>(A.n, r + step);
@@ -1021,6 +1152,7 @@ int dg_debug_planes(dg_ctx* ctx, int which, uint32_t* core, uint32_t* aux, uint6
 int dg_get_timings(const dg_ctx* ctx, dg_timings* out) {
     if (!ctx || !out) return DG_ERR_INVALID_ARG;
     *out = ctx->tm;
+    out->engine = (uint64_t)ctx->last_engine;
     return DG_OK;
 }
 

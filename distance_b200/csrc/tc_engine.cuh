@@ -18,6 +18,16 @@
 //                             inverted index of the (rare) partial codes.
 // DIFF = width - overlap  <=>  #sites with (q & t) < 16  (measures.rs:14-23).
 //
+// The other families use the same GEMM kernel once per integer count (a "schedule" of plane pairs per
+// accumulator, raw int32 sums written to a scratch matrix) followed by tc_combine_kernel, which derives
+// the reference's counts and runs the same f64 epilogues as the LOP3 path:
+//   raw/jc69 : acc0 = the n/n_high sum above (DIFF), acc1 = sum_b k_b k_b (SAME; k_b = known one-hot)
+//   k80      : SAME; CS = PURk.PURk + PYRk.PYRk (known, same class) -> ts = CS - SAME;
+//              tv = PURc.PYRc' + PYRc.PURc' (classes {A,G,R} / {C,T,Y}, measures.rs:90-103)
+//   tn93     : L = K.K, PP = PURk.PURk, YY = PYRk.PYRk, SP = kA.kA + kG.kG, SY = kC.kC + kT.kT
+//              -> d = L - SP - SY, P1 = PP - SP, P2 = YY - SY      (7 MAC / site, all exact: only known
+//              bases enter k80 / tn93 counts apart from the rank-2 R/Y classes of tv)
+//
 // Kernel: persistent, warp-specialised CTA of 192 threads per SM.
 //   warp 0     : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
 //   warp 1     : TMEM allocator + MMA issuer (one elected lane, tcgen05.mma.cta_group::1.kind::i8,
@@ -40,8 +50,6 @@ constexpr int B_BYTES = TN * KB;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int THREADS = 192;
-constexpr int NPLANES_STORED = 6;
-constexpr int NPLANES_K = 5;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel traps instead of hanging
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -110,55 +118,68 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 // ---- operand packing ------------------------------------------------------------------------------
+// plane ids (value of a plane at a site is 0/1, except NEG_NL which is 0/-1)
+enum PlaneId { P_MA = 0, P_MG, P_MC, P_MT, P_NL, P_NEG_NL, P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_K, P_PURC, P_PYRC };
+constexpr int MAX_PLANES = 10;
+
 struct PackI8Params {
     const uint8_t* codes;  // n x width
     uint64_t n, n_pad, width;
     uint64_t wp8;          // bytes per plane (width rounded up to 128)
-    int8_t* ops;           // n_pad x 6 x wp8
+    int8_t* ops;           // n_pad x nplanes x wp8
     uint32_t* nN;          // n_pad: N-like sites per record (zeroed by the caller)
     int ascii;
+    int nplanes;
+    uint8_t plane_id[MAX_PLANES];
 };
 
-// One thread per (record, 16-site group): 16 byte loads -> six 16-byte stores.
+// bit i of the result = value of plane id i for Paradis code c
+__device__ __forceinline__ uint32_t plane_bits(uint32_t c) {
+    const bool nl = (c & 0xF0u) == 0xF0u;  // N 240, '-' 244, '?' 242
+    const uint32_t known = (c >> 3) & 1u;
+    const uint32_t poss = nl ? 0u : (c >> 4);  // bit3 = A, bit2 = G, bit1 = C, bit0 = T
+    const uint32_t a = (poss >> 3) & 1u, g = (poss >> 2) & 1u, cc = (poss >> 1) & 1u, t = poss & 1u;
+    uint32_t m = a | (g << 1) | (cc << 2) | (t << 3);
+    m |= (nl ? 1u : 0u) << P_NL;
+    m |= (nl ? 1u : 0u) << P_NEG_NL;
+    m |= (known & a) << P_KA | (known & g) << P_KG | (known & cc) << P_KC | (known & t) << P_KT;
+    m |= (known & (a | g)) << P_PURK | (known & (cc | t)) << P_PYRK | known << P_K;
+    m |= ((c & 55u) == 0u ? 1u : 0u) << P_PURC;   // measures.rs:90  {A,G,R}
+    m |= ((c & 199u) == 0u ? 1u : 0u) << P_PYRC;  // measures.rs:94  {C,T,Y}
+    return m;
+}
+
+// One thread per (record, 16-site group): 16 byte loads -> one 16-byte store per stored plane.
 __global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
     const uint64_t groups = p.wp8 / 16;
     const uint64_t total = p.n_pad * groups;
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t seq = u / groups;
         const uint64_t s0 = (u % groups) * 16;
-        uint32_t w[6][4];
-#pragma unroll
-        for (int pl = 0; pl < 6; pl++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) w[pl][k] = 0;
+        uint32_t bits[16];
         uint32_t nn = 0;
-        if (seq < p.n) {
-            const uint8_t* row = p.codes + seq * p.width;
 #pragma unroll
-            for (int k = 0; k < 16; k++) {
-                const uint64_t s = s0 + k;
-                if (s >= p.width) break;
-                uint32_t c = row[s];
+        for (int k = 0; k < 16; k++) {
+            bits[k] = 0;
+            const uint64_t s = s0 + k;
+            if (seq < p.n && s < p.width) {
+                uint32_t c = p.codes[seq * p.width + s];
                 if (p.ascii) c = c_ascii_lut[c];
-                const bool nl = (c & 0xF0u) == 0xF0u;  // N 240, '-' 244, '?' 242
-                const int sh = (k & 3) * 8;
-                if (nl) {
-                    w[4][k >> 2] |= 1u << sh;
-                    w[5][k >> 2] |= 0xFFu << sh;  // -1
-                    nn++;
-                } else {
-                    w[0][k >> 2] |= ((c >> 7) & 1u) << sh;
-                    w[1][k >> 2] |= ((c >> 6) & 1u) << sh;
-                    w[2][k >> 2] |= ((c >> 5) & 1u) << sh;
-                    w[3][k >> 2] |= ((c >> 4) & 1u) << sh;
-                }
+                bits[k] = plane_bits(c);
+                nn += (bits[k] >> P_NL) & 1u;
             }
         }
-        int8_t* base = p.ops + (seq * NPLANES_STORED) * p.wp8 + s0;
+        int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + s0;
+        for (int pl = 0; pl < p.nplanes; pl++) {
+            const uint32_t id = p.plane_id[pl];
+            const uint32_t one = id == P_NEG_NL ? 0xFFu : 1u;
+            uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
-        for (int pl = 0; pl < 6; pl++)
-            *reinterpret_cast<uint4*>(base + pl * p.wp8) = make_uint4(w[pl][0], w[pl][1], w[pl][2], w[pl][3]);
-        if (nn) atomicAdd(p.nN + seq, nn);
+            for (int k = 0; k < 16; k++)
+                if ((bits[k] >> id) & 1u) w[k >> 2] |= one << ((k & 3) * 8);
+            *reinterpret_cast<uint4*>(base + pl * p.wp8) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        if (nn && p.nN) atomicAdd(p.nN + seq, nn);
     }
 }
 
@@ -220,7 +241,8 @@ struct PpCorrParams {
     uint32_t row0, row_end, n_b;
     int square;
     uint64_t n_total, out_base;
-    uint32_t* out;                                    // DIFF counts of the panel
+    uint32_t* out;                                    // panel counts: DIFF (sign +1) or the raw overlap sum (sign -1)
+    int sign;
 };
 // Both-partial sites whose ambiguity sets share x >= 2 bases were counted x times as overlap: add x-1 back to DIFF.
 __global__ void pp_correct_kernel(PpCorrParams p) {
@@ -236,7 +258,7 @@ __global__ void pp_correct_kernel(PpCorrParams p) {
             const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
             if (p.square && col <= row) continue;
             const int x = __popc(ma & (uint32_t)(eb & 15));
-            if (x >= 2) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), (uint32_t)(x - 1));
+            if (x >= 2) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), (uint32_t)(p.sign * (x - 1)));
         }
     }
 }
@@ -252,10 +274,18 @@ struct TcParams {
     uint32_t width;        // valid sites
     uint32_t wp8;          // bytes per plane
     uint32_t nsb;          // wp8 / KB
+    uint32_t npairs;       // plane pairs summed into this accumulator
+    uint8_t pa[8], pb[8];  // stored-plane index of the A / B operand of each pair
+    int raw_sums;          // 0: out = width - (acc + nN(q) + nN(t))  (n / n_high);  1: out = acc (int32 scratch)
 };
 
+// Tile order: bands of RASTER_G row blocks, column-major inside a band, so the ~148 tiles in flight
+// cover a near-square patch of the pair matrix and share their A / B operand rows through L2.
+constexpr uint32_t RASTER_G = 16;
 __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t& rowA0, uint32_t& rowB0) {
-    const uint32_t by = t / p.gx, bx = t % p.gx;
+    const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
+    const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
+    const uint32_t bx = r / gb, by = band * RASTER_G + (r - bx * gb);
     rowA0 = p.row0 + by * TM;
     rowB0 = (p.col_block0 + bx) * TN;
     if (rowA0 >= p.row_end) return false;
@@ -277,7 +307,7 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ntiles = p.gx * p.gy;
-    const uint32_t KT = NPLANES_K * p.nsb;
+    const uint32_t KT = p.npairs * p.nsb;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
@@ -304,11 +334,10 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 for (uint32_t kt = 0; kt < KT; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
-                    const uint32_t plane = kt / p.nsb, sb = kt - plane * p.nsb;
-                    const uint32_t plane_b = plane < 4 ? plane : 5;
+                    const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, (int)(plane * p.wp8 + sb * KB), (int)rowA0, full + stage);
-                    tma_load_2d(sa + A_BYTES, &tmB, (int)(plane_b * p.wp8 + sb * KB), (int)rowB0, full + stage);
+                    tma_load_2d(sa, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)rowA0, full + stage);
+                    tma_load_2d(sa + A_BYTES, &tmB, (int)(p.pb[pr] * p.wp8 + sb * KB), (int)rowB0, full + stage);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -351,7 +380,7 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tc_fence_after();
             const uint32_t row = rowA0 + quad * 32 + lane;
             const bool row_ok = row < p.row_end;
-            const uint32_t nq = row_ok ? p.a_nN[row] : 0;
+            const uint32_t nq = (row_ok && !p.raw_sums) ? p.a_nN[row] : 0;
             const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
                                                : (uint64_t)(row - p.row0) * p.n_b;
 #pragma unroll 1
@@ -364,8 +393,9 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         const uint32_t col = rowB0 + c * 32 + j;
                         if (col >= p.n_b) break;
                         if (p.square && col <= row) continue;
-                        const uint32_t overlap = v[j] + nq + p.b_nN[col];
-                        p.out[p.square ? row_base + (col - row - 1) : row_base + col] = p.width - overlap;
+                        const uint64_t idx = p.square ? row_base + (col - row - 1) : row_base + col;
+                        if (p.raw_sums) p.out[idx] = v[j];
+                        else p.out[idx] = p.width - (v[j] + nq + p.b_nN[col]);
                     }
                 }
             }
@@ -380,6 +410,57 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
+}
+
+
+// ---- combine: raw int32 sums of the accumulators -> reference counts -> result ------------------------
+struct CombineParams {
+    const uint32_t* acc;    // [nacc][panel pairs]
+    uint64_t acc_stride;    // pairs per accumulator
+    const uint32_t* a_nN; const uint32_t* b_nN;
+    const uint32_t* a_acgt; const uint32_t* b_acgt;
+    uint32_t n_b, row0, row_end, col0;
+    int square, swap_roles, measure, fam, counts;
+    uint64_t n_total, out_base;
+    uint32_t width;
+    void* out;              // double[pairs], or uint4[pairs] canonical counts (dg_debug_counts)
+};
+
+__global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
+    const uint32_t row = p.row0 + blockIdx.y;
+    const uint32_t col = p.col0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= p.row_end || col >= p.n_b) return;
+    if (p.square && col <= row) return;
+    const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
+                                  : (uint64_t)(row - p.row0) * p.n_b + col;
+    const uint32_t a0 = p.acc[idx];
+    const uint32_t a1 = p.fam != FAM_SNP ? p.acc[p.acc_stride + idx] : 0;
+    uint4 cnt = make_uint4(0, 0, 0, 0);
+    if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
+        const uint32_t diff = p.width - (a0 + p.a_nN[row] + p.b_nN[col]);
+        cnt = make_uint4(diff, a1, 0, 0);  // {n, same}
+    } else if (p.fam == FAM_K80) {
+        const uint32_t tv = p.acc[2 * p.acc_stride + idx];
+        cnt = make_uint4(a0, (a1 - a0) + tv, tv, 0);  // {same, ts + tv, tv}
+    } else {
+        const uint32_t yy = p.acc[2 * p.acc_stride + idx], sp = p.acc[3 * p.acc_stride + idx],
+                       sy = p.acc[4 * p.acc_stride + idx];
+        cnt = make_uint4(a0, a0 - sp - sy, a1 - sp, yy - sy);  // {L, d, P1, P2}
+    }
+    if (p.counts) {
+        reinterpret_cast<uint4*>(p.out)[idx] = cnt;
+        return;
+    }
+    double r;
+    if (p.fam == FAM_SNP) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; return; }
+    if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
+    else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z);
+    else {
+        const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
+        const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
+        r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc);
+    }
+    reinterpret_cast<double*>(p.out)[idx] = r;
 }
 
 }  // namespace tc

@@ -118,7 +118,8 @@ typedef struct dg_ctx dg_ctx;
 #define DG_OPT_PANEL_BYTES 1 /* target bytes of one result panel (default 128 MiB) */
 #define DG_OPT_KEEP_CODES 2  /* keep the raw code bytes on the device after dg_load_resident (0/1) */
 #define DG_OPT_TILE_VARIANT 3 /* tuning: 0 = default tile shape per measure family, >0 = alternatives */
-#define DG_OPT_ENGINE 4      /* 0 = auto, 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 one-hot GEMM */
+#define DG_OPT_ENGINE 4      /* 0 = auto (per shape / ambiguity load), 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8
+                                one-hot GEMM.  Set it before dg_load_resident: it decides which operands are built. */
 
 typedef struct {
     double pack_ms;       /* pack_planes kernels, CUDA events on the launching stream */
@@ -132,6 +133,7 @@ typedef struct {
     uint64_t pairs;       /* pairs computed by count kernels since the last reset */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
+    uint64_t engine;      /* engine of the last run: 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 GEMM */
 } dg_timings;
 
 DG_API int dg_abi_version(void);

@@ -13,6 +13,14 @@ REL_TOL = 1e-12  # BASELINE.json north_star: "raw/jc69/k80/tn93 must agree withi
 ALL = ["n", "n_high", "raw", "jc69", "k80", "tn93"]
 
 
+@pytest.fixture(autouse=True, params=["lop3", "tc", "auto"])
+def engine(request, monkeypatch):
+    """Every test runs on both count engines and on the automatic choice: DG_ENGINE overrides
+    DG_OPT_ENGINE at dg_create (1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 one-hot GEMM, 0 = auto)."""
+    monkeypatch.setenv("DG_ENGINE", {"lop3": "1", "tc": "2", "auto": "0"}[request.param])
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def dg():
     import distance_b200 as d
@@ -204,8 +212,10 @@ def test_rect_matches_oracle_both_orders(dg, oracle, measure):
 
 
 @pytest.mark.parametrize("measure", ALL)
-def test_stream_matches_oracle(dg, oracle, measure):
+def test_stream_matches_oracle(dg, oracle, measure, engine):
     from distance_b200 import synth
+    if engine == "tc" and measure in ("n", "n_high", "raw", "jc69"):
+        pytest.skip("engine 2 streams k80 / tn93 only (the ambiguity correction index is per alignment)")
     rng = np.random.default_rng(1234)
     loaded = synth.random_codes(rng, 45, 500, p_ambig=0.2)
     streamed = synth.random_codes(rng, 210, 500, p_ambig=0.2)
@@ -308,10 +318,12 @@ def test_sars_cov_2_width_against_oracle(dg, oracle, measure):
     check(measure, got, oracle_run(oracle, measure, "square", codes))
 
 
-def test_config2_full_size_properties(dg, oracle):
+def test_config2_full_size_properties(dg, oracle, engine):
     """BASELINE config 2 (n_high, 20,000 x 29,903, 1% ambiguity/gaps): rows sampled against the
     oracle, symmetry square-vs-rect on a block, and a checksum that is independent of panel size."""
     from distance_b200 import api, synth
+    if engine == "auto":
+        pytest.skip("covered by the explicit engines")
     n = 20000
     codes = synth.encode_ascii(synth.make_alignment(n, seed=20251018 + 2, ambiguity=True))
     with dg.Engine("n_high", synth.SC2_WIDTH) as e:
@@ -340,7 +352,30 @@ def test_config2_full_size_properties(dg, oracle):
         assert np.array_equal(got[off(i) + (15000 - i - 1): off(i) + (15100 - i - 1)], rect[:, ii])
 
 
-def test_multi_gpu_single_process_matches_oracle(dg, oracle):
+def test_auto_engine_choice(dg, oracle, engine):
+    """auto: tensor cores for ordinary alignments, LOP3 tiles when nearly every site is a partial
+    ambiguity code (the both-partial correction would dominate); results identical either way."""
+    from distance_b200 import synth
+    if engine != "auto":
+        pytest.skip("auto only")
+    rng = np.random.default_rng(77)
+    normal = synth.encode_ascii(synth.make_alignment(200, width=2000, seed=5, ambiguity=True))
+    partial = np.array([192, 160, 144, 96, 80, 48, 224, 176, 208, 112], np.uint8)[rng.integers(0, 10, size=(200, 2000))]
+    for codes, want_engine in ((normal, 2), (partial, 1)):
+        for measure in ("n_high", "raw"):
+            with dg.Engine(measure, 2000) as e:
+                e.load(0, codes)
+                got = e.run_square()
+                assert e.timings()["engine"] == want_engine
+            check(measure, got, oracle_run(oracle, measure, "square", codes))
+    with dg.Engine("tn93", 2000) as e:  # k80 / tn93 need no correction: always tensor cores
+        e.load(0, partial)
+        got = e.run_square()
+        assert e.timings()["engine"] == 2
+    check("tn93", got, oracle_run(oracle, "tn93", "square", partial))
+
+
+def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
     """One process driving every visible device: planes replicated, panels dealt round-robin, the sink
     still sees them in global order.  Skipped on a one-GPU box."""
     from distance_b200 import api, synth
@@ -358,6 +393,8 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle):
             got = e.run_square()
             assert len(e.last_panels) >= 2 * ndev
             check(measure, got, want)
+            if engine == "tc" and measure == "n_high":
+                continue
             loaded, streamed = codes[:40], codes[40:400]
             e.load(0, loaded)
             got = e.stream([streamed[i:i + 50] for i in range(0, 360, 50)], max_batch=64)
