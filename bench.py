@@ -177,6 +177,8 @@ def run_ours(args):
     eng.set_option(api.DG_OPT_KEEP_CODES, 1)
     if args.tile_variant:
         eng.set_option(api.DG_OPT_TILE_VARIANT, args.tile_variant)
+    if args.engine:
+        eng.set_option(api.DG_OPT_ENGINE, args.engine)
     eng.load(0, pinned)
 
     def sync_all():
@@ -248,7 +250,7 @@ def run_ours(args):
         peak = 16 * 148 * mhz * 1e6 * ops_per_word / 1e12
         peak_src = f"nominal 16 word-pairs/clk/SM x 148 SM x {mhz:.0f} MHz (no measured int peaks file)"
         frac_lop3 = achieved / (64 * 148 * mhz * 1e6 / 1e12)
-    roofline = {
+    roofline_lop3 = {
         "bound": "int_issue", "kernel": "count_tile_kernel<FAM_SNP>", "achieved": achieved, "peak": peak,
         "unit": "Tlaneop/s", "frac": achieved / peak, "traffic": peaks.get("count_kernel_dram_bytes_per_launch"),
         "ops_per_pair_site": OPS_PER_PAIR_SITE[MEASURE], "peak_source": peak_src,
@@ -259,6 +261,29 @@ def run_ours(args):
                 "tensor bound (SURVEY 8d); consecutive panel launches overlap on two streams, so achieved uses "
                 "the device time of the whole step; traffic = DRAM bytes of one profiled launch (see profiles/)",
     }
+    if int(tm.get("engine", 1)) == 2:
+        # tcgen05 engine: ALGORITHMIC int8 ops (5 MAC = 10 ops per pair-site for n / n_high) of this
+        # rank's launches / device time of the step, against the MEASURED kind::i8 issue rate.
+        i8ops = my_pairs * WIDTH * 10.0
+        ach = i8ops / (run_ms_step * 1e-3) / 1e12
+        pk8 = peaks.get("int8_tops_measured")
+        src8 = "measured: tools/ubench_tc (profiles/ubench_tc_r01.json), tcgen05.mma kind::i8 M128 N256 K32 SS on 148 SMs"
+        if not pk8:
+            pk8 = 2.0 * measured.get("bf16_tflops", 1590.0)
+            src8 = "2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json (kind::i8 is nominally 2 x bf16)"
+        roofline = {
+            "bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)", "achieved": ach, "peak": pk8,
+            "unit": "TOP/s (int8; the spec's TFLOP/s slot)", "frac": ach / pk8,
+            "traffic": peaks.get("tc_kernel_dram_bytes_per_launch"),
+            "ops_per_pair_site": 10, "peak_source": src8,
+            "padded_frac": ach / pk8 * (math.ceil(WIDTH / 128) * 128) / WIDTH,
+            "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
+            "note": "engine chosen automatically per shape (DG_OPT_ENGINE=0): tensor cores here; the LOP3+POPC engine "
+                    "stays for alignments dominated by ambiguity codes.  padded_frac counts the 49 zero-padded sites per "
+                    "128-site K block as work done.",
+        }
+    else:
+        roofline = roofline_lop3
     hbm = measured.get("hbm_gbs")
     pack_ms_step = tm["pack_ms"] / args.steps
     pack_bytes = n * WIDTH + n * math.ceil(WIDTH / 32) * 16  # read 1 B/site, write the 4 core planes
@@ -281,7 +306,7 @@ def run_ours(args):
             "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
             "pair_sites_per_s": value * WIDTH, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u32 bit-planes (popcount), u32 results", "data": "synthetic",
+            "vs_baseline": None, "dtype": "int8 one-hot planes, int32 accumulation (tcgen05) / u32 bit-planes (LOP3+POPC); u32 results", "data": "synthetic",
             "config": {"workload": f"config 2: -m {MEASURE} all-vs-all, {n:,} x 29,903 nt, 1% N/ambiguity/gaps",
                        "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
                        "weak_scaling": "n = round(20000*sqrt(N)) so pairs per GPU stay ~2.0e8",
@@ -289,7 +314,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (bit-planes %.0f MB vs 126 MB L2)" % (n * 936 * 16 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * 4)},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8"}.get(int(tm.get("engine", 0)), "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -305,8 +330,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the record count (debug)")
-    ap.add_argument("--panel-bytes", type=int, default=128 << 20)
+    ap.add_argument("--panel-bytes", type=int, default=256 << 20)
     ap.add_argument("--tile-variant", type=int, default=0)
+    ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -130,7 +130,7 @@ def device_count() -> int:
 
 
 _NULL_SINK = C.cast(None, SINK_FN)
-DEFAULT_PANEL_BYTES = 128 << 20
+DEFAULT_PANEL_BYTES = 256 << 20
 
 
 def plan_panels(measure: str, mode: int, n_rows: int, n_cols: int, panel_bytes: int = DEFAULT_PANEL_BYTES,

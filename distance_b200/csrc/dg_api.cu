@@ -155,7 +155,7 @@ struct dg_ctx {
     std::vector<Device> devs;
     std::string err;
     // options
-    size_t panel_bytes = (size_t)128 << 20;
+    size_t panel_bytes = (size_t)256 << 20;
     bool keep_codes = false;
     int tile_variant = 0;
     int engine = 0;       // DG_OPT_ENGINE
@@ -406,7 +406,8 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
     tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tc::TN) : 0;
     tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
-    tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM - 1) / tc::TM);
+    const int cl = c->tile_variant == 2 ? 2 : 1;  // tile variant 2 = the 2-CTA cluster kernel with TMA multicast of B
+    tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl - 1) / (tc::TM * cl));
     tp.n_total = A.n; tp.out_base = p.out_base;
     tp.out = out;
     tp.width = (uint32_t)c->width; tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
@@ -414,10 +415,25 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     for (int i = 0; i < sch.npairs[acc]; i++) { tp.pa[i] = sch.pa[acc][i]; tp.pb[i] = sch.pb[acc][i]; }
     tp.raw_sums = raw_sums ? 1 : 0;
     if (tp.gx == 0 || tp.gy == 0) return;
-    CUDA_CHECK(cudaFuncSetAttribute(tc::tc_snp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)tp.gx * tp.gy, (uint64_t)g_num_sms(d.id));
-    tc::tc_snp_kernel<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_b, tp);
-    CUDA_CHECK(cudaGetLastError());
+    const uint64_t tiles = (uint64_t)tp.gx * tp.gy;
+    if (cl == 1) {
+        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id));
+        tc::tc_gemm_kernel<1><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_a, tp);
+        CUDA_CHECK(cudaGetLastError());
+    } else {
+        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(2 * (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id) / 2));
+        cfg.blockDim = dim3(tc::THREADS);
+        cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::tc_gemm_kernel<2>, A.map_a, B.map_a, tp));
+    }
     c->tm.count_launches++;
     if (acc == 0 && sch.needs_pp && A.pp.n_entries && B.pp.n_entries) {
         tc::PpCorrParams cp{};
@@ -452,9 +468,8 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
     cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
     cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam; cp.counts = counts ? 1 : 0;
     cp.n_total = A.n; cp.out_base = p.out_base; cp.width = (uint32_t)c->width; cp.out = d_out;
-    dim3 grid((unsigned)((B.n - cp.col0 + 255) / 256), (unsigned)(p.row1 - p.row0));
+    dim3 grid((unsigned)((B.n - cp.col0 + 255) / 256), (unsigned)std::min<uint64_t>(p.row1 - p.row0, 32768));
     if (grid.x == 0 || grid.y == 0) return;
-    if (grid.y > 65535) fail(DG_ERR_INVALID_ARG, "panel too tall for the combine kernel");
     tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.count_launches++;
@@ -479,7 +494,8 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
     if (rows_major == 0 || n_cols == 0) return v;
     uint64_t per = panel_bytes / (elem_bytes * std::max<uint64_t>(1, n_cols));
     per = std::min<uint64_t>(per, (uint64_t)tm * 32768);  // gridDim.y limit
-    per = std::max<uint64_t>(tm, per / tm * tm);
+    const uint64_t quantum = std::max<uint64_t>(tm, 256);  // also a multiple of the tensor engine's 256-row super-tile
+    per = std::max<uint64_t>(quantum, per / quantum * quantum);
     for (uint64_t r = 0; r < rows_major; r += per) {
         Panel p;
         p.row0 = r;

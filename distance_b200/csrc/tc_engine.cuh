@@ -81,10 +81,29 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// same, but the arrive lands on the barrier at this offset in every CTA of `mask` (cluster multicast)
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32
 __device__ __forceinline__ void tc_mma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
@@ -267,7 +286,7 @@ __global__ void pp_correct_kernel(PpCorrParams p) {
 struct TcParams {
     const uint32_t* a_nN; const uint32_t* b_nN;
     uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of TN
-    uint32_t gx, gy;                           // tiles: gx column blocks x gy row blocks
+    uint32_t gx, gy;                           // tiles: gx column blocks x gy row blocks (of TM * CL rows)
     int square;
     uint64_t n_total, out_base;
     uint32_t* out;
@@ -279,22 +298,30 @@ struct TcParams {
     int raw_sums;          // 0: out = width - (acc + nN(q) + nN(t))  (n / n_high);  1: out = acc (int32 scratch)
 };
 
-// Tile order: bands of RASTER_G row blocks, column-major inside a band, so the ~148 tiles in flight
-// cover a near-square patch of the pair matrix and share their A / B operand rows through L2.
-constexpr uint32_t RASTER_G = 16;
-__device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t& rowA0, uint32_t& rowB0) {
+// Tile order: bands of RASTER_G row blocks, column-major inside a band, so the tiles in flight cover a
+// near-square patch of the pair matrix and share their A / B operand rows through L2.  With CL = 2 a
+// "row block" is the 256-row super-tile of a CTA pair (rank r owns rows [128 r, 128 r + 128) of it).
+constexpr uint32_t RASTER_G = 8;
+template <int CL>
+__device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t rank, uint32_t& rowA0, uint32_t& rowB0) {
     const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
     const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
     const uint32_t bx = r / gb, by = band * RASTER_G + (r - bx * gb);
-    rowA0 = p.row0 + by * TM;
+    const uint32_t rowS0 = p.row0 + by * (TM * CL);
     rowB0 = (p.col_block0 + bx) * TN;
-    if (rowA0 >= p.row_end) return false;
-    if (p.square && rowB0 + TN <= rowA0 + 1) return false;
+    rowA0 = rowS0 + rank * TM;
+    if (rowS0 >= p.row_end) return false;
+    if (p.square && rowB0 + TN <= rowS0 + 1) return false;   // decided per super-tile: identical in both CTAs
     return true;
 }
 
+// CL = 1: one CTA per tile.  CL = 2: a cluster of two CTAs shares the B tile -- each CTA fetches one
+// 128-row half of it and TMA-multicasts it into both CTAs' shared memory, which cuts the L2 -> SM
+// operand traffic per MAC by a third; the MMAs stay cta_group::1.  A stage is free again only when
+// BOTH CTAs' MMAs have retired (multicast tcgen05.commit onto both `empty` barriers, count 2).
+template <int CL>
 __global__ void __launch_bounds__(THREADS, 1)
-tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -308,9 +335,12 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ntiles = p.gx * p.gy;
     const uint32_t KT = p.npairs * p.nsb;
+    const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
+    const uint32_t cid = blockIdx.x / CL, ncl = gridDim.x / CL;   // tiles are dealt to clusters
+    constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }
         for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -321,6 +351,7 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -328,16 +359,23 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = cid; t < ntiles; t += ncl) {
                 uint32_t rowA0, rowB0;
-                if (!tile_live(p, t, rowA0, rowB0)) continue;
+                if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
                 for (uint32_t kt = 0; kt < KT; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
                     const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
+                    const int xb = (int)(p.pb[pr] * p.wp8 + sb * KB);
                     tma_load_2d(sa, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)rowA0, full + stage);
-                    tma_load_2d(sa + A_BYTES, &tmB, (int)(p.pb[pr] * p.wp8 + sb * KB), (int)rowB0, full + stage);
+                    if (CL == 1) {  // both 128-row halves of the B tile
+                        tma_load_2d(sa + A_BYTES, &tmB, xb, (int)rowB0, full + stage);
+                        tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmB, xb, (int)(rowB0 + TN / 2), full + stage);
+                    } else {        // my half, delivered to both CTAs of the cluster
+                        tma_load_2d_mc(sa + A_BYTES + rank * (B_BYTES / 2), &tmB, xb, (int)(rowB0 + rank * (TN / 2)),
+                                       full + stage, MC_MASK);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -346,9 +384,9 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // ===== MMA issuer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, it = 0;
-            for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+            for (uint32_t t = cid; t < ntiles; t += ncl) {
                 uint32_t rowA0, rowB0;
-                if (!tile_live(p, t, rowA0, rowB0)) continue;
+                if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
                 const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
                 mbar_wait(tempty + ab, aphase ^ 1);
                 tc_fence_after();
@@ -361,7 +399,8 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                     for (uint32_t k4 = 0; k4 < KB / 32; k4++)
                         tc_mma_i8(d_tmem, da + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
-                    tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
+                    if (CL == 1) tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
+                    else tc_commit_mc(empty + stage, MC_MASK);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull + ab);         // accumulator ready for the epilogue
@@ -372,9 +411,9 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         // ===== epilogue: TMEM -> registers -> DIFF -> global, reference order =====
         const uint32_t quad = warp & 3;  // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
         uint32_t it = 0;
-        for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (uint32_t t = cid; t < ntiles; t += ncl) {
             uint32_t rowA0, rowB0;
-            if (!tile_live(p, t, rowA0, rowB0)) continue;
+            if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
             const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
             mbar_wait(tfull + ab, aphase);
             tc_fence_after();
@@ -407,6 +446,7 @@ tc_snp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
@@ -427,10 +467,10 @@ struct CombineParams {
 };
 
 __global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
-    const uint32_t row = p.row0 + blockIdx.y;
     const uint32_t col = p.col0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= p.row_end || col >= p.n_b) return;
-    if (p.square && col <= row) return;
+    if (col >= p.n_b) return;
+    for (uint32_t row = p.row0 + blockIdx.y; row < p.row_end; row += gridDim.y) {
+    if (p.square && col <= row) continue;
     const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
                                   : (uint64_t)(row - p.row0) * p.n_b + col;
     const uint32_t a0 = p.acc[idx];
@@ -449,10 +489,10 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
     }
     if (p.counts) {
         reinterpret_cast<uint4*>(p.out)[idx] = cnt;
-        return;
+        continue;
     }
     double r;
-    if (p.fam == FAM_SNP) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; return; }
+    if (p.fam == FAM_SNP) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; continue; }
     if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
     else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z);
     else {
@@ -461,6 +501,7 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
         r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc);
     }
     reinterpret_cast<double*>(p.out)[idx] = r;
+    }
 }
 
 }  // namespace tc

@@ -115,7 +115,7 @@ typedef struct dg_ctx dg_ctx;
 #define DG_RUN_REPACK 2u      /* re-run pack_planes from the device-resident codes first (needs DG_OPT_KEEP_CODES) */
 
 /* dg_set_option keys */
-#define DG_OPT_PANEL_BYTES 1 /* target bytes of one result panel (default 128 MiB) */
+#define DG_OPT_PANEL_BYTES 1 /* target bytes of one result panel (default 256 MiB) */
 #define DG_OPT_KEEP_CODES 2  /* keep the raw code bytes on the device after dg_load_resident (0/1) */
 #define DG_OPT_TILE_VARIANT 3 /* tuning: 0 = default tile shape per measure family, >0 = alternatives */
 #define DG_OPT_ENGINE 4      /* 0 = auto (per shape / ambiguity load), 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8

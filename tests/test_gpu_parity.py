@@ -278,11 +278,11 @@ def test_panels_and_parts_cover_the_triangle(dg, oracle, measure):
     from distance_b200 import synth
     from distance_b200 import api
     rng = np.random.default_rng(3)
-    n, width = 700, 200
+    n, width = 1400, 200
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     want = oracle_run(oracle, measure, "square", codes)
     with dg.Engine(measure, width) as e:
-        e.set_option(api.DG_OPT_PANEL_BYTES, 128 * n * (4 if measure == "n_high" else 8))
+        e.set_option(api.DG_OPT_PANEL_BYTES, 256 * n * (4 if measure == "n_high" else 8))
         e.load(0, codes)
         got = e.run_square()
         assert len(e.last_panels) >= 5
