@@ -96,6 +96,9 @@ struct PlaneSet {  // one alignment packed on one device
     uint8_t* codes = nullptr;  // kept only with DG_OPT_KEEP_CODES
     int input_kind = 0;
     bool acgt_from_host = false;
+    uint64_t cap_pad = 0;     // resident sets: record capacity of codes / acgt / tc_ops (buffers are reused across loads)
+    bool lop3_ready = false;  // core / aux hold the current alignment (built lazily: only when the LOP3 engine runs)
+    bool tc_ready = false;    // tc_ops / tc_nN / pp hold the current alignment
     // tcgen05 engine (DG_OPT_ENGINE = 2): int8 one-hot operand planes, N-like counts, partial-code index
     int8_t* tc_ops = nullptr;
     uint32_t* tc_nN = nullptr;
@@ -129,6 +132,13 @@ struct Device {
     size_t out_cap = 0;   // bytes of d_out / h_out
     size_t in_cap = 0;    // records of stream staging
     cudaEvent_t run_start = nullptr, run_stop = nullptr;
+    // load-path scratch, allocated once (no cudaMalloc / cudaFree on the per-load path)
+    uint32_t* pp_cnt = nullptr;     // [width] partial codes per site
+    uint32_t* pp_cursor = nullptr;  // [width]
+    double* pp_work = nullptr;
+    uint32_t* h_pp_total = nullptr; // pinned {entries}
+    double* h_pp_work = nullptr;    // pinned
+    cudaEvent_t chunk_ev[32] = {};
     unsigned long long* d_invalid = nullptr;  // [3]: ring slot 0, ring slot 1, resident loads
     unsigned long long* h_invalid = nullptr;  // [3] pinned mirror
 };
@@ -322,57 +332,56 @@ void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
 }
 
 // Enqueue (no sync) the int8 operand planes + N-like counts of the first `n` records of the set.
-void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, cudaStream_t st) {
+void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, bool count_acgt,
+                     cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr) {
     const TcSchedule& sch = tc_schedule(c->fam);
+    // rows [row0, row0 + n) of the set; the last chunk also zero-fills the padding rows up to a multiple of 128
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
-    CUDA_CHECK(cudaMemsetAsync(s.tc_nN, 0, (size_t)n_pad * 4, st));
+    CUDA_CHECK(cudaMemsetAsync(s.tc_nN + row0, 0, (size_t)n_pad * 4, st));
+    if (count_acgt) CUDA_CHECK(cudaMemsetAsync(s.acgt + row0 * 4, 0, (size_t)n_pad * 16, st));
     tc::PackI8Params pp{};
-    pp.codes = d_codes; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
-    pp.ops = s.tc_ops; pp.nN = s.tc_nN; pp.ascii = input_kind == DG_INPUT_ASCII;
+    pp.codes = d_codes + row0 * c->width; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
+    pp.ops = s.tc_ops + (size_t)row0 * sch.nplanes * s.tc_wp8; pp.nN = s.tc_nN + row0;
+    pp.invalid = d_inv; pp.seq0 = row0;
+    pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
     const uint64_t total = n_pad * (s.tc_wp8 / 16);
     tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32), 256, 0, st>>>(pp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.pack_launches++;
+    if (count_acgt) {
+        tc::acgt_count_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(pp.codes, n, c->width, pp.ascii, s.acgt + row0 * 4);
+        CUDA_CHECK(cudaGetLastError());
+        c->tm.pack_launches++;
+    }
 }
 
-// Inverted index of the partial ambiguity codes of a resident alignment (counting sort by site; syncs).
-void build_pp_index(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
-    if (s.pp.entries) { cudaFree(s.pp.entries); s.pp.entries = nullptr; }
-    if (s.pp.site_off) { cudaFree(s.pp.site_off); s.pp.site_off = nullptr; }
-    uint32_t *cnt = nullptr, *cursor = nullptr;
-    double* d_work = nullptr;
+// Inverted index of the partial ambiguity codes of a resident alignment: the per-site counts were
+// accumulated by pp_count_kernel while the chunks arrived; scan them, then scatter the entries
+// (counting sort by site).  Synchronises the stream: the entry count sizes the allocation.
+void finish_pp_index(dg_ctx* c, Device& d, PlaneSet& s, cudaStream_t st) {
+    if (!s.pp.site_off) CUDA_CHECK(cudaMalloc(&s.pp.site_off, (size_t)(c->width + 1) * 4));
     const int ascii = s.input_kind == DG_INPUT_ASCII;
-    CUDA_CHECK(cudaMalloc(&cnt, (size_t)c->width * 4));
-    CUDA_CHECK(cudaMalloc(&cursor, (size_t)c->width * 4));
-    CUDA_CHECK(cudaMalloc(&d_work, 8));
-    CUDA_CHECK(cudaMalloc(&s.pp.site_off, (size_t)(c->width + 1) * 4));
-    CUDA_CHECK(cudaMemsetAsync(cnt, 0, (size_t)c->width * 4, st));
-    const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
-    tc::pp_count_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, ascii, cnt);
-    tc::pp_scan_kernel<<<1, 1024, 0, st>>>(cnt, c->width, s.pp.site_off, cursor, d_work);
+    tc::pp_scan_kernel<<<1, 1024, 0, st>>>(d.pp_cnt, c->width, s.pp.site_off, d.pp_cursor, d.pp_work);
     CUDA_CHECK(cudaGetLastError());
-    uint32_t total_entries = 0;
-    CUDA_CHECK(cudaMemcpyAsync(&total_entries, s.pp.site_off + c->width, 4, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaMemcpyAsync(&s.pp.pair_work, d_work, 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(d.h_pp_total, s.pp.site_off + c->width, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(d.h_pp_work, d.pp_work, 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    s.pp.n_entries = total_entries;
-    CUDA_CHECK(cudaMalloc(&s.pp.entries, (size_t)std::max<uint32_t>(1, total_entries) * 8));
-    if (total_entries) {
-        tc::pp_fill_kernel<<<gb, 256, 0, st>>>(d_codes, s.n, c->width, ascii, cursor, s.pp.entries);
+    s.pp.n_entries = *d.h_pp_total;
+    s.pp.pair_work = *d.h_pp_work;
+    if (s.pp.n_entries > s.pp.cap_entries || !s.pp.entries) {  // grows rarely: reloads of similar data reuse it
+        if (s.pp.entries) cudaFree(s.pp.entries);
+        s.pp.entries = nullptr;
+        s.pp.cap_entries = std::max<uint32_t>(1024, s.pp.n_entries + s.pp.n_entries / 4);
+        CUDA_CHECK(cudaMalloc(&s.pp.entries, (size_t)s.pp.cap_entries * 8));
+    }
+    if (s.pp.n_entries) {
+        const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
+        tc::pp_fill_kernel<<<gb, 256, 0, st>>>(s.codes, s.n, c->width, ascii, d.pp_cursor, s.pp.entries);
         CUDA_CHECK(cudaGetLastError());
     }
-    c->tm.pack_launches += 3;
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaFree(cnt); cudaFree(cursor); cudaFree(d_work);
-}
-
-void build_tc_operands(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, cudaStream_t st) {
-    alloc_tc_operands(c, s);
-    enqueue_tc_pack(c, s, d_codes, s.n, s.input_kind, st);
-    if (tc_schedule(c->fam).needs_pp) build_pp_index(c, s, d_codes, st);
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    c->tm.pack_launches += 2;
 }
 
 int g_num_sms(int dev) {
@@ -386,7 +395,7 @@ int g_num_sms(int dev) {
 // GEMM (adversarially ambiguous alignments stay on the LOP3 tiles, which need no correction).
 bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
     if (c->engine == 1) return false;
-    if (!A.tc_ops || !B.tc_ops) {
+    if (!A.tc_ready || !B.tc_ready) {
         if (c->engine == 2) fail(DG_ERR_STATE, "tensor-engine operands were not built (set DG_OPT_ENGINE before loading)");
         return false;
     }
@@ -406,23 +415,29 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
     tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tc::TN) : 0;
     tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
-    const int cl = c->tile_variant == 2 ? 2 : 1;  // tile variant 2 = the 2-CTA cluster kernel with TMA multicast of B
-    tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl - 1) / (tc::TM * cl));
+    // tile variants: 0 = 256 x 256 block per CTA (two A sub-tiles, default), 1 = 128 x 256 per CTA,
+    //                2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of the shared B tile
+    const int cl = c->tile_variant == 2 ? 2 : 1;
+    const int mt = c->tile_variant == 0 ? 2 : 1;
+    tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl * mt - 1) / (tc::TM * cl * mt));
     tp.n_total = A.n; tp.out_base = p.out_base;
     tp.out = out;
     tp.width = (uint32_t)c->width; tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
     tp.npairs = (uint32_t)sch.npairs[acc];
     for (int i = 0; i < sch.npairs[acc]; i++) { tp.pa[i] = sch.pa[acc][i]; tp.pb[i] = sch.pb[acc][i]; }
     tp.raw_sums = raw_sums ? 1 : 0;
+    tp.stages = mt == 2 ? tc::StageCfg<2>::N : tc::StageCfg<1>::N;
+    if (const char* e = std::getenv("DG_TC_STAGES")) tp.stages = (uint32_t)std::min<int>((int)tp.stages, std::max(1, std::atoi(e)));
     if (tp.gx == 0 || tp.gy == 0) return;
     const uint64_t tiles = (uint64_t)tp.gx * tp.gy;
     if (cl == 1) {
-        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        auto kern = mt == 2 ? tc::tc_gemm_kernel<1, 2> : tc::tc_gemm_kernel<1, 1>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         const unsigned grid = (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id));
-        tc::tc_gemm_kernel<1><<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_a, tp);
+        kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_a, tp);
         CUDA_CHECK(cudaGetLastError());
     } else {
-        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id) / 2));
         cfg.blockDim = dim3(tc::THREADS);
@@ -432,7 +447,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::tc_gemm_kernel<2>, A.map_a, B.map_a, tp));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::tc_gemm_kernel<2, 1>, A.map_a, B.map_a, tp));
     }
     c->tm.count_launches++;
     if (acc == 0 && sch.needs_pp && A.pp.n_entries && B.pp.n_entries) {
@@ -544,6 +559,45 @@ void harvest_kernel_time(dg_ctx* c, Slot& s) {
     if (cudaEventElapsedTime(&ms, s.k_start, s.k_stop) == cudaSuccess) c->tm.count_ms += ms;
 }
 
+
+// ---- resident alignments: buffer reuse, pipelined upload, lazy LOP3 planes ---------------------------
+// (Re)size the buffers of a resident alignment; buffers are kept when the new alignment fits.
+void reserve_resident(dg_ctx* c, PlaneSet& s, uint64_t n, bool want_tc) {
+    const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
+    const bool fits = s.codes && s.cap_pad >= n_pad && (!want_tc || s.tc_ops);
+    if (!fits) {
+        free_set(s);
+        s.cap_pad = n_pad;
+        CUDA_CHECK(cudaMalloc(&s.codes, (size_t)n_pad * c->width));
+        CUDA_CHECK(cudaMalloc(&s.acgt, (size_t)n_pad * 4 * sizeof(uint32_t)));
+        if (want_tc) {
+            s.n = n; s.n_pad = n_pad;
+            alloc_tc_operands(c, s);
+        }
+    }
+    s.n = n;
+    s.n_pad = n_pad;
+    s.lop3_ready = false;
+    s.tc_ready = false;
+}
+
+// Build the LOP3 bit-planes of a resident alignment from its device-resident codes, once, on demand.
+void ensure_lop3(dg_ctx* c, Device& d, PlaneSet& s) {
+    if (s.lop3_ready) return;
+    CUDA_CHECK(cudaSetDevice(d.id));
+    const size_t plane_bytes = (size_t)s.cap_pad * c->wp * sizeof(uint4);
+    if (!s.core) CUDA_CHECK(cudaMalloc(&s.core, plane_bytes));
+    if (!s.aux && c->fam != FAM_SNP) CUDA_CHECK(cudaMalloc(&s.aux, plane_bytes));
+    CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
+    enqueue_pack(c, d.d_invalid + 2, s, s.codes, s.n, s.input_kind, !s.acgt_from_host, false, d.compute);
+    CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
+    CUDA_CHECK(cudaStreamSynchronize(d.compute));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
+    c->tm.pack_ms += ms;
+    s.lop3_ready = true;
+}
+
 // ---- square / rect runs ------------------------------------------------------------------------
 void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user,
               uint32_t flags) {
@@ -564,15 +618,19 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         CUDA_CHECK(cudaStreamWaitEvent(d.compute2, d.run_start, 0));
     }
 
-    if (flags & DG_RUN_REPACK) {
+    const bool tc_run = use_tc(c, c->devs[0].set[0], c->devs[0].set[wb]);
+    c->last_engine = tc_run ? 2 : 1;
+    if (!tc_run)
+        for (auto& d : c->devs)
+            for (int w = 0; w <= wb; w++) ensure_lop3(c, d, d.set[w]);
+    if (flags & DG_RUN_REPACK) {  // re-run the operand packing of the engine in use from the resident codes
         for (auto& d : c->devs) {
             CUDA_CHECK(cudaSetDevice(d.id));
             for (int w = 0; w <= wb; w++) {
                 PlaneSet& s = d.set[w];
-                if (!s.codes) fail(DG_ERR_STATE, "DG_RUN_REPACK needs DG_OPT_KEEP_CODES before loading");
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
-                enqueue_pack(c, d.d_invalid + 2, s, s.codes, s.n, s.input_kind, !s.acgt_from_host, false, d.compute);
-                if (s.tc_ops) enqueue_tc_pack(c, s, s.codes, s.n, s.input_kind, d.compute);
+                if (tc_run) enqueue_tc_pack(c, s, s.codes, s.n, s.input_kind, !s.acgt_from_host && c->fam == FAM_TN93, d.compute);
+                else enqueue_pack(c, d.d_invalid + 2, s, s.codes, s.n, s.input_kind, !s.acgt_from_host, false, d.compute);
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
                 CUDA_CHECK(cudaEventSynchronize(d.slot[0].p_stop));
                 float ms = 0;
@@ -591,8 +649,6 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         if (k % n_parts == part) mine.push_back(all[k]);
     size_t max_bytes = 0;
     for (auto& p : mine) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
-    const bool tc_run = use_tc(c, c->devs[0].set[0], c->devs[0].set[wb]);
-    c->last_engine = tc_run ? 2 : 1;
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
@@ -704,7 +760,9 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     const bool needs_pp = tc_schedule(c->fam).needs_pp;
     if (c->engine == 2 && needs_pp)
         fail(DG_ERR_INVALID_ARG, "engine 2 covers -s streaming for k80 / tn93 only; use engine 0 or 1 for this measure");
-    const bool s_tc = c->engine != 1 && !needs_pp && c->devs[0].set[0].tc_ops != nullptr;
+    const bool s_tc = c->engine != 1 && !needs_pp && c->devs[0].set[0].tc_ready;
+    if (!s_tc)
+        for (auto& d : c->devs) ensure_lop3(c, d, d.set[0]);
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
@@ -768,7 +826,7 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     Panel p;
     p.row0 = 0; p.row1 = nb; p.out_base = 0;
     p.n_results = nb * d.set[0].n;
-    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, cst);
+    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, false, cst);
     CUDA_CHECK(cudaEventRecord(s.k_start, cst));
     if (c->s_tc) enqueue_panel_tc(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, s.d_scratch, true, false, cst);
     else enqueue_panel_kernel<false>(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, true, cst);
@@ -834,6 +892,12 @@ void destroy_device(Device& d) {
         for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop})
             if (e) cudaEventDestroy(e);
     }
+    if (d.pp_cnt) cudaFree(d.pp_cnt);
+    if (d.pp_cursor) cudaFree(d.pp_cursor);
+    if (d.pp_work) cudaFree(d.pp_work);
+    if (d.h_pp_total) cudaFreeHost(d.h_pp_total);
+    if (d.h_pp_work) cudaFreeHost(d.h_pp_work);
+    for (auto& e : d.chunk_ev) if (e) cudaEventDestroy(e);
     if (d.run_start) cudaEventDestroy(d.run_start);
     if (d.run_stop) cudaEventDestroy(d.run_stop);
     if (d.d_invalid) cudaFree(d.d_invalid);
@@ -921,6 +985,12 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
                     CUDA_CHECK(cudaEventCreate(e));
             CUDA_CHECK(cudaEventCreate(&d.run_start));
             CUDA_CHECK(cudaEventCreate(&d.run_stop));
+            CUDA_CHECK(cudaMalloc(&d.pp_cnt, (size_t)width * 4));
+            CUDA_CHECK(cudaMalloc(&d.pp_cursor, (size_t)width * 4));
+            CUDA_CHECK(cudaMalloc(&d.pp_work, 8));
+            CUDA_CHECK(cudaHostAlloc(&d.h_pp_total, 4, cudaHostAllocDefault));
+            CUDA_CHECK(cudaHostAlloc(&d.h_pp_work, 8, cudaHostAllocDefault));
+            for (auto& e : d.chunk_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             CUDA_CHECK(cudaMemcpyToSymbol(c_ascii_lut, lut, 256));
             CUDA_CHECK(cudaMemcpyToSymbol(c_valid_code, valid, 32));
             CUDA_CHECK(cudaMalloc(&d.d_invalid, 3 * sizeof(unsigned long long)));
@@ -984,43 +1054,67 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
             c32.resize(n * 4);
             for (uint64_t i = 0; i < n * 4; i++) c32[i] = (uint32_t)acgt_counts[i];
         }
+        const bool want_tc = ctx->engine != 1;
+        const bool needs_pp = tc_schedule(ctx->fam).needs_pp;
+        const bool trace = std::getenv("DG_TRACE") != nullptr;
+        const double t_begin = wall_ms();
         for (auto& d : ctx->devs) {
             CUDA_CHECK(cudaSetDevice(d.id));
             PlaneSet& s = d.set[which];
-            free_set(s);
-            alloc_set(ctx, s, n, true);
+            reserve_resident(ctx, s, n, want_tc);
             s.input_kind = input_kind;
             s.acgt_from_host = acgt_counts != nullptr;
-            const double th = wall_ms();
-            CUDA_CHECK(cudaMemcpyAsync(s.codes, codes, (size_t)n * ctx->width, cudaMemcpyHostToDevice, d.compute));
-            CUDA_CHECK(cudaStreamSynchronize(d.compute));
-            ctx->tm.h2d_ms += wall_ms() - th;
-            ctx->tm.h2d_bytes += n * ctx->width;
-            CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
-            enqueue_pack(ctx, d.d_invalid + 2, s, s.codes, n, input_kind, acgt_counts == nullptr, false, d.compute);
-            CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
-            if (acgt_counts) {
-                CUDA_CHECK(cudaMemsetAsync(s.acgt, 0, (size_t)s.n_pad * 16, d.compute));
-                CUDA_CHECK(cudaMemcpyAsync(s.acgt, c32.data(), (size_t)n * 16, cudaMemcpyHostToDevice, d.compute));
-            }
-            CUDA_CHECK(cudaStreamSynchronize(d.compute));
-            float ms = 0;
-            CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
-            ctx->tm.pack_ms += ms;
+            // Upload in chunks on the copy stream; each chunk is packed on the compute stream as soon as
+            // it has landed, so packing hides behind the PCIe transfer of the next chunk.
+            const uint64_t target = std::max<uint64_t>(48ull << 20, n * ctx->width / 30);  // <= 32 chunks
+            const uint64_t chunk = std::max<uint64_t>(ROW_ALIGN, (target / ctx->width + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN);
+            uint32_t* pp_cnt = d.pp_cnt;
+            int n_ev = 0;
             try {
+                if (want_tc && needs_pp) CUDA_CHECK(cudaMemsetAsync(pp_cnt, 0, (size_t)ctx->width * 4, d.compute));
+                const double th = wall_ms();
+                CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
+                for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+                    const uint64_t nr = std::min(chunk, n - r0);
+                    CUDA_CHECK(cudaMemcpyAsync(s.codes + r0 * ctx->width, codes + r0 * ctx->width, (size_t)nr * ctx->width,
+                                               cudaMemcpyHostToDevice, d.copy_in));
+                    cudaEvent_t ev = d.chunk_ev[n_ev++ & 31];
+                    CUDA_CHECK(cudaEventRecord(ev, d.copy_in));
+                    CUDA_CHECK(cudaStreamWaitEvent(d.compute, ev, 0));
+                    if (want_tc) {
+                        enqueue_tc_pack(ctx, s, s.codes, nr, input_kind, !acgt_counts && ctx->fam == FAM_TN93, d.compute, r0,
+                                        d.d_invalid + 2);
+                        if (needs_pp) {
+                            const unsigned gb = (unsigned)std::min<uint64_t>((nr * ctx->width + 255) / 256, 148 * 32);
+                            tc::pp_count_kernel<<<gb, 256, 0, d.compute>>>(s.codes + r0 * ctx->width, nr, ctx->width,
+                                                                           input_kind == DG_INPUT_ASCII, pp_cnt);
+                            CUDA_CHECK(cudaGetLastError());
+                            ctx->tm.pack_launches++;
+                        }
+                    }
+                }
+                if (acgt_counts) {
+                    CUDA_CHECK(cudaMemsetAsync(s.acgt, 0, (size_t)s.n_pad * 16, d.compute));
+                    CUDA_CHECK(cudaMemcpyAsync(s.acgt, c32.data(), (size_t)n * 16, cudaMemcpyHostToDevice, d.compute));
+                }
+                if (want_tc && needs_pp) finish_pp_index(ctx, d, s, d.compute);   // scan + fill (one sync for the entry count)
+                CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
+                CUDA_CHECK(cudaStreamSynchronize(d.copy_in));
+                CUDA_CHECK(cudaStreamSynchronize(d.compute));
+                ctx->tm.h2d_ms += wall_ms() - th;
+                ctx->tm.h2d_bytes += n * ctx->width;
+                float ms = 0;
+                CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
+                ctx->tm.pack_ms += ms;  // device span of the pipelined upload + packing
+                s.tc_ready = want_tc;
+                if (!want_tc) ensure_lop3(ctx, d, s);  // engine 1: build the bit-planes now (also validates the bytes)
                 check_invalid(ctx, d, codes, 0);
-                if (ctx->engine != 1) build_tc_operands(ctx, s, s.codes, d.compute);
             } catch (...) {
-                free_set(s);
-                throw;
-            }
-            if (!ctx->keep_codes) { cudaFree(s.codes); s.codes = nullptr; }
-            try {
-            } catch (...) {
-                free_set(s);
+                s.n = 0; s.tc_ready = false; s.lop3_ready = false;
                 throw;
             }
         }
+        if (trace) fprintf(stderr, "[dg_load_resident] %llu records: %.3f ms\n", (unsigned long long)n, wall_ms() - t_begin);
     });
 }
 
@@ -1127,11 +1221,14 @@ int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
                     }
                 } catch (...) { cudaFree(scratch); throw; }
                 cudaFree(scratch);
-            } else
+            } else {
+            ensure_lop3(ctx, d, d.set[which_a]);
+            ensure_lop3(ctx, d, d.set[which_b]);
             for (uint64_t r = 0; r < A.n; r += step) {
                 Panel q = p;
                 q.row0 = r; q.row1 = std::min<uint64_t>(A.n, r + step);
                 enqueue_panel_kernel<true>(ctx, d, A, B, DG_MODE_RECT, q, dbuf + r * B.n, false, d.compute);
+            }
             }
             CUDA_CHECK(cudaStreamSynchronize(d.compute));
             CUDA_CHECK(cudaMemcpy(out, dbuf, bytes, cudaMemcpyDeviceToHost));
@@ -1148,8 +1245,9 @@ int dg_debug_planes(dg_ctx* ctx, int which, uint32_t* core, uint32_t* aux, uint6
         if (which < 0 || which > 1) fail(DG_ERR_INVALID_ARG, "which must be 0 or 1");
         Device& d = ctx->devs[0];
         CUDA_CHECK(cudaSetDevice(d.id));
+        if (d.set[which].n == 0) fail(DG_ERR_STATE, "alignment not loaded");
+        ensure_lop3(ctx, d, d.set[which]);
         const PlaneSet& s = d.set[which];
-        if (s.n == 0) fail(DG_ERR_STATE, "alignment not loaded");
         if (words_out) *words_out = ctx->wp;
         const size_t bytes = (size_t)s.n * ctx->wp * 16;
         if (core) CUDA_CHECK(cudaMemcpy(core, s.core, bytes, cudaMemcpyDeviceToHost));

@@ -44,11 +44,14 @@ namespace tc {
 constexpr int TM = 128;          // tile rows    (UMMA M)
 constexpr int TN = 256;          // tile columns (UMMA N)
 constexpr int KB = 128;          // K bytes per stage = one 128B swizzle atom = 128 sites of one plane
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;        // barrier slots; MT = 1 uses 4 stages of 48 KB, MT = 2 uses 3 stages of 64 KB
 constexpr int A_BYTES = TM * KB;
 constexpr int B_BYTES = TN * KB;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align slack*/ + 256 /*barriers*/;
+template <int MT> struct StageCfg {
+    static constexpr int BYTES = MT * A_BYTES + B_BYTES;
+    static constexpr int N = (192 * 1024) / BYTES;   // 4 or 3
+};
 constexpr int THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel traps instead of hanging
 
@@ -150,6 +153,8 @@ struct PackI8Params {
     int ascii;
     int nplanes;
     uint8_t plane_id[MAX_PLANES];
+    unsigned long long* invalid;  // min over ((seq0 + record) << 32 | site) of invalid bytes; or NULL
+    uint64_t seq0;                // global index of record 0 of this chunk
 };
 
 // bit i of the result = value of plane id i for Paradis code c
@@ -183,7 +188,13 @@ __global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
             const uint64_t s = s0 + k;
             if (seq < p.n && s < p.width) {
                 uint32_t c = p.codes[seq * p.width + s];
-                if (p.ascii) c = c_ascii_lut[c];
+                bool ok;
+                if (p.ascii) { c = c_ascii_lut[c]; ok = c != 0; }
+                else ok = (c_valid_code[c >> 5] >> (c & 31)) & 1u;
+                if (!ok) {
+                    if (p.invalid) atomicMin(p.invalid, ((unsigned long long)(p.seq0 + seq) << 32) | (unsigned long long)s);
+                    c = 240;
+                }
                 bits[k] = plane_bits(c);
                 nn += (bits[k] >> P_NL) & 1u;
             }
@@ -202,12 +213,33 @@ __global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
     }
 }
 
+// count_bases (fastaio.rs:53-66) for tn93 when the LOP3 planes are not built: one warp per record,
+// histogram of the codes 136 / 24 / 72 / 40 -> acgt[record] = {A, T, G, C}.
+__global__ void __launch_bounds__(256) acgt_count_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* acgt) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const uint8_t* row = codes + warp * width;
+    uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
+    for (uint64_t s = lane; s < width; s += 32) {
+        uint32_t c = row[s];
+        if (ascii) c = c_ascii_lut[c];
+        cA += c == 136; cT += c == 24; cG += c == 72; cC += c == 40;
+    }
+    for (int o = 16; o; o >>= 1) {
+        cA += __shfl_xor_sync(0xffffffffu, cA, o); cT += __shfl_xor_sync(0xffffffffu, cT, o);
+        cG += __shfl_xor_sync(0xffffffffu, cG, o); cC += __shfl_xor_sync(0xffffffffu, cC, o);
+    }
+    if (lane == 0) *reinterpret_cast<uint4*>(acgt + warp * 4) = make_uint4(cA, cT, cG, cC);
+}
+
 // ---- inverted index of partial ambiguity codes (R Y M W S K V H D B) -----------------------------------
 // entry = site << 36 | record << 4 | possibility nibble
 struct PpIndex {
     uint64_t* entries = nullptr;   // sorted by site (order inside a site is arbitrary)
     uint32_t* site_off = nullptr;  // width + 1 offsets
     uint32_t n_entries = 0;
+    uint32_t cap_entries = 0;
     double pair_work = 0;          // sum over sites of |L_s|^2 (cost of the correction)
 };
 
@@ -295,6 +327,7 @@ struct TcParams {
     uint32_t nsb;          // wp8 / KB
     uint32_t npairs;       // plane pairs summed into this accumulator
     uint8_t pa[8], pb[8];  // stored-plane index of the A / B operand of each pair
+    uint32_t stages;       // pipeline depth in use (<= STAGES; tuning knob)
     int raw_sums;          // 0: out = width - (acc + nN(q) + nN(t))  (n / n_high);  1: out = acc (int32 scratch)
 };
 
@@ -302,14 +335,14 @@ struct TcParams {
 // near-square patch of the pair matrix and share their A / B operand rows through L2.  With CL = 2 a
 // "row block" is the 256-row super-tile of a CTA pair (rank r owns rows [128 r, 128 r + 128) of it).
 constexpr uint32_t RASTER_G = 8;
-template <int CL>
+template <int CL, int MT>
 __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t rank, uint32_t& rowA0, uint32_t& rowB0) {
     const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
     const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
     const uint32_t bx = r / gb, by = band * RASTER_G + (r - bx * gb);
-    const uint32_t rowS0 = p.row0 + by * (TM * CL);
+    const uint32_t rowS0 = p.row0 + by * (TM * MT * CL);
     rowB0 = (p.col_block0 + bx) * TN;
-    rowA0 = rowS0 + rank * TM;
+    rowA0 = rowS0 + rank * (TM * MT);
     if (rowS0 >= p.row_end) return false;
     if (p.square && rowB0 + TN <= rowS0 + 1) return false;   // decided per super-tile: identical in both CTAs
     return true;
@@ -319,13 +352,19 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
 // 128-row half of it and TMA-multicasts it into both CTAs' shared memory, which cuts the L2 -> SM
 // operand traffic per MAC by a third; the MMAs stay cta_group::1.  A stage is free again only when
 // BOTH CTAs' MMAs have retired (multicast tcgen05.commit onto both `empty` barriers, count 2).
-template <int CL>
+// MT = 2: the CTA owns TWO 128-row A sub-tiles against one B tile (a 256 x 256 block of pairs, two
+// accumulators filling all 512 TMEM columns).  The kernel is bound by the operand bytes that fit in
+// flight in shared memory (measured: 2 / 3 / 4 stages = 15.9 / 10.8 / 9.5 ms), and this shape needs a
+// third fewer staged bytes per MAC; the price is a single-buffered accumulator (the epilogue of a tile
+// no longer overlaps the next tile's MMAs, ~2 % of a tile).
+template <int CL, int MT>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    constexpr int STAGE_BYTES = StageCfg<MT>::BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 192 * 1024);
     uint64_t* full = bars;               // [STAGES]
     uint64_t* empty = bars + STAGES;     // [STAGES]
     uint64_t* tfull = bars + 2 * STAGES; // [2]
@@ -361,22 +400,25 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t stage = 0, phase = 0;
             for (uint32_t t = cid; t < ntiles; t += ncl) {
                 uint32_t rowA0, rowB0;
-                if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
+                if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
                 for (uint32_t kt = 0; kt < KT; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
                     const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     const int xb = (int)(p.pb[pr] * p.wp8 + sb * KB);
-                    tma_load_2d(sa, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)rowA0, full + stage);
+#pragma unroll
+                    for (int m = 0; m < MT; m++)
+                        tma_load_2d(sa + m * A_BYTES, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
+                    uint8_t* sbp = sa + MT * A_BYTES;
                     if (CL == 1) {  // both 128-row halves of the B tile
-                        tma_load_2d(sa + A_BYTES, &tmB, xb, (int)rowB0, full + stage);
-                        tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmB, xb, (int)(rowB0 + TN / 2), full + stage);
+                        tma_load_2d(sbp, &tmB, xb, (int)rowB0, full + stage);
+                        tma_load_2d(sbp + B_BYTES / 2, &tmB, xb, (int)(rowB0 + TN / 2), full + stage);
                     } else {        // my half, delivered to both CTAs of the cluster
-                        tma_load_2d_mc(sa + A_BYTES + rank * (B_BYTES / 2), &tmB, xb, (int)(rowB0 + rank * (TN / 2)),
+                        tma_load_2d_mc(sbp + rank * (B_BYTES / 2), &tmB, xb, (int)(rowB0 + rank * (TN / 2)),
                                        full + stage, MC_MASK);
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -386,8 +428,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t stage = 0, phase = 0, it = 0;
             for (uint32_t t = cid; t < ntiles; t += ncl) {
                 uint32_t rowA0, rowB0;
-                if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
-                const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+                if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
+                // MT = 1: two accumulators of 256 columns alternate; MT = 2: both are used by every tile
+                const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
                 mbar_wait(tempty + ab, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + ab * TN;
@@ -395,13 +438,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da = make_smem_desc(sa), db = make_smem_desc(sa + A_BYTES);
+                    const uint64_t db = make_smem_desc(sa + MT * A_BYTES);
 #pragma unroll
                     for (uint32_t k4 = 0; k4 < KB / 32; k4++)
-                        tc_mma_i8(d_tmem, da + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
+#pragma unroll
+                        for (int m = 0; m < MT; m++)
+                            tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
                     if (CL == 1) tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
                     else tc_commit_mc(empty + stage, MC_MASK);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 tc_commit(tfull + ab);         // accumulator ready for the epilogue
                 it++;
@@ -413,11 +458,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t it = 0;
         for (uint32_t t = cid; t < ntiles; t += ncl) {
             uint32_t rowA0, rowB0;
-            if (!tile_live<CL>(p, t, rank, rowA0, rowB0)) continue;
-            const uint32_t ab = it & 1, aphase = (it >> 1) & 1;
+            if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
+            const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(tfull + ab, aphase);
             tc_fence_after();
-            const uint32_t row = rowA0 + quad * 32 + lane;
+#pragma unroll 1
+            for (int m = 0; m < MT; m++) {
+            const uint32_t row = rowA0 + m * TM + quad * 32 + lane;
             const bool row_ok = row < p.row_end;
             const uint32_t nq = (row_ok && !p.raw_sums) ? p.a_nN[row] : 0;
             const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
@@ -425,7 +472,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
             for (uint32_t c = 0; c < TN / 32; c++) {
                 uint32_t v[32];
-                tc_ld32(tmem_base + ((quad * 32u) << 16) + ab * TN + c * 32, v);
+                tc_ld32(tmem_base + ((quad * 32u) << 16) + (ab + m) * TN + c * 32, v);
                 if (row_ok) {
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
@@ -437,6 +484,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         else p.out[idx] = p.width - (v[j] + nq + p.b_nN[col]);
                     }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
