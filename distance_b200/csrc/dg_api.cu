@@ -415,10 +415,12 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
     tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tc::TN) : 0;
     tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
-    // tile variants: 0 = 256 x 256 block per CTA (two A sub-tiles, default), 1 = 128 x 256 per CTA,
-    //                2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of the shared B tile
-    const int cl = c->tile_variant == 2 ? 2 : 1;
-    const int mt = c->tile_variant == 0 ? 2 : 1;
+    // tile variants: 0 = cta_group::2 pairs (default): 512 x 256 block per CTA pair, each CTA stages half of B
+    //                1 = 128 x 256 per CTA,  2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of B,
+    //                3 = 256 x 256 block per CTA (two A sub-tiles, no cluster)
+    const int cl = (c->tile_variant == 2 || c->tile_variant == 0) ? 2 : 1;
+    const int mt = (c->tile_variant == 0 || c->tile_variant == 3) ? 2 : 1;
+    const bool pair = c->tile_variant == 0;
     tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl * mt - 1) / (tc::TM * cl * mt));
     tp.n_total = A.n; tp.out_base = p.out_base;
     tp.out = out;
@@ -426,7 +428,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.npairs = (uint32_t)sch.npairs[acc];
     for (int i = 0; i < sch.npairs[acc]; i++) { tp.pa[i] = sch.pa[acc][i]; tp.pb[i] = sch.pb[acc][i]; }
     tp.raw_sums = raw_sums ? 1 : 0;
-    tp.stages = mt == 2 ? tc::StageCfg<2>::N : tc::StageCfg<1>::N;
+    tp.stages = pair ? tc::StageCfg<2, true>::N : (mt == 2 ? tc::StageCfg<2>::N : tc::StageCfg<1>::N);
     if (const char* e = std::getenv("DG_TC_STAGES")) tp.stages = (uint32_t)std::min<int>((int)tp.stages, std::max(1, std::atoi(e)));
     if (tp.gx == 0 || tp.gy == 0) return;
     const uint64_t tiles = (uint64_t)tp.gx * tp.gy;
@@ -437,7 +439,8 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_a, tp);
         CUDA_CHECK(cudaGetLastError());
     } else {
-        CUDA_CHECK(cudaFuncSetAttribute(tc::tc_gemm_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        auto kern2 = pair ? tc::tc_gemm_kernel<2, 2, true> : tc::tc_gemm_kernel<2, 1, false>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id) / 2));
         cfg.blockDim = dim3(tc::THREADS);
@@ -447,7 +450,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc::tc_gemm_kernel<2, 1>, A.map_a, B.map_a, tp));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, A.map_a, B.map_a, tp));
     }
     c->tm.count_launches++;
     if (acc == 0 && sch.needs_pp && A.pp.n_entries && B.pp.n_entries) {
@@ -509,7 +512,7 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
     if (rows_major == 0 || n_cols == 0) return v;
     uint64_t per = panel_bytes / (elem_bytes * std::max<uint64_t>(1, n_cols));
     per = std::min<uint64_t>(per, (uint64_t)tm * 32768);  // gridDim.y limit
-    const uint64_t quantum = std::max<uint64_t>(tm, 256);  // also a multiple of the tensor engine's 256-row super-tile
+    const uint64_t quantum = std::max<uint64_t>(tm, 512);  // a multiple of every tensor-engine block height (256 / 512 rows)
     per = std::max<uint64_t>(quantum, per / quantum * quantum);
     for (uint64_t r = 0; r < rows_major; r += per) {
         Panel p;

@@ -48,9 +48,9 @@ constexpr int STAGES = 4;        // barrier slots; MT = 1 uses 4 stages of 48 KB
 constexpr int A_BYTES = TM * KB;
 constexpr int B_BYTES = TN * KB;
 constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align slack*/ + 256 /*barriers*/;
-template <int MT> struct StageCfg {
-    static constexpr int BYTES = MT * A_BYTES + B_BYTES;
-    static constexpr int N = (192 * 1024) / BYTES;   // 4 or 3
+template <int MT, bool PAIR = false> struct StageCfg {
+    static constexpr int BYTES = MT * A_BYTES + (PAIR ? B_BYTES / 2 : B_BYTES);  // a pair CTA stages only its half of B
+    static constexpr int N = (192 * 1024) / BYTES < STAGES ? (192 * 1024) / BYTES : STAGES;
 };
 constexpr int THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel traps instead of hanging
@@ -88,6 +88,33 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "h"(mask) : "memory");
+}
+// 2-SM (cta_group::2) TMA load: the bytes land in MY shared memory, the transaction count goes to the
+// LEADER CTA's barrier at the same offset (peer bit 24 of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y) : "memory");
+}
+// arrive on the barrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// one instruction for the CTA pair: D (256 x N, 128 rows in each CTA's TMEM) (+)= A (128 rows from each CTA) * B^T (N/2 rows from each CTA)
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -138,6 +165,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // kind::i8 instruction descriptor: D = S32, A = B = signed int8, both K-major, N = 256, M = 128.
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+constexpr uint32_t IDESC_I8_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);  // M = 256 over two CTAs
 
 // ---- operand packing ------------------------------------------------------------------------------
 // plane ids (value of a plane at a site is 0/1, except NEG_NL which is 0/-1)
@@ -357,13 +385,20 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
 // flight in shared memory (measured: 2 / 3 / 4 stages = 15.9 / 10.8 / 9.5 ms), and this shape needs a
 // third fewer staged bytes per MAC; the price is a single-buffered accumulator (the epilogue of a tile
 // no longer overlaps the next tile's MMAs, ~2 % of a tile).
-template <int CL, int MT>
+// PAIR (with CL = 2): tcgen05 cta_group::2.  The leader CTA issues ONE M = 256 instruction for both SMs;
+// each CTA stages its own A sub-tiles and only ITS 128-row half of the B tile (the tensor cores read the
+// other half from the peer's shared memory), so a stage is 48 KB instead of 64 KB for the same MACs
+// per SM and four stages fit again.  Both CTAs' TMA loads report to the leader's `full` barrier; the
+// leader's commits are multicast onto both CTAs' `empty` / `tfull` barriers; both CTAs' epilogue warps
+// arrive on the leader's `tempty`.
+template <int CL, int MT, bool PAIR = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int STAGE_BYTES = StageCfg<MT>::BYTES;
+    static_assert(!PAIR || CL == 2, "cta_group::2 needs a 2-CTA cluster");
+    constexpr int STAGE_BYTES = StageCfg<MT, PAIR>::BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 192 * 1024);
     uint64_t* full = bars;               // [STAGES]
     uint64_t* empty = bars + STAGES;     // [STAGES]
@@ -379,14 +414,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr uint16_t MC_MASK = (1u << CL) - 1;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, CL); }
-        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, 4); }
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, PAIR ? 1 : CL); }
+        for (int b = 0; b < 2; b++) { mbar_init(tfull + b, 1); mbar_init(tempty + b, PAIR ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -403,10 +443,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
                 for (uint32_t kt = 0; kt < KT; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
-                    mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
                     const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     const int xb = (int)(p.pb[pr] * p.wp8 + sb * KB);
+                    if (PAIR) {
+                        // the leader's barrier counts the bytes of both CTAs
+                        if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * STAGE_BYTES);
+#pragma unroll
+                        for (int m = 0; m < MT; m++)
+                            tma_load_2d_pair(sa + m * A_BYTES, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
+                        tma_load_2d_pair(sa + MT * A_BYTES, &tmB, xb, (int)(rowB0 + rank * (TN / 2)), full + stage);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
+                    mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
 #pragma unroll
                     for (int m = 0; m < MT; m++)
                         tma_load_2d(sa + m * A_BYTES, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
@@ -423,8 +473,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
+        // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
+        if (lane == 0 && (!PAIR || rank == 0)) {
             uint32_t stage = 0, phase = 0, it = 0;
             for (uint32_t t = cid; t < ntiles; t += ncl) {
                 uint32_t rowA0, rowB0;
@@ -442,13 +492,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (uint32_t k4 = 0; k4 < KB / 32; k4++)
 #pragma unroll
-                        for (int m = 0; m < MT; m++)
-                            tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
-                    if (CL == 1) tc_commit(empty + stage);  // frees the smem stage when these MMAs retire
+                        for (int m = 0; m < MT; m++) {
+                            if (PAIR) tc_mma_i8_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8_PAIR, (kt | k4) != 0);
+                            else tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
+                        }
+                    if (PAIR) tc_commit_pair(empty + stage, MC_MASK);   // frees the stage in both CTAs
+                    else if (CL == 1) tc_commit(empty + stage);         // frees the smem stage when these MMAs retire
                     else tc_commit_mc(empty + stage, MC_MASK);
                     if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(tfull + ab);         // accumulator ready for the epilogue
+                if (PAIR) tc_commit_pair(tfull + ab, MC_MASK);  // accumulators ready in both CTAs
+                else tc_commit(tfull + ab);                     // accumulator ready for the epilogue
                 it++;
             }
         }
@@ -488,7 +542,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty + ab);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_remote(tempty + ab, 0);  // the leader's MMA thread waits for both CTAs
+                else mbar_arrive(tempty + ab);
+            }
             it++;
         }
     }
@@ -496,7 +553,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 

@@ -278,11 +278,11 @@ def test_panels_and_parts_cover_the_triangle(dg, oracle, measure):
     from distance_b200 import synth
     from distance_b200 import api
     rng = np.random.default_rng(3)
-    n, width = 1400, 200
+    n, width = 2800, 100
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     want = oracle_run(oracle, measure, "square", codes)
     with dg.Engine(measure, width) as e:
-        e.set_option(api.DG_OPT_PANEL_BYTES, 256 * n * (4 if measure == "n_high" else 8))
+        e.set_option(api.DG_OPT_PANEL_BYTES, 512 * n * (4 if measure == "n_high" else 8))
         e.load(0, codes)
         got = e.run_square()
         assert len(e.last_panels) >= 5
@@ -383,12 +383,12 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
     if ndev < 2:
         pytest.skip("needs >= 2 GPUs")
     rng = np.random.default_rng(21)
-    n, width = 900, 700
+    n, width = 2100, 300
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     for measure in ("n_high", "tn93"):
         want = oracle_run(oracle, measure, "square", codes)
         with dg.Engine(measure, width, gpus=list(range(ndev))) as e:
-            e.set_option(api.DG_OPT_PANEL_BYTES, 128 * n * (4 if measure == "n_high" else 8))
+            e.set_option(api.DG_OPT_PANEL_BYTES, 512 * n * (4 if measure == "n_high" else 8))
             e.load(0, codes)
             got = e.run_square()
             assert len(e.last_panels) >= 2 * ndev

@@ -9,11 +9,14 @@ from distance_b200 import api, synth
 ap = argparse.ArgumentParser()
 ap.add_argument("--big", type=int, default=0, help="records of the 29,903-nt timing run (0 = skip)")
 ap.add_argument("--measure", default="n_high")
+ap.add_argument("--variant", type=int, default=0)
 a = ap.parse_args()
 
 def run(codes, engine, mode="square", codes_b=None, panel=None):
     e = dg.Engine(a.measure, codes.shape[1])
     e.set_option(api.DG_OPT_ENGINE, engine)
+    if engine == 2 and a.variant:
+        e.set_option(api.DG_OPT_TILE_VARIANT, a.variant)
     if panel:
         e.set_option(api.DG_OPT_PANEL_BYTES, panel)
     e.load(0, codes)
@@ -28,7 +31,7 @@ rng = np.random.default_rng(1)
 for (n, w, amb) in [(2, 5, 0.3), (130, 100, 0.3), (300, 1000, 0.5), (700, 333, 0.05), (1000, 4097, 0.9)]:
     codes = synth.random_codes(rng, n, w, p_ambig=amb)
     ref = run(codes, 1)
-    got = run(codes, 2, panel=max(4096, 128 * n * 4))
+    got = run(codes, 2, panel=max(4096, 512 * n * 4))
     bad = int((ref != got).sum())
     print(f"square n={n} w={w} amb={amb}: mismatches {bad} / {ref.size}", flush=True)
     if bad:
@@ -47,6 +50,8 @@ if a.big and ok:
     for eng in (1, 2):
         e = dg.Engine(a.measure, synth.SC2_WIDTH)
         e.set_option(api.DG_OPT_ENGINE, eng)
+        if eng == 2 and a.variant:
+            e.set_option(api.DG_OPT_TILE_VARIANT, a.variant)
         e.load(0, codes)
         e.run_device_only()
         e.reset_timings()
