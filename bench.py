@@ -37,6 +37,10 @@ WIDTH = 29903
 SEED = 20251018 + 2
 # algorithmic 32-bit lane-ops per pair-site (4 LOP3 + 1 POPC + 1 IADD per 32 sites)
 OPS_PER_PAIR_SITE = {"n": 0.1875, "n_high": 0.1875, "raw": 0.28125, "jc69": 0.28125, "k80": 0.5, "tn93": 0.5}
+# tensor engine: int8 ops (2 per MAC) per pair-site of the minimal-rank schedules in tc_engine.cuh / DESIGN.md 3.1
+# (SURVEY 8d budgeted 10 / 10 / 14 / 14; the 4-MAC DIFF and the W/Z factorisation need fewer)
+I8_OPS_PER_PAIR_SITE = {"n": 8, "n_high": 8, "raw": 16, "jc69": 16, "k80": 12, "tn93": 10}
+WORKLOAD = f"config 2: -m {MEASURE} all-vs-all, 20,000 x 29,903 nt (n = round(20000*sqrt(N)) for N GPUs), 1% N/ambiguity/gaps"
 
 
 def load_json(path):
@@ -142,8 +146,8 @@ def run_reference(args):
         "pair_sites_per_s": value * WIDTH, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": f"config 2: -m {MEASURE} all-vs-all, 29,903 nt, 1% N/ambiguity/gaps (bounded CPU sample)",
-                   "measure": MEASURE, "width": WIDTH},
+        "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH,
+                   "reference_arm_sample": sample},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (C oracle), not the Rust binary: no Rust toolchain in this image",
@@ -175,6 +179,8 @@ def run_ours(args):
     eng = dg.Engine(MEASURE, WIDTH, gpus=[d.local_rank])
     eng.set_option(api.DG_OPT_PANEL_BYTES, args.panel_bytes)
     eng.set_option(api.DG_OPT_KEEP_CODES, 1)
+    if not args.u32_results:
+        eng.set_option(api.DG_OPT_RESULT_U16, 1)   # counts <= width < 65536: lossless, half the D2H bytes
     if args.tile_variant:
         eng.set_option(api.DG_OPT_TILE_VARIANT, args.tile_variant)
     if args.engine:
@@ -264,7 +270,7 @@ def run_ours(args):
     if int(tm.get("engine", 1)) == 2:
         # tcgen05 engine: ALGORITHMIC int8 ops (5 MAC = 10 ops per pair-site for n / n_high) of this
         # rank's launches / device time of the step, against the MEASURED kind::i8 issue rate.
-        i8ops = my_pairs * WIDTH * 10.0
+        i8ops = my_pairs * WIDTH * float(I8_OPS_PER_PAIR_SITE[MEASURE])
         ach = i8ops / (run_ms_step * 1e-3) / 1e12
         pk8 = peaks.get("int8_tops_measured")
         src8 = "measured: tools/ubench_tc (profiles/ubench_tc_r01.json), tcgen05.mma kind::i8 M128 N256 K32 SS on 148 SMs"
@@ -275,19 +281,26 @@ def run_ours(args):
             "bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)", "achieved": ach, "peak": pk8,
             "unit": "TOP/s (int8; the spec's TFLOP/s slot)", "frac": ach / pk8,
             "traffic": peaks.get("tc_kernel_dram_bytes_per_launch"),
-            "ops_per_pair_site": 10, "peak_source": src8,
+            "ops_per_pair_site": I8_OPS_PER_PAIR_SITE[MEASURE], "peak_source": src8,
+            "frac_in_survey_units": ach / pk8 * 10.0 / I8_OPS_PER_PAIR_SITE[MEASURE],
             "padded_frac": ach / pk8 * (math.ceil(WIDTH / 128) * 128) / WIDTH,
             "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
-            "note": "engine chosen automatically per shape (DG_OPT_ENGINE=0): tensor cores here; the LOP3+POPC engine "
-                    "stays for alignments dominated by ambiguity codes.  padded_frac counts the 49 zero-padded sites per "
-                    "128-site K block as work done.",
+            "note": "achieved = executed algorithmic int8 ops (4 MAC per pair-site: DIFF as a rank-4 bilinear form, "
+                    "DESIGN.md 3.1) / device time of the whole step (operand re-pack included); frac_in_survey_units "
+                    "scores the same time against SURVEY 8d's 5-MAC budget.  padded_frac counts the 49 zero-padded "
+                    "sites per 128-site K block as work done.  Engine chosen automatically (DG_OPT_ENGINE=0).",
         }
     else:
         roofline = roofline_lop3
     hbm = measured.get("hbm_gbs")
     pack_ms_step = tm["pack_ms"] / args.steps
-    pack_bytes = n * WIDTH + n * math.ceil(WIDTH / 32) * 16  # read 1 B/site, write the 4 core planes
-    roofline_pack = {"bound": "hbm", "kernel": "pack_planes_kernel", "achieved": pack_bytes / (pack_ms_step * 1e-3) / 1e9,
+    if int(tm.get("engine", 1)) == 2:
+        pack_bytes = n * WIDTH + n * 8 * math.ceil(WIDTH / 128) * 128  # read 1 B/site, write 8 int8 planes (U, V)
+        pack_kernel = "pack_i8_kernel"
+    else:
+        pack_bytes = n * WIDTH + n * math.ceil(WIDTH / 32) * 16  # read 1 B/site, write the 4 core bit-planes
+        pack_kernel = "pack_planes_kernel"
+    roofline_pack = {"bound": "hbm", "kernel": pack_kernel, "achieved": pack_bytes / (pack_ms_step * 1e-3) / 1e9,
                      "peak": hbm, "unit": "GB/s", "frac": (pack_bytes / (pack_ms_step * 1e-3) / 1e9 / hbm) if hbm else None,
                      "ms": pack_ms_step}
 
@@ -306,14 +319,14 @@ def run_ours(args):
             "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
             "pair_sites_per_s": value * WIDTH, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int8 one-hot planes, int32 accumulation (tcgen05) / u32 bit-planes (LOP3+POPC); u32 results", "data": "synthetic",
-            "config": {"workload": f"config 2: -m {MEASURE} all-vs-all, {n:,} x 29,903 nt, 1% N/ambiguity/gaps",
-                       "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
+            "vs_baseline": None, "dtype": "i8 (int8 planes, int32 accumulation, tcgen05 kind::i8)" if int(tm.get("engine", 1)) == 2 else "u32 bit-planes (LOP3+POPC)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
                        "weak_scaling": "n = round(20000*sqrt(N)) so pairs per GPU stay ~2.0e8",
                        "panel_bytes": args.panel_bytes, "panels": len(plan),
                        "l2": "inputs larger than L2 (bit-planes %.0f MB vs 126 MB L2)" % (n * 936 * 16 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
-                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * 4)},
+                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * (4 if args.u32_results else 2)),
+                    "result_type": "u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)"},
             "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8"}.get(int(tm.get("engine", 0)), "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -330,12 +343,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the record count (debug)")
-    ap.add_argument("--panel-bytes", type=int, default=256 << 20)
+    ap.add_argument("--panel-bytes", type=int, default=None,
+                    help="result panel size (default: 6.7e7 results per panel = 128 MiB of uint16 / 256 MiB of uint32)")
     ap.add_argument("--tile-variant", type=int, default=0)
     ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
     args = ap.parse_args()
+    if args.panel_bytes is None:
+        args.panel_bytes = (256 << 20) if args.u32_results else (128 << 20)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

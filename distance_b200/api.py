@@ -18,7 +18,8 @@ MEASURES = {"n": 0, "n_high": 1, "raw": 2, "jc69": 3, "k80": 4, "tn93": 5}
 DG_INPUT_PARADIS, DG_INPUT_ASCII = 0, 1
 DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
 DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
-DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE = 1, 2, 3, 4
+DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16 = 1, 2, 3, 4, 5
+DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
           -4: "DG_ERR_INVALID_CODE", -5: "DG_ERR_SINK", -6: "DG_ERR_NOMEM"}
 
@@ -173,6 +174,7 @@ class Engine:
             raise DistanceGpuError(rc, self.L.dg_last_error(None).decode())
         self.h = h
         self.is_int = measure in ("n", "n_high")
+        self.u16 = False
         self._n = [0, 0]
 
     # -- plumbing --------------------------------------------------------------------------------
@@ -199,6 +201,12 @@ class Engine:
 
     def set_option(self, key: int, value: int):
         self._check(self.L.dg_set_option(self.h, key, value))
+        if key == DG_OPT_RESULT_U16:
+            self.u16 = bool(value) and self.is_int
+
+    def _dtype(self):
+        """element type of the result panels (dg_panel.result_kind)"""
+        return (np.uint16 if self.u16 else np.uint32) if self.is_int else np.float64
 
     # -- inputs ----------------------------------------------------------------------------------
     def load(self, which: int, codes: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None):
@@ -217,7 +225,7 @@ class Engine:
 
     # -- runs ------------------------------------------------------------------------------------
     def _collect(self, total: int):
-        dtype = np.uint32 if self.is_int else np.float64
+        dtype = self._dtype()
         out = np.empty(total, dtype=dtype)
         state = {"pos": 0, "panels": []}
 
@@ -249,7 +257,7 @@ class Engine:
 
     def run_part(self, mode: int, part: int, n_parts: int, flags: int = 0):
         """Returns [(row_begin, row_end, values)] for this part's panels."""
-        dtype = np.uint32 if self.is_int else np.float64
+        dtype = self._dtype()
         got = []
 
         def sink(user, pp):
@@ -283,7 +291,7 @@ class Engine:
 
     def stream(self, batches, input_kind: int = DG_INPUT_PARADIS, max_batch: int = 1 << 20, acgt_batches=None):
         """Stream an iterable of (n_b x width) uint8 arrays against alignment 0."""
-        dtype = np.uint32 if self.is_int else np.float64
+        dtype = self._dtype()
         chunks, panels = [], []
 
         def sink(user, pp):

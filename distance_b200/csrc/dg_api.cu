@@ -98,10 +98,9 @@ struct PlaneSet {  // one alignment packed on one device
     bool acgt_from_host = false;
     uint64_t cap_pad = 0;     // resident sets: record capacity of codes / acgt / tc_ops (buffers are reused across loads)
     bool lop3_ready = false;  // core / aux hold the current alignment (built lazily: only when the LOP3 engine runs)
-    bool tc_ready = false;    // tc_ops / tc_nN / pp hold the current alignment
+    bool tc_ready = false;    // tc_ops / pp hold the current alignment
     // tcgen05 engine (DG_OPT_ENGINE = 2): int8 one-hot operand planes, N-like counts, partial-code index
     int8_t* tc_ops = nullptr;
-    uint32_t* tc_nN = nullptr;
     uint64_t tc_wp8 = 0;
     tc::PpIndex pp;
     CUtensorMap map_a{}, map_b{};  // box 128 rows / box 256 rows over tc_ops
@@ -110,8 +109,11 @@ struct PlaneSet {  // one alignment packed on one device
 struct Slot {  // one stage of the result ring (and of the stream-input ring)
     void* d_out = nullptr;
     void* h_out = nullptr;
-    uint32_t* d_scratch = nullptr;  // tcgen05 engine: raw int32 sums, [accumulator][panel pair]
+    int* d_scratch = nullptr;       // tcgen05 engine: raw int32 sums, [accumulator][panel pair]
     size_t scratch_cap = 0;
+    uint32_t* d_tiles = nullptr;    // tcgen05 engine, square panels: live-tile list of this slot's launch
+    uint32_t* h_tiles = nullptr;    // pinned staging of the same
+    size_t tiles_cap = 0;
     cudaEvent_t k_start = nullptr, k_stop = nullptr, copied = nullptr, in_ready = nullptr;
     // stream mode staging
     uint8_t* h_in = nullptr;
@@ -184,15 +186,16 @@ struct dg_ctx {
     std::vector<InFlight> s_queue;  // FIFO of batches not yet sunk
     double s_t0 = 0;
 
-    size_t elem_bytes() const { return measure <= 1 ? 4 : 8; }
-    int result_kind() const { return measure <= 1 ? DG_RESULT_U32 : DG_RESULT_F64; }
+    bool result_u16 = false;  // DG_OPT_RESULT_U16: n / n_high panels hold uint16 counts (needs width <= 65535)
+    bool u16() const { return measure <= 1 && result_u16; }
+    size_t elem_bytes() const { return measure <= 1 ? (u16() ? 2 : 4) : 8; }
+    int result_kind() const { return measure <= 1 ? (u16() ? DG_RESULT_U16 : DG_RESULT_U32) : DG_RESULT_F64; }
 };
 
 namespace {
 
 void free_set(PlaneSet& s) {
     if (s.tc_ops) cudaFree(s.tc_ops);
-    if (s.tc_nN) cudaFree(s.tc_nN);
     if (s.pp.entries) cudaFree(s.pp.entries);
     if (s.pp.site_off) cudaFree(s.pp.site_off);
     if (s.core) cudaFree(s.core);
@@ -202,12 +205,12 @@ void free_set(PlaneSet& s) {
     s = PlaneSet{};
 }
 
-void alloc_set(dg_ctx* c, PlaneSet& s, uint64_t n, bool with_codes) {
+void alloc_set(dg_ctx* c, PlaneSet& s, uint64_t n, bool with_codes, bool lop3_planes = true) {
     s.n = n;
     s.n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     const size_t plane_bytes = (size_t)s.n_pad * c->wp * sizeof(uint4);
-    CUDA_CHECK(cudaMalloc(&s.core, plane_bytes));
-    if (c->fam != FAM_SNP) CUDA_CHECK(cudaMalloc(&s.aux, plane_bytes));
+    if (lop3_planes) CUDA_CHECK(cudaMalloc(&s.core, plane_bytes));
+    if (lop3_planes && c->fam != FAM_SNP) CUDA_CHECK(cudaMalloc(&s.aux, plane_bytes));
     CUDA_CHECK(cudaMalloc(&s.acgt, (size_t)s.n_pad * 4 * sizeof(uint32_t)));
     if (with_codes) CUDA_CHECK(cudaMalloc(&s.codes, (size_t)std::max<uint64_t>(1, n * c->width)));
 }
@@ -303,58 +306,53 @@ struct TcSchedule {
     uint8_t plane_id[tc::MAX_PLANES];
     int nacc;
     int npairs[5];
-    uint8_t pa[5][8], pb[5][8];
+    uint8_t pa[5][4], pb[5][4];
     bool needs_pp;  // the n/n_high sum needs the both-partial correction
 };
 
 const TcSchedule& tc_schedule(int fam) {
     using namespace tc;
-    static const TcSchedule snp = {6, {P_MA, P_MG, P_MC, P_MT, P_NL, P_NEG_NL}, 1, {5},
-                                   {{0, 1, 2, 3, 4}}, {{0, 1, 2, 3, 5}}, true};
-    static const TcSchedule raw = {10, {P_MA, P_MG, P_MC, P_MT, P_NL, P_NEG_NL, P_KA, P_KG, P_KC, P_KT}, 2, {5, 4},
-                                   {{0, 1, 2, 3, 4}, {6, 7, 8, 9}}, {{0, 1, 2, 3, 5}, {6, 7, 8, 9}}, true};
-    static const TcSchedule k80 = {8, {P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_PURC, P_PYRC}, 3, {4, 2, 2},
-                                   {{0, 1, 2, 3}, {4, 5}, {6, 7}}, {{0, 1, 2, 3}, {4, 5}, {7, 6}}, false};
-    static const TcSchedule tn93 = {7, {P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_K}, 5, {1, 1, 1, 2, 2},
-                                    {{6}, {4}, {5}, {0, 1}, {2, 3}}, {{6}, {4}, {5}, {0, 1}, {2, 3}}, false};
+    static const TcSchedule snp = {8, {P_UA, P_UG, P_UC, P_UT, P_VA, P_VG, P_VC, P_VT}, 1, {4},
+                                   {{0, 1, 2, 3}}, {{4, 5, 6, 7}}, true};
+    static const TcSchedule raw = {12, {P_UA, P_UG, P_UC, P_UT, P_VA, P_VG, P_VC, P_VT, P_KA, P_KG, P_KC, P_KT}, 2, {4, 4},
+                                   {{0, 1, 2, 3}, {8, 9, 10, 11}}, {{4, 5, 6, 7}, {8, 9, 10, 11}}, true};
+    static const TcSchedule k80 = {6, {P_PURK, P_PYRK, P_W, P_Z, P_PURC, P_PYRC}, 3, {2, 2, 2},
+                                   {{0, 1}, {2, 3}, {4, 5}}, {{0, 1}, {2, 3}, {5, 4}}, false};
+    static const TcSchedule tn93 = {5, {P_K, P_PURK, P_PYRK, P_W, P_Z}, 5, {1, 1, 1, 1, 1},
+                                    {{0}, {1}, {2}, {3}, {4}}, {{0}, {1}, {2}, {3}, {4}}, false};
     return fam == FAM_SNP ? snp : (fam == FAM_RAW ? raw : (fam == FAM_K80 ? k80 : tn93));
 }
+// first stored plane of the V operand (pp_correct_scan_kernel reads the partial codes back from it)
+constexpr uint32_t TC_VPLANE0 = 4;
 
 void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
     const TcSchedule& sch = tc_schedule(c->fam);
     const uint64_t wp8 = (c->width + tc::KB - 1) / tc::KB * tc::KB;
     s.tc_wp8 = wp8;
     CUDA_CHECK(cudaMalloc(&s.tc_ops, (size_t)s.n_pad * sch.nplanes * wp8));
-    CUDA_CHECK(cudaMalloc(&s.tc_nN, (size_t)s.n_pad * 4));
     const uint64_t row_bytes = (uint64_t)sch.nplanes * wp8;
     make_ops_map(&s.map_a, s.tc_ops, row_bytes, s.n_pad, tc::TM);
     make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, tc::TN);
 }
 
-// Enqueue (no sync) the int8 operand planes + N-like counts of the first `n` records of the set.
+// Enqueue (no sync) the int8 operand planes (and, with count_acgt, the per-record A,T,G,C counts) of rows
+// [row0, row0 + n) of the set; the chunk's padding rows up to a multiple of 128 are zero-filled.
 void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, bool count_acgt,
-                     cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr) {
+                     cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr, bool upper_ascii = false) {
     const TcSchedule& sch = tc_schedule(c->fam);
-    // rows [row0, row0 + n) of the set; the last chunk also zero-fills the padding rows up to a multiple of 128
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
-    CUDA_CHECK(cudaMemsetAsync(s.tc_nN + row0, 0, (size_t)n_pad * 4, st));
-    if (count_acgt) CUDA_CHECK(cudaMemsetAsync(s.acgt + row0 * 4, 0, (size_t)n_pad * 16, st));
     tc::PackI8Params pp{};
     pp.codes = d_codes + row0 * c->width; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
-    pp.ops = s.tc_ops + (size_t)row0 * sch.nplanes * s.tc_wp8; pp.nN = s.tc_nN + row0;
+    pp.ops = s.tc_ops + (size_t)row0 * sch.nplanes * s.tc_wp8;
+    pp.acgt = count_acgt ? s.acgt + row0 * 4 : nullptr;
+    pp.count_upper_ascii = upper_ascii && input_kind == DG_INPUT_ASCII ? 1 : 0;
     pp.invalid = d_inv; pp.seq0 = row0;
     pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
-    const uint64_t total = n_pad * (s.tc_wp8 / 16);
-    tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>((total + 255) / 256, 148 * 32), 256, 0, st>>>(pp);
+    tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.pack_launches++;
-    if (count_acgt) {
-        tc::acgt_count_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(pp.codes, n, c->width, pp.ascii, s.acgt + row0 * 4);
-        CUDA_CHECK(cudaGetLastError());
-        c->tm.pack_launches++;
-    }
 }
 
 // Inverted index of the partial ambiguity codes of a resident alignment: the per-site counts were
@@ -405,11 +403,11 @@ bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
     return work <= 2.0 * (double)A.n * (double)B.n;
 }
 
+// One launch computes every accumulator of the family's schedule: work items = accumulators x tiles.
 void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                    int acc, bool raw_sums, uint32_t* out, cudaStream_t st) {
+                    int out_mode, void* out, uint64_t acc_stride, cudaStream_t st, Slot* ws = nullptr) {
     const TcSchedule& sch = tc_schedule(c->fam);
     tc::TcParams tp{};
-    tp.a_nN = A.tc_nN; tp.b_nN = B.tc_nN;
     tp.n_b = (uint32_t)B.n;
     tp.row0 = (uint32_t)p.row0; tp.row_end = (uint32_t)p.row1;
     tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
@@ -424,14 +422,47 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl * mt - 1) / (tc::TM * cl * mt));
     tp.n_total = A.n; tp.out_base = p.out_base;
     tp.out = out;
-    tp.width = (uint32_t)c->width; tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
-    tp.npairs = (uint32_t)sch.npairs[acc];
-    for (int i = 0; i < sch.npairs[acc]; i++) { tp.pa[i] = sch.pa[acc][i]; tp.pb[i] = sch.pb[acc][i]; }
-    tp.raw_sums = raw_sums ? 1 : 0;
+    tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
+    tp.nacc = out_mode == tc::OUT_RAW_I32 ? (uint32_t)sch.nacc : 1u;
+    for (uint32_t a = 0; a < tp.nacc; a++) {
+        tp.npairs[a] = (uint32_t)sch.npairs[a];
+        for (int i = 0; i < sch.npairs[a]; i++) { tp.pa[a][i] = sch.pa[a][i]; tp.pb[a][i] = sch.pb[a][i]; }
+    }
+    tp.acc_stride = acc_stride;
+    tp.out_mode = out_mode;
     tp.stages = pair ? tc::StageCfg<2, true>::N : (mt == 2 ? tc::StageCfg<2>::N : tc::StageCfg<1>::N);
     if (const char* e = std::getenv("DG_TC_STAGES")) tp.stages = (uint32_t)std::min<int>((int)tp.stages, std::max(1, std::atoi(e)));
     if (tp.gx == 0 || tp.gy == 0) return;
-    const uint64_t tiles = (uint64_t)tp.gx * tp.gy;
+    uint64_t live = (uint64_t)tp.gx * tp.gy;
+    if (tp.square && ws && tp.gx < (1u << 20) && tp.gy < (1u << 12)) {
+        // Upper-triangle panels: tiles on / below the diagonal are dead.  Deal only the live ones (same raster
+        // order: bands of RASTER_G row blocks, column-major) so every CTA (pair) gets the same amount of work.
+        if (ws->tiles_cap < live) {
+            if (ws->d_tiles) cudaFree(ws->d_tiles);
+            if (ws->h_tiles) cudaFreeHost(ws->h_tiles);
+            ws->d_tiles = ws->h_tiles = nullptr; ws->tiles_cap = 0;
+            CUDA_CHECK(cudaMalloc(&ws->d_tiles, live * 4));
+            CUDA_CHECK(cudaHostAlloc(&ws->h_tiles, live * 4, cudaHostAllocDefault));
+            ws->tiles_cap = live;
+        }
+        const uint32_t rows_per_block = (uint32_t)(tc::TM * cl * mt);
+        uint32_t n_live = 0;
+        for (uint32_t band0 = 0; band0 < tp.gy; band0 += tc::RASTER_G) {
+            const uint32_t gb = std::min<uint32_t>(tc::RASTER_G, tp.gy - band0);
+            for (uint32_t bx = 0; bx < tp.gx; bx++)
+                for (uint32_t by = band0; by < band0 + gb; by++) {
+                    const uint64_t rowS0 = (uint64_t)tp.row0 + (uint64_t)by * rows_per_block;
+                    const uint64_t rowB0 = (uint64_t)(tp.col_block0 + bx) * tc::TN;
+                    if (rowS0 >= tp.row_end || rowB0 + tc::TN <= rowS0 + 1) continue;
+                    ws->h_tiles[n_live++] = (by << 20) | bx;
+                }
+        }
+        if (n_live == 0) return;
+        CUDA_CHECK(cudaMemcpyAsync(ws->d_tiles, ws->h_tiles, (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
+        tp.tile_list = ws->d_tiles; tp.n_live = n_live;
+        live = n_live;
+    }
+    const uint64_t tiles = live * tp.nacc;
     if (cl == 1) {
         auto kern = mt == 2 ? tc::tc_gemm_kernel<1, 2> : tc::tc_gemm_kernel<1, 1>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -453,39 +484,55 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, A.map_a, B.map_a, tp));
     }
     c->tm.count_launches++;
-    if (acc == 0 && sch.needs_pp && A.pp.n_entries && B.pp.n_entries) {
-        tc::PpCorrParams cp{};
-        cp.a_entries = A.pp.entries; cp.a_n = A.pp.n_entries;
-        cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
-        cp.row0 = tp.row0; cp.row_end = tp.row_end; cp.n_b = tp.n_b; cp.square = tp.square;
-        cp.n_total = tp.n_total; cp.out_base = tp.out_base; cp.out = out;
-        cp.sign = raw_sums ? -1 : 1;
-        tc::pp_correct_kernel<<<(A.pp.n_entries + 255) / 256, 256, 0, st>>>(cp);
-        CUDA_CHECK(cudaGetLastError());
-        c->tm.count_launches++;
-    }
 }
 
-// tcgen05 variant of enqueue_panel_kernel.  n / n_high: one GEMM writes the result directly.  Other
-// families (and the debug counts): one GEMM per accumulator into `scratch`, then tc_combine_kernel.
+// Will this (A rows, B columns) product need the both-partial repair of accumulator 0?  A stream batch has
+// no index: its partial codes are found by scanning its V planes, so only B's index decides.
+bool tc_pp_pending(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B, bool a_is_batch) {
+    return tc_schedule(c->fam).needs_pp && B.pp.n_entries != 0 && (a_is_batch || A.pp.n_entries != 0);
+}
+
+// tcgen05 variant of enqueue_panel_kernel.  n / n_high with no correction pending: one GEMM writes the result
+// directly.  Otherwise (and for the debug counts): one GEMM per accumulator into `scratch`, the both-partial
+// repair of accumulator 0, then tc_combine_kernel.
 void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                      void* d_out, uint32_t* scratch, bool swap_roles, bool counts, cudaStream_t st) {
+                      void* d_out, int* scratch, bool swap_roles, bool counts, cudaStream_t st, bool a_is_batch = false,
+                      Slot* ws = nullptr) {
     const TcSchedule& sch = tc_schedule(c->fam);
-    if (c->fam == FAM_SNP && !counts) {
-        launch_tc_gemm(c, d, A, B, mode, p, 0, false, static_cast<uint32_t*>(d_out), st);
+    const bool pp_pending = tc_pp_pending(c, A, B, a_is_batch);
+    if (c->fam == FAM_SNP && !counts && !pp_pending) {
+        launch_tc_gemm(c, d, A, B, mode, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, d_out, 0, st, ws);
         return;
     }
     if (!scratch) fail(DG_ERR_STATE, "tensor engine: no scratch buffer");
     const uint64_t stride = p.n_results;
-    for (int a = 0; a < sch.nacc; a++) launch_tc_gemm(c, d, A, B, mode, p, a, true, scratch + (size_t)a * stride, st);
+    launch_tc_gemm(c, d, A, B, mode, p, tc::OUT_RAW_I32, scratch, stride, st, ws);
+    if (pp_pending) {
+        tc::PpCorrParams cp{};
+        cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
+        cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1; cp.n_b = (uint32_t)B.n;
+        cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
+        cp.n_total = A.n; cp.out_base = p.out_base; cp.out = scratch;
+        if (a_is_batch) {
+            cp.a_ops = A.tc_ops; cp.a_nplanes = (uint32_t)sch.nplanes; cp.a_wp8 = (uint32_t)A.tc_wp8; cp.a_vplane0 = TC_VPLANE0;
+            const uint64_t units = (p.row1 - p.row0) * (A.tc_wp8 / 16);
+            tc::pp_correct_scan_kernel<<<(unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 16), 256, 0, st>>>(cp);
+        } else {
+            cp.a_entries = A.pp.entries; cp.a_n = A.pp.n_entries;
+            tc::pp_correct_kernel<<<(A.pp.n_entries + 255) / 256, 256, 0, st>>>(cp);
+        }
+        CUDA_CHECK(cudaGetLastError());
+        c->tm.count_launches++;
+    }
     tc::CombineParams cp{};
     cp.acc = scratch; cp.acc_stride = stride;
-    cp.a_nN = A.tc_nN; cp.b_nN = B.tc_nN; cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
+    cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
     cp.n_b = (uint32_t)B.n; cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
     cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
     cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
-    cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam; cp.counts = counts ? 1 : 0;
-    cp.n_total = A.n; cp.out_base = p.out_base; cp.width = (uint32_t)c->width; cp.out = d_out;
+    cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
+    cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
+    cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
     dim3 grid((unsigned)((B.n - cp.col0 + 255) / 256), (unsigned)std::min<uint64_t>(p.row1 - p.row0, 32768));
     if (grid.x == 0 || grid.y == 0) return;
     tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
@@ -548,6 +595,7 @@ void enqueue_panel_kernel(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSe
     cp.out_base = COUNTS ? 0 : p.out_base;
     cp.out = d_out;
     cp.measure = c->measure;
+    cp.out_u16 = (!COUNTS && c->u16()) ? 1 : 0;
     cp.col_block0 = cp.square ? (uint32_t)((p.row0 + 1) / ts.tn) : 0;
     const uint64_t col_blocks_total = (B.n + ts.tn - 1) / ts.tn;
     dim3 grid((unsigned)(col_blocks_total - cp.col_block0), (unsigned)((p.row1 - p.row0 + ts.tm - 1) / ts.tm));
@@ -655,7 +703,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
-        if (tc_run && c->fam != FAM_SNP)
+        if (tc_run && (c->fam != FAM_SNP || tc_pp_pending(c, d.set[0], d.set[wb], false)))
             for (auto& sl : d.slot) ensure_scratch(c, sl, std::max<size_t>(max_bytes / c->elem_bytes(), 64));
     }
 
@@ -694,7 +742,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
             CUDA_CHECK(cudaSetDevice(d.id));
             const Panel& p = mine[k];
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
-            if (tc_run) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si));
+            if (tc_run) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si), false, &s);
             else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
             CUDA_CHECK(cudaEventRecord(s.k_stop, d.cs(si)));
             if (!device_only) {
@@ -758,12 +806,12 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     const TileShape ts = tile_shape(c->fam, c->tile_variant);
     uint64_t mb = std::min(max_batch, std::max<uint64_t>(cap_rows / ts.tm * ts.tm, ts.tm));
     c->s_max_batch = mb;
-    // Streamed batches run on the tensor cores for k80 / tn93 (no ambiguity correction needed); the
-    // n / n_high / raw / jc69 batches stay on the LOP3 tiles (their correction index is per alignment).
-    const bool needs_pp = tc_schedule(c->fam).needs_pp;
-    if (c->engine == 2 && needs_pp)
-        fail(DG_ERR_INVALID_ARG, "engine 2 covers -s streaming for k80 / tn93 only; use engine 0 or 1 for this measure");
-    const bool s_tc = c->engine != 1 && !needs_pp && c->devs[0].set[0].tc_ready;
+    // Streamed batches run on the tensor cores like resident panels (the both-partial repair of n / n_high /
+    // raw / jc69 scans the batch's own V planes against the resident index) unless the resident alignment is
+    // so full of partial ambiguity codes that the repair would dominate; then the LOP3 tiles run.
+    const PlaneSet& R0 = c->devs[0].set[0];
+    const bool cheap_pp = !tc_schedule(c->fam).needs_pp || R0.pp.pair_work <= 2.0 * (double)R0.n * (double)R0.n;
+    const bool s_tc = c->engine != 1 && R0.tc_ready && (c->engine == 2 || cheap_pp);
     if (!s_tc)
         for (auto& d : c->devs) ensure_lop3(c, d, d.set[0]);
     for (auto& d : c->devs) {
@@ -771,7 +819,7 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
         if (s_tc)
             for (auto& sl : d.slot) ensure_scratch(c, sl, (size_t)mb * n_res);
-        if (d.in_cap < mb || (s_tc && !d.slot[0].batch.tc_ops)) {
+        if (d.in_cap < mb || (s_tc && !d.slot[0].batch.tc_ops) || (!s_tc && !d.slot[0].batch.core)) {
             for (auto& s : d.slot) {
                 if (s.h_in) cudaFreeHost(s.h_in);
                 if (s.d_in) cudaFree(s.d_in);
@@ -781,7 +829,7 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
                 CUDA_CHECK(cudaHostAlloc(&s.h_in, (size_t)mb * c->width, cudaHostAllocDefault));
                 CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)mb * c->width));
                 CUDA_CHECK(cudaHostAlloc(&s.h_acgt, (size_t)mb * 4 * sizeof(uint32_t), cudaHostAllocDefault));
-                alloc_set(c, s.batch, mb, false);
+                alloc_set(c, s.batch, mb, false, !s_tc);
                 if (s_tc) alloc_tc_operands(c, s.batch);
             }
             d.in_cap = mb;
@@ -824,14 +872,15 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     s.batch.n = nb;
     CUDA_CHECK(cudaEventRecord(s.p_start, cst));
     // fastaio.rs:250-254: the streamed tn93 records count raw upper-case chars only (:139-142)
-    enqueue_pack(c, d.d_invalid + si, s.batch, s.d_in, nb, input_kind, !host_counts, input_kind == DG_INPUT_ASCII, cst);
+    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, !host_counts && c->fam == FAM_TN93, cst, 0,
+                                 d.d_invalid + si, true);
+    else enqueue_pack(c, d.d_invalid + si, s.batch, s.d_in, nb, input_kind, !host_counts, input_kind == DG_INPUT_ASCII, cst);
     CUDA_CHECK(cudaEventRecord(s.p_stop, cst));
     Panel p;
     p.row0 = 0; p.row1 = nb; p.out_base = 0;
     p.n_results = nb * d.set[0].n;
-    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, false, cst);
     CUDA_CHECK(cudaEventRecord(s.k_start, cst));
-    if (c->s_tc) enqueue_panel_tc(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, s.d_scratch, true, false, cst);
+    if (c->s_tc) enqueue_panel_tc(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, s.d_scratch, true, false, cst, true);
     else enqueue_panel_kernel<false>(c, d, s.batch, d.set[0], DG_MODE_RECT, p, s.d_out, true, cst);
     CUDA_CHECK(cudaEventRecord(s.k_stop, cst));
     CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
@@ -887,6 +936,8 @@ void destroy_device(Device& d) {
     for (auto& s : d.slot) {
         if (s.d_out) cudaFree(s.d_out);
         if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.d_tiles) cudaFree(s.d_tiles);
+        if (s.h_tiles) cudaFreeHost(s.h_tiles);
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.d_in) cudaFree(s.d_in);
@@ -1034,6 +1085,10 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             break;
         case DG_OPT_KEEP_CODES: ctx->keep_codes = value != 0; break;
         case DG_OPT_TILE_VARIANT: ctx->tile_variant = (int)value; break;
+        case DG_OPT_RESULT_U16:
+            if (value != 0 && ctx->width > 65535) fail(DG_ERR_INVALID_ARG, "uint16 results need width <= 65535");
+            ctx->result_u16 = value != 0;
+            break;
         case DG_OPT_ENGINE:
             if (value < 0 || value > 2) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
             ctx->engine = (int)value;
@@ -1211,7 +1266,7 @@ int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
             const uint64_t step = (uint64_t)ts.tm * 32768;
             if (use_tc(ctx, A, B)) {
                 // tensor engine: raw sums of every accumulator -> the same canonical counts
-                uint32_t* scratch = nullptr;
+                int* scratch = nullptr;
                 const uint64_t rows_step = std::min<uint64_t>(A.n, 32768);
                 CUDA_CHECK(cudaMalloc(&scratch, (size_t)rows_step * B.n * 4 * tc_schedule(ctx->fam).nacc));
                 try {

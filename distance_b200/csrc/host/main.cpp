@@ -250,6 +250,7 @@ int run(const Args& a) {
     int rc = dg_create(gpus.data(), (int)gpus.size(), measure_id(a.measure), width, &ctx);
     if (rc != DG_OK) throw message_error(std::string("GPU engine: ") + dg_last_error(nullptr));
     struct Guard { dg_ctx* c; ~Guard() { dg_destroy(c); } } guard{ctx};
+    if (width <= 65535) dg_set_option(ctx, DG_OPT_RESULT_U16, 1);  // n / n_high: half the D2H bytes, same text
 
     for (size_t k = 0; k < loaded.size(); k++)
         gpu_check(ctx, dg_load_resident(ctx, (int)k, loaded[k].seqs.data(), loaded[k].n(), DG_INPUT_ASCII, nullptr));

@@ -99,6 +99,7 @@ inline void emit(std::string& t, const std::string& a, const std::string& b, con
     t += b;
     t.push_back('\t');
     if (p.result_kind == DG_RESULT_U32) format_u32(static_cast<const uint32_t*>(p.data)[k], t);
+    else if (p.result_kind == DG_RESULT_U16) format_u32(static_cast<const uint16_t*>(p.data)[k], t);
     else format_float12(static_cast<const double*>(p.data)[k], t);
     t.push_back('\n');
 }

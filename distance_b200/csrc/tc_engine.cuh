@@ -3,30 +3,29 @@
 // The per-pair counts are a dense contraction over sites, so they can run on the 5th-gen tensor
 // cores with exact int32 accumulation in TMEM.  Operand planes are int8, K-major:
 //
-//   ops[record][plane][site]   plane 0..3 = m_A, m_G, m_C, m_T : possibility bit of the base, but 0 for
-//                                           N-like codes (N, '-', '?')
-//                              plane 4    = +Nl  (1 where the code is N-like)          -- A operand
-//                              plane 5    = -Nl                                        -- B operand
+//   ops[record][plane][site]      (plane ids and values: PlaneId below)
 //
-// For a pair (q, t):  acc = sum_sites [ sum_b m_b(q) m_b(t)  -  Nl(q) Nl(t) ]            (5 MAC / site)
-//   * q, t known            : 1 iff same base
-//   * one known, one partial: 1 iff the base is in the ambiguity set   (overlap indicator, exact)
-//   * anything vs N-like    : the m-part is 0; N-like sites are added back from per-record counts:
-//                             overlap = acc + nN(q) + nN(t)   [the -Nl*Nl term removes the double count]
-//   * both partial          : sum_b = |Sq ^ St| which over-counts by (|X|-1) when the two ambiguity sets
-//                             share >= 2 bases; fixed exactly by pp_correct_kernel from a per-site
-//                             inverted index of the (rare) partial codes.
-// DIFF = width - overlap  <=>  #sites with (q & t) < 16  (measures.rs:14-23).
+// A "schedule" lists, per integer count, the (A plane, B plane) pairs whose products are summed.  Every count
+// is written as a bilinear form of MINIMAL rank over the four bases, so the MAC count per pair-site is
 //
-// The other families use the same GEMM kernel once per integer count (a "schedule" of plane pairs per
-// accumulator, raw int32 sums written to a scratch matrix) followed by tc_combine_kernel, which derives
-// the reference's counts and runs the same f64 epilogues as the LOP3 path:
-//   raw/jc69 : acc0 = the n/n_high sum above (DIFF), acc1 = sum_b k_b k_b (SAME; k_b = known one-hot)
-//   k80      : SAME; CS = PURk.PURk + PYRk.PYRk (known, same class) -> ts = CS - SAME;
-//              tv = PURc.PYRc' + PYRc.PURc' (classes {A,G,R} / {C,T,Y}, measures.rs:90-103)
-//   tn93     : L = K.K, PP = PURk.PURk, YY = PYRk.PYRk, SP = kA.kA + kG.kG, SY = kC.kC + kT.kT
-//              -> d = L - SP - SY, P1 = PP - SP, P2 = YY - SY      (7 MAC / site, all exact: only known
-//              bases enter k80 / tn93 counts apart from the rank-2 R/Y classes of tv)
+//   n, n_high : 3 DIFF = sum_b U_b(q) V_b(t)                                                     4 MAC
+//               U_b = 1 - possibility bit, V_b = 3 * possibility bit - (|S| - 1); both 0 for N-like codes.
+//               * q known (base a)    : sum_{b != a} V_b(t) = 3 [a not in St]   (exact for every t)
+//               * t known (base a)    : 3 U_a(q) = 3 [a not in Sq]              (exact for every q)
+//               * N-like on a side    : 0  (N, '-', '?' are never DIFF: measures.rs:17)
+//               * both partial codes  : off by a small integer, repaired exactly by pp_correct_kernel from a
+//                                       per-site inverted index of the (rare) partial codes
+//               (J - I on four bases has rank 4: no exact formulation needs fewer planes.)
+//   raw, jc69 : the same + SAME = sum_b K_b K_b                                                  8 MAC
+//   k80       : CS = PURK.PURK + PYRK.PYRK = SAME + ts;  X = W.W + Z.Z = SAME - ts  (W = K_A - K_G,
+//               Z = K_C - K_T);  tv = PURC.PYRC' + PYRC.PURC' (measures.rs:90-103)                6 MAC
+//   tn93      : L = K.K;  PP = PURK.PURK = SP + P1;  YY = SY + P2;  W.W = SP - P1;  Z.Z = SY - P2
+//               -> d = L - SP - SY (measures.rs:156-175)                                          5 MAC
+// DIFF <=> (q & t) < 16 (measures.rs:14-23).  int32 accumulation is exact; the halvings are exact.
+//
+// n / n_high without pending corrections: the GEMM epilogue stores acc / 3 directly (uint32 or uint16).
+// Otherwise each accumulator's raw int32 sums go to a scratch matrix, pp_correct repairs accumulator 0 and
+// tc_combine_kernel derives the reference's counts and runs the same f64 epilogues as the LOP3 path.
 //
 // Kernel: persistent, warp-specialised CTA of 192 threads per SM.
 //   warp 0     : TMA producer  (cp.async.bulk.tensor.2d, 128B swizzle, 4-stage mbarrier ring)
@@ -47,7 +46,9 @@ constexpr int KB = 128;          // K bytes per stage = one 128B swizzle atom = 
 constexpr int STAGES = 4;        // barrier slots; MT = 1 uses 4 stages of 48 KB, MT = 2 uses 3 stages of 64 KB
 constexpr int A_BYTES = TM * KB;
 constexpr int B_BYTES = TN * KB;
-constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_PITCH = 33;     // words per row of an epilogue warp's 32 x 32 transpose buffer (+1: conflict-free)
+constexpr int EPI_BYTES = 4 * 32 * EPI_PITCH * 4;
+constexpr int SMEM_BYTES = 192 * 1024 + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_BYTES;
 template <int MT, bool PAIR = false> struct StageCfg {
     static constexpr int BYTES = MT * A_BYTES + (PAIR ? B_BYTES / 2 : B_BYTES);  // a pair CTA stages only its half of B
     static constexpr int N = (192 * 1024) / BYTES < STAGES ? (192 * 1024) / BYTES : STAGES;
@@ -168,97 +169,162 @@ constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(T
 constexpr uint32_t IDESC_I8_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);  // M = 256 over two CTAs
 
 // ---- operand packing ------------------------------------------------------------------------------
-// plane ids (value of a plane at a site is 0/1, except NEG_NL which is 0/-1)
-enum PlaneId { P_MA = 0, P_MG, P_MC, P_MT, P_NL, P_NEG_NL, P_KA, P_KG, P_KC, P_KT, P_PURK, P_PYRK, P_K, P_PURC, P_PYRC };
-constexpr int MAX_PLANES = 10;
+// Plane ids.  A plane holds one int8 per site; every plane is 0 for N-like codes (N, '-', '?') and for the
+// zero padding beyond `width` / beyond the last record, so padding lands in no count.
+//   U_b   = 1 - possibility bit of base b                (A-side operand of DIFF)
+//   V_b   = 3 * possibility bit - (|S| - 1)              (B-side operand of DIFF; values 3,2,1,0,-1,-2)
+//   K_b   = known one-hot;  PURK / PYRK = known purine / pyrimidine;  K = known
+//   W     = K_A - K_G,  Z = K_C - K_T                    (rank-1 factors of SAME - ts inside a class)
+//   PURC / PYRC = code in {A,G,R} / {C,T,Y}              (measures.rs:90, 94)
+enum PlaneId { P_UA = 0, P_UG, P_UC, P_UT, P_VA, P_VG, P_VC, P_VT, P_KA, P_KG, P_KC, P_KT,
+               P_PURK, P_PYRK, P_K, P_W, P_Z, P_PURC, P_PYRC };
+constexpr int MAX_PLANES = 12;
 
 struct PackI8Params {
     const uint8_t* codes;  // n x width
     uint64_t n, n_pad, width;
     uint64_t wp8;          // bytes per plane (width rounded up to 128)
     int8_t* ops;           // n_pad x nplanes x wp8
-    uint32_t* nN;          // n_pad: N-like sites per record (zeroed by the caller)
+    uint32_t* acgt;        // n_pad x 4 (A,T,G,C) written per record, or NULL
     int ascii;
+    int count_upper_ascii; // ASCII input: count raw 'A','T','G','C' only (fastaio.rs:139-142) instead of count_bases
     int nplanes;
     uint8_t plane_id[MAX_PLANES];
     unsigned long long* invalid;  // min over ((seq0 + record) << 32 | site) of invalid bytes; or NULL
     uint64_t seq0;                // global index of record 0 of this chunk
 };
 
-// bit i of the result = value of plane id i for Paradis code c
-__device__ __forceinline__ uint32_t plane_bits(uint32_t c) {
-    const bool nl = (c & 0xF0u) == 0xF0u;  // N 240, '-' 244, '?' 242
-    const uint32_t known = (c >> 3) & 1u;
-    const uint32_t poss = nl ? 0u : (c >> 4);  // bit3 = A, bit2 = G, bit1 = C, bit0 = T
-    const uint32_t a = (poss >> 3) & 1u, g = (poss >> 2) & 1u, cc = (poss >> 1) & 1u, t = poss & 1u;
-    uint32_t m = a | (g << 1) | (cc << 2) | (t << 3);
-    m |= (nl ? 1u : 0u) << P_NL;
-    m |= (nl ? 1u : 0u) << P_NEG_NL;
-    m |= (known & a) << P_KA | (known & g) << P_KG | (known & cc) << P_KC | (known & t) << P_KT;
-    m |= (known & (a | g)) << P_PURK | (known & (cc | t)) << P_PYRK | known << P_K;
-    m |= ((c & 55u) == 0u ? 1u : 0u) << P_PURC;   // measures.rs:90  {A,G,R}
-    m |= ((c & 199u) == 0u ? 1u : 0u) << P_PYRC;  // measures.rs:94  {C,T,Y}
-    return m;
+constexpr uint32_t M1 = 0x01010101u;
+
+// Four Paradis codes (one per byte) -> per-byte 0/1 words of the code bits and E = |S| - 1.
+struct CodeBits { uint32_t A, G, C, T, K, E; };
+__device__ __forceinline__ CodeBits code_bits(uint32_t w) {
+    CodeBits b;
+    b.A = (w >> 7) & M1; b.G = (w >> 6) & M1; b.C = (w >> 5) & M1; b.T = (w >> 4) & M1; b.K = (w >> 3) & M1;
+    b.E = b.A + b.G + b.C + b.T - M1;   // every valid code has >= 1 possibility bit: no borrow between bytes
+    return b;
+}
+// The four int8 values of plane `id` for the four codes of `b`.
+__device__ __forceinline__ uint32_t plane_word(const CodeBits& b, uint32_t id) {
+    switch (id) {
+    case P_UA: return b.A ^ M1;
+    case P_UG: return b.G ^ M1;
+    case P_UC: return b.C ^ M1;
+    case P_UT: return b.T ^ M1;
+    case P_VA: return __vsub4(b.A * 3u, b.E);
+    case P_VG: return __vsub4(b.G * 3u, b.E);
+    case P_VC: return __vsub4(b.C * 3u, b.E);
+    case P_VT: return __vsub4(b.T * 3u, b.E);
+    case P_KA: return b.A & b.K;
+    case P_KG: return b.G & b.K;
+    case P_KC: return b.C & b.K;
+    case P_KT: return b.T & b.K;
+    case P_PURK: return (b.A | b.G) & b.K;
+    case P_PYRK: return (b.C | b.T) & b.K;
+    case P_K: return b.K;
+    case P_W: return __vsub4(b.A & b.K, b.G & b.K);
+    case P_Z: return __vsub4(b.C & b.K, b.T & b.K);
+    case P_PURC: return (b.A | b.G) & ~(b.C | b.T);   // {A,G,R}: measures.rs:90
+    default: return (b.C | b.T) & ~(b.A | b.G);       // P_PYRC {C,T,Y}: measures.rs:94
+    }
 }
 
-// One thread per (record, 16-site group): 16 byte loads -> one 16-byte store per stored plane.
+// One CTA per record (grid-stride), one thread per 16-site group: 16 code bytes are fetched with aligned
+// 32-bit loads + funnel shifts (rows are `width` bytes apart, so they are not 16-byte aligned), translated
+// through a 256-entry LUT in shared memory (ASCII -> Paradis, encoding.rs:4-41; or Paradis -> itself if
+// legal), expanded to every stored plane with byte-SIMD arithmetic and written as one 16-byte store per
+// plane.  Per-record A,T,G,C counts (count_bases, fastaio.rs:53-66) are reduced in the CTA: no atomics.
 __global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
-    const uint64_t groups = p.wp8 / 16;
-    const uint64_t total = p.n_pad * groups;
-    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t seq = u / groups;
-        const uint64_t s0 = (u % groups) * 16;
-        uint32_t bits[16];
-        uint32_t nn = 0;
+    __shared__ uint8_t lut[256];
+    __shared__ uint32_t red[8][4];
+    {
+        const uint32_t t = threadIdx.x;
+        lut[t] = p.ascii ? c_ascii_lut[t] : (((c_valid_code[t >> 5] >> (t & 31)) & 1u) ? (uint8_t)t : (uint8_t)0);
+    }
+    __syncthreads();
+    const uint32_t groups = (uint32_t)(p.wp8 / 16);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint64_t seq = blockIdx.x; seq < p.n_pad; seq += gridDim.x) {
+        uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
+        const uint8_t* row = p.codes + seq * p.width;
+        for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
+            const uint64_t s0 = (uint64_t)g * 16;
+            uint32_t w[4] = {0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u};   // N-like padding
+            if (seq < p.n && s0 < p.width) {
+                uint32_t raw[4];
+                if (s0 + 20 <= p.width) {   // the aligned window [a & ~3, +20) stays inside this row
+                    const uintptr_t a = reinterpret_cast<uintptr_t>(row + s0);
+                    const uint32_t* ap = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(a & 3) * 8;
+                    const uint32_t x0 = __ldg(ap), x1 = __ldg(ap + 1), x2 = __ldg(ap + 2), x3 = __ldg(ap + 3), x4 = __ldg(ap + 4);
+                    raw[0] = __funnelshift_r(x0, x1, sh); raw[1] = __funnelshift_r(x1, x2, sh);
+                    raw[2] = __funnelshift_r(x2, x3, sh); raw[3] = __funnelshift_r(x3, x4, sh);
+                } else {                    // last groups of the row: byte loads, bounded by width
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            bits[k] = 0;
-            const uint64_t s = s0 + k;
-            if (seq < p.n && s < p.width) {
-                uint32_t c = p.codes[seq * p.width + s];
-                bool ok;
-                if (p.ascii) { c = c_ascii_lut[c]; ok = c != 0; }
-                else ok = (c_valid_code[c >> 5] >> (c & 31)) & 1u;
-                if (!ok) {
-                    if (p.invalid) atomicMin(p.invalid, ((unsigned long long)(p.seq0 + seq) << 32) | (unsigned long long)s);
-                    c = 240;
+                    for (int k = 0; k < 4; k++) {
+                        uint32_t v = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint64_t s = s0 + 4 * k + j;
+                            const uint32_t byte = s < p.width ? (uint32_t)row[s] : (p.ascii ? (uint32_t)'N' : 240u);
+                            v |= byte << (8 * j);
+                        }
+                        raw[k] = v;
+                    }
                 }
-                bits[k] = plane_bits(c);
-                nn += (bits[k] >> P_NL) & 1u;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t r = raw[k];
+                    uint32_t t = (uint32_t)lut[r & 0xFF] | ((uint32_t)lut[(r >> 8) & 0xFF] << 8) |
+                                 ((uint32_t)lut[(r >> 16) & 0xFF] << 16) | ((uint32_t)lut[r >> 24] << 24);
+                    if ((t - M1) & ~t & 0x80808080u) {   // a zero byte = invalid nucleotide (fastaio.rs:111-113)
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            if (((t >> (8 * j)) & 0xFFu) == 0) {
+                                if (p.invalid) atomicMin(p.invalid, ((unsigned long long)(p.seq0 + seq) << 32) | (unsigned long long)(s0 + 4 * k + j));
+                                t |= 0xF0u << (8 * j);
+                            }
+                    }
+                    w[k] = t;
+                    if (p.acgt && p.count_upper_ascii) {   // the streamed tn93 records count raw upper-case letters only
+                        cA += __popc(__vcmpeq4(r, 0x41414141u)); cT += __popc(__vcmpeq4(r, 0x54545454u));
+                        cG += __popc(__vcmpeq4(r, 0x47474747u)); cC += __popc(__vcmpeq4(r, 0x43434343u));
+                    }
+                }
+            }
+            CodeBits b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) b[k] = code_bits(w[k]);
+            if (p.acgt && !p.count_upper_ascii) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    cA += __popc(b[k].A & b[k].K); cT += __popc(b[k].T & b[k].K);
+                    cG += __popc(b[k].G & b[k].K); cC += __popc(b[k].C & b[k].K);
+                }
+            }
+            int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + s0;
+            for (int pl = 0; pl < p.nplanes; pl++) {
+                const uint32_t id = p.plane_id[pl];
+                *reinterpret_cast<uint4*>(base + pl * p.wp8) =
+                    make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id));
             }
         }
-        int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + s0;
-        for (int pl = 0; pl < p.nplanes; pl++) {
-            const uint32_t id = p.plane_id[pl];
-            const uint32_t one = id == P_NEG_NL ? 0xFFu : 1u;
-            uint32_t w[4] = {0, 0, 0, 0};
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                if ((bits[k] >> id) & 1u) w[k >> 2] |= one << ((k & 3) * 8);
-            *reinterpret_cast<uint4*>(base + pl * p.wp8) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (p.acgt) {   // uniform branch: CTA reduction of the four counts
+            if (p.count_upper_ascii) { cA >>= 3; cT >>= 3; cG >>= 3; cC >>= 3; }   // vcmpeq4 sets 8 bits per hit
+            for (int o = 16; o; o >>= 1) {
+                cA += __shfl_xor_sync(0xffffffffu, cA, o); cT += __shfl_xor_sync(0xffffffffu, cT, o);
+                cG += __shfl_xor_sync(0xffffffffu, cG, o); cC += __shfl_xor_sync(0xffffffffu, cC, o);
+            }
+            if (lane == 0) { red[warp][0] = cA; red[warp][1] = cT; red[warp][2] = cG; red[warp][3] = cC; }
+            __syncthreads();
+            if (threadIdx.x < 4) {
+                uint32_t v = 0;
+                for (int q = 0; q < 8; q++) v += red[q][threadIdx.x];
+                p.acgt[seq * 4 + threadIdx.x] = seq < p.n ? v : 0u;
+            }
+            __syncthreads();
         }
-        if (nn && p.nN) atomicAdd(p.nN + seq, nn);
     }
-}
-
-// count_bases (fastaio.rs:53-66) for tn93 when the LOP3 planes are not built: one warp per record,
-// histogram of the codes 136 / 24 / 72 / 40 -> acgt[record] = {A, T, G, C}.
-__global__ void __launch_bounds__(256) acgt_count_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* acgt) {
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const uint8_t* row = codes + warp * width;
-    uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
-    for (uint64_t s = lane; s < width; s += 32) {
-        uint32_t c = row[s];
-        if (ascii) c = c_ascii_lut[c];
-        cA += c == 136; cT += c == 24; cG += c == 72; cC += c == 40;
-    }
-    for (int o = 16; o; o >>= 1) {
-        cA += __shfl_xor_sync(0xffffffffu, cA, o); cT += __shfl_xor_sync(0xffffffffu, cT, o);
-        cG += __shfl_xor_sync(0xffffffffu, cG, o); cC += __shfl_xor_sync(0xffffffffu, cC, o);
-    }
-    if (lane == 0) *reinterpret_cast<uint4*>(acgt + warp * 4) = make_uint4(cA, cT, cG, cC);
 }
 
 // ---- inverted index of partial ambiguity codes (R Y M W S K V H D B) -----------------------------------
@@ -314,49 +380,89 @@ __global__ void pp_fill_kernel(const uint8_t* codes, uint64_t n, uint64_t width,
     }
 }
 
+// DIFF is computed as sum_b U_b(q) V_b(t) = 3 [Sq, St disjoint] whenever at least one code is a known base or
+// N-like (tc_engine.cuh header).  When BOTH codes are partial ambiguity codes the product is off by a small
+// integer: add (3 * want - got) to the raw accumulator.  ma = row (U side) nibble, mb = column (V side) nibble.
+__device__ __forceinline__ int pp_corr(uint32_t ma, uint32_t mb) {
+    const uint32_t nma = ~ma & 15u;
+    const int cb = __popc(mb);
+    const int got = __popc(nma & mb) * (4 - cb) + __popc(nma & ~mb & 15u) * (1 - cb);
+    return ((ma & mb) ? 0 : 3) - got;
+}
+
 struct PpCorrParams {
-    const uint64_t* a_entries; uint32_t a_n;          // row alignment's entries
+    const uint64_t* a_entries; uint32_t a_n;          // row alignment's entries (resident rows)
+    const int8_t* a_ops; uint32_t a_nplanes, a_wp8, a_vplane0;  // or: scan the V planes of the row records (stream batches)
     const uint64_t* b_entries; const uint32_t* b_off; // column alignment's index
     uint32_t row0, row_end, n_b;
     int square;
     uint64_t n_total, out_base;
-    uint32_t* out;                                    // panel counts: DIFF (sign +1) or the raw overlap sum (sign -1)
-    int sign;
+    int* out;                                         // raw sums of accumulator 0 (3 * DIFF) of the panel
 };
-// Both-partial sites whose ambiguity sets share x >= 2 bases were counted x times as overlap: add x-1 back to DIFF.
+__device__ __forceinline__ void pp_fix_row(const PpCorrParams& p, uint32_t row, uint32_t site, uint32_t ma) {
+    const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
+                                       : (uint64_t)(row - p.row0) * p.n_b;
+    for (uint32_t k = p.b_off[site]; k < p.b_off[site + 1]; k++) {
+        const uint64_t eb = p.b_entries[k];
+        const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
+        if (p.square && col <= row) continue;
+        const int c = pp_corr(ma, (uint32_t)(eb & 15));
+        if (c) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), c);
+    }
+}
+// rows given as index entries (resident alignments)
 __global__ void pp_correct_kernel(PpCorrParams p) {
     for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < p.a_n; e += gridDim.x * blockDim.x) {
         const uint64_t ea = p.a_entries[e];
         const uint32_t row = (uint32_t)((ea >> 4) & 0xFFFFFFFFull);
         if (row < p.row0 || row >= p.row_end) continue;
-        const uint32_t site = (uint32_t)(ea >> 36), ma = (uint32_t)(ea & 15);
-        uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
-                                     : (uint64_t)(row - p.row0) * p.n_b;
-        for (uint32_t k = p.b_off[site]; k < p.b_off[site + 1]; k++) {
-            const uint64_t eb = p.b_entries[k];
-            const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
-            if (p.square && col <= row) continue;
-            const int x = __popc(ma & (uint32_t)(eb & 15));
-            if (x >= 2) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), (uint32_t)(p.sign * (x - 1)));
+        pp_fix_row(p, row, (uint32_t)(ea >> 36), (uint32_t)(ea & 15));
+    }
+}
+// rows found by scanning their V planes (stream batches have no index): a site holds a partial code iff
+// one of its V values is negative; its possibility nibble is then {b : V_b > 0}.
+__global__ void pp_correct_scan_kernel(PpCorrParams p) {
+    const uint32_t gpr = p.a_wp8 / 16;   // 16-site groups per record
+    const uint64_t total = (uint64_t)(p.row_end - p.row0) * gpr;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t row = p.row0 + (uint32_t)(u / gpr);
+        const uint32_t s0 = (uint32_t)(u % gpr) * 16;
+        const int8_t* base = p.a_ops + ((uint64_t)row * p.a_nplanes + p.a_vplane0) * p.a_wp8 + s0;
+        uint4 v[4];
+#pragma unroll
+        for (int b = 0; b < 4; b++) v[b] = *reinterpret_cast<const uint4*>(base + (uint64_t)b * p.a_wp8);
+        const uint32_t any = (v[0].x | v[1].x | v[2].x | v[3].x | v[0].y | v[1].y | v[2].y | v[3].y |
+                              v[0].z | v[1].z | v[2].z | v[3].z | v[0].w | v[1].w | v[2].w | v[3].w) & 0x80808080u;
+        if (!any) continue;
+        const int8_t* vb[4] = {reinterpret_cast<const int8_t*>(&v[0]), reinterpret_cast<const int8_t*>(&v[1]),
+                               reinterpret_cast<const int8_t*>(&v[2]), reinterpret_cast<const int8_t*>(&v[3])};
+        for (int k = 0; k < 16; k++) {
+            if (vb[0][k] >= 0 && vb[1][k] >= 0 && vb[2][k] >= 0 && vb[3][k] >= 0) continue;
+            const uint32_t ma = (vb[0][k] > 0 ? 8u : 0u) | (vb[1][k] > 0 ? 4u : 0u) | (vb[2][k] > 0 ? 2u : 0u) | (vb[3][k] > 0 ? 1u : 0u);
+            pp_fix_row(p, row, s0 + k, ma);
         }
     }
 }
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
+enum OutMode { OUT_RAW_I32 = 0, OUT_DIV3_U32 = 1, OUT_DIV3_U16 = 2 };
 struct TcParams {
-    const uint32_t* a_nN; const uint32_t* b_nN;
     uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of TN
     uint32_t gx, gy;                           // tiles: gx column blocks x gy row blocks (of TM * CL rows)
+    const uint32_t* tile_list;                 // square panels: the LIVE tiles (by << 20 | bx) in raster order, so that
+    uint32_t n_live;                           // the static round-robin deals only real work; NULL = all gx * gy tiles
     int square;
     uint64_t n_total, out_base;
-    uint32_t* out;
-    uint32_t width;        // valid sites
+    void* out;
     uint32_t wp8;          // bytes per plane
     uint32_t nsb;          // wp8 / KB
-    uint32_t npairs;       // plane pairs summed into this accumulator
-    uint8_t pa[8], pb[8];  // stored-plane index of the A / B operand of each pair
+    uint32_t nacc;         // accumulators (integer counts) computed by this launch: work items = nacc x tiles
+    uint32_t npairs[5];    // plane pairs summed into each accumulator
+    uint8_t pa[5][4], pb[5][4];  // stored-plane index of the A / B operand of each pair
+    uint64_t acc_stride;   // OUT_RAW_I32: results of accumulator a start at out + a * acc_stride
     uint32_t stages;       // pipeline depth in use (<= STAGES; tuning knob)
-    int raw_sums;          // 0: out = width - (acc + nN(q) + nN(t))  (n / n_high);  1: out = acc (int32 scratch)
+    int out_mode;          // OUT_RAW_I32: out = acc (int32 scratch);  OUT_DIV3_*: out = acc / 3 = DIFF (n / n_high, no
+                           // both-partial correction pending), as uint32 or uint16
 };
 
 // Tile order: bands of RASTER_G row blocks, column-major inside a band, so the tiles in flight cover a
@@ -365,9 +471,15 @@ struct TcParams {
 constexpr uint32_t RASTER_G = 8;
 template <int CL, int MT>
 __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_t rank, uint32_t& rowA0, uint32_t& rowB0) {
-    const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
-    const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
-    const uint32_t bx = r / gb, by = band * RASTER_G + (r - bx * gb);
+    uint32_t bx, by;
+    if (p.tile_list) {
+        const uint32_t code = __ldg(p.tile_list + t);
+        bx = code & 0xFFFFFu; by = code >> 20;
+    } else {
+        const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
+        const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
+        bx = r / gb; by = band * RASTER_G + (r - bx * gb);
+    }
     const uint32_t rowS0 = p.row0 + by * (TM * MT * CL);
     rowB0 = (p.col_block0 + bx) * TN;
     rowA0 = rowS0 + rank * (TM * MT);
@@ -407,8 +519,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ntiles = p.gx * p.gy;
-    const uint32_t KT = p.npairs * p.nsb;
+    const uint32_t ntiles = p.tile_list ? p.n_live : p.gx * p.gy;
+    const uint32_t nwork = ntiles * p.nacc;   // accumulator-major: concurrent tiles read the same planes (L2 reuse)
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
     const uint32_t cid = blockIdx.x / CL, ncl = gridDim.x / CL;   // tiles are dealt to clusters
     constexpr uint16_t MC_MASK = (1u << CL) - 1;
@@ -438,20 +550,22 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (uint32_t t = cid; t < ntiles; t += ncl) {
+            for (uint32_t w = cid; w < nwork; w += ncl) {
+                const uint32_t a = w / ntiles, t = w - a * ntiles;
                 uint32_t rowA0, rowB0;
                 if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
+                const uint32_t KT = p.npairs[a] * p.nsb;
                 for (uint32_t kt = 0; kt < KT; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
-                    const int xb = (int)(p.pb[pr] * p.wp8 + sb * KB);
+                    const int xb = (int)(p.pb[a][pr] * p.wp8 + sb * KB);
                     if (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
                         if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * STAGE_BYTES);
 #pragma unroll
                         for (int m = 0; m < MT; m++)
-                            tma_load_2d_pair(sa + m * A_BYTES, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
+                            tma_load_2d_pair(sa + m * A_BYTES, &tmA, (int)(p.pa[a][pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
                         tma_load_2d_pair(sa + MT * A_BYTES, &tmB, xb, (int)(rowB0 + rank * (TN / 2)), full + stage);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         continue;
@@ -459,7 +573,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_arrive_expect_tx(full + stage, STAGE_BYTES);
 #pragma unroll
                     for (int m = 0; m < MT; m++)
-                        tma_load_2d(sa + m * A_BYTES, &tmA, (int)(p.pa[pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
+                        tma_load_2d(sa + m * A_BYTES, &tmA, (int)(p.pa[a][pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
                     uint8_t* sbp = sa + MT * A_BYTES;
                     if (CL == 1) {  // both 128-row halves of the B tile
                         tma_load_2d(sbp, &tmB, xb, (int)rowB0, full + stage);
@@ -476,9 +590,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== MMA issuer (PAIR: the leader CTA issues for both) =====
         if (lane == 0 && (!PAIR || rank == 0)) {
             uint32_t stage = 0, phase = 0, it = 0;
-            for (uint32_t t = cid; t < ntiles; t += ncl) {
+            for (uint32_t w = cid; w < nwork; w += ncl) {
+                const uint32_t a = w / ntiles, t = w - a * ntiles;
                 uint32_t rowA0, rowB0;
                 if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
+                const uint32_t KT = p.npairs[a] * p.nsb;
                 // MT = 1: two accumulators of 256 columns alternate; MT = 2: both are used by every tile
                 const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
                 mbar_wait(tempty + ab, aphase ^ 1);
@@ -507,38 +623,54 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> DIFF -> global, reference order =====
+        // ===== epilogue: TMEM -> registers -> shared-memory transpose -> coalesced stores, reference order =====
+        // tcgen05.ld hands each lane one ROW of the accumulator; storing from there would scatter every
+        // warp store over 32 rows (32 partial sectors).  Each warp transposes its 32 x 32 chunk through a
+        // private conflict-free buffer so that one store instruction writes 32 consecutive results of one row.
         const uint32_t quad = warp & 3;  // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
+        uint32_t* ebuf = reinterpret_cast<uint32_t*>(smem + 192 * 1024 + 256) + quad * (32 * EPI_PITCH);
         uint32_t it = 0;
-        for (uint32_t t = cid; t < ntiles; t += ncl) {
+        for (uint32_t w = cid; w < nwork; w += ncl) {
+            const uint32_t a = w / ntiles, t = w - a * ntiles;
             uint32_t rowA0, rowB0;
             if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
+            uint32_t* const outw = reinterpret_cast<uint32_t*>(p.out) + (uint64_t)a * p.acc_stride;
             const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(tfull + ab, aphase);
             tc_fence_after();
 #pragma unroll 1
             for (int m = 0; m < MT; m++) {
-            const uint32_t row = rowA0 + m * TM + quad * 32 + lane;
-            const bool row_ok = row < p.row_end;
-            const uint32_t nq = (row_ok && !p.raw_sums) ? p.a_nN[row] : 0;
-            const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
-                                               : (uint64_t)(row - p.row0) * p.n_b;
+                const uint32_t rq0 = rowA0 + m * TM + quad * 32;   // first row of this warp's quadrant
+                if (rq0 >= p.row_end) continue;                     // warp-uniform
+                const uint32_t nrows = min(32u, p.row_end - rq0);
+                // index of (rq0, column 0) [rect] / of the virtual element (rq0, rq0 + 1) [square] in the panel
+                const uint64_t base0 = p.square ? (uint64_t)rq0 * (2 * p.n_total - rq0 - 1) / 2 - p.out_base
+                                                : (uint64_t)(rq0 - p.row0) * p.n_b;
 #pragma unroll 1
-            for (uint32_t c = 0; c < TN / 32; c++) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + ((quad * 32u) << 16) + (ab + m) * TN + c * 32, v);
-                if (row_ok) {
+                for (uint32_t c = 0; c < TN / 32; c++) {
+                    const uint32_t col0 = rowB0 + c * 32;
+                    if (col0 >= p.n_b) break;                                   // warp-uniform
+                    if (p.square && col0 + 32 <= rq0 + 1) continue;             // chunk entirely on / below the diagonal
+                    uint32_t v[32];
+                    tc_ld32(tmem_base + ((quad * 32u) << 16) + (ab + m) * TN + c * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const uint32_t col = rowB0 + c * 32 + j;
-                        if (col >= p.n_b) break;
-                        if (p.square && col <= row) continue;
-                        const uint64_t idx = p.square ? row_base + (col - row - 1) : row_base + col;
-                        if (p.raw_sums) p.out[idx] = v[j];
-                        else p.out[idx] = p.width - (v[j] + nq + p.b_nN[col]);
+                    for (int j = 0; j < 32; j++)
+                        ebuf[lane * EPI_PITCH + j] = p.out_mode == OUT_RAW_I32 ? v[j] : v[j] / 3u;
+                    __syncwarp();
+                    const uint32_t col = col0 + lane;
+                    uint64_t rb = base0;
+                    for (uint32_t r = 0; r < nrows; r++) {
+                        const uint32_t row = rq0 + r;
+                        const uint32_t val = ebuf[r * EPI_PITCH + lane];
+                        if (col < p.n_b && (!p.square || col > row)) {
+                            const uint64_t idx = p.square ? rb + (col - row - 1) : rb + col;
+                            if (p.out_mode == OUT_DIV3_U16) reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)val;
+                            else outw[idx] = val;
+                        }
+                        rb += p.square ? (uint64_t)(p.n_total - row - 1) : (uint64_t)p.n_b;
                     }
+                    __syncwarp();
                 }
-            }
             }
             tc_fence_before();
             __syncwarp();
@@ -560,53 +692,55 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 
 // ---- combine: raw int32 sums of the accumulators -> reference counts -> result ------------------------
+//   n, n_high : acc0 = 3 DIFF
+//   raw, jc69 : acc0 = 3 DIFF, acc1 = SAME
+//   k80       : acc0 = CS = SAME + ts, acc1 = X = SAME - ts, acc2 = tv
+//   tn93      : acc0 = L, acc1 = PP = SP + P1, acc2 = YY = SY + P2, acc3 = SP - P1, acc4 = SY - P2
+enum ResultKind { RES_U32 = 0, RES_F64 = 1, RES_U16 = 2, RES_COUNTS = 3 };
 struct CombineParams {
-    const uint32_t* acc;    // [nacc][panel pairs]
+    const int* acc;         // [nacc][panel pairs]
     uint64_t acc_stride;    // pairs per accumulator
-    const uint32_t* a_nN; const uint32_t* b_nN;
     const uint32_t* a_acgt; const uint32_t* b_acgt;
     uint32_t n_b, row0, row_end, col0;
-    int square, swap_roles, measure, fam, counts;
+    int square, swap_roles, measure, fam, result;
     uint64_t n_total, out_base;
-    uint32_t width;
-    void* out;              // double[pairs], or uint4[pairs] canonical counts (dg_debug_counts)
+    void* out;              // uint32 / uint16 / double [pairs], or uint4[pairs] canonical counts (dg_debug_counts)
 };
 
 __global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
     const uint32_t col = p.col0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= p.n_b) return;
     for (uint32_t row = p.row0 + blockIdx.y; row < p.row_end; row += gridDim.y) {
-    if (p.square && col <= row) continue;
-    const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
-                                  : (uint64_t)(row - p.row0) * p.n_b + col;
-    const uint32_t a0 = p.acc[idx];
-    const uint32_t a1 = p.fam != FAM_SNP ? p.acc[p.acc_stride + idx] : 0;
-    uint4 cnt = make_uint4(0, 0, 0, 0);
-    if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
-        const uint32_t diff = p.width - (a0 + p.a_nN[row] + p.b_nN[col]);
-        cnt = make_uint4(diff, a1, 0, 0);  // {n, same}
-    } else if (p.fam == FAM_K80) {
-        const uint32_t tv = p.acc[2 * p.acc_stride + idx];
-        cnt = make_uint4(a0, (a1 - a0) + tv, tv, 0);  // {same, ts + tv, tv}
-    } else {
-        const uint32_t yy = p.acc[2 * p.acc_stride + idx], sp = p.acc[3 * p.acc_stride + idx],
-                       sy = p.acc[4 * p.acc_stride + idx];
-        cnt = make_uint4(a0, a0 - sp - sy, a1 - sp, yy - sy);  // {L, d, P1, P2}
-    }
-    if (p.counts) {
-        reinterpret_cast<uint4*>(p.out)[idx] = cnt;
-        continue;
-    }
-    double r;
-    if (p.fam == FAM_SNP) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; continue; }
-    if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
-    else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z);
-    else {
-        const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
-        const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
-        r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc);
-    }
-    reinterpret_cast<double*>(p.out)[idx] = r;
+        if (p.square && col <= row) continue;
+        const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
+                                      : (uint64_t)(row - p.row0) * p.n_b + col;
+        const int a0 = p.acc[idx];
+        const int a1 = p.fam != FAM_SNP ? p.acc[p.acc_stride + idx] : 0;
+        uint4 cnt = make_uint4(0, 0, 0, 0);
+        if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
+            cnt = make_uint4((uint32_t)a0 / 3u, (uint32_t)a1, 0, 0);  // {n, same}
+        } else if (p.fam == FAM_K80) {
+            const int tv = p.acc[2 * p.acc_stride + idx];
+            const int same = (a0 + a1) >> 1, ts = (a0 - a1) >> 1;
+            cnt = make_uint4((uint32_t)same, (uint32_t)(ts + tv), (uint32_t)tv, 0);  // {same, ts + tv, tv}
+        } else {
+            const int yy = p.acc[2 * p.acc_stride + idx], ww = p.acc[3 * p.acc_stride + idx],
+                      zz = p.acc[4 * p.acc_stride + idx];
+            const int sp = (a1 + ww) >> 1, p1 = (a1 - ww) >> 1, sy = (yy + zz) >> 1, p2 = (yy - zz) >> 1;
+            cnt = make_uint4((uint32_t)a0, (uint32_t)(a0 - sp - sy), (uint32_t)p1, (uint32_t)p2);  // {L, d, P1, P2}
+        }
+        if (p.result == RES_COUNTS) { reinterpret_cast<uint4*>(p.out)[idx] = cnt; continue; }
+        if (p.result == RES_U32) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; continue; }
+        if (p.result == RES_U16) { reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)cnt.x; continue; }
+        double r;
+        if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
+        else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z);
+        else {
+            const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
+            const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
+            r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc);
+        }
+        reinterpret_cast<double*>(p.out)[idx] = r;
     }
 }
 

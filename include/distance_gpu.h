@@ -79,7 +79,8 @@ typedef enum {
 
 typedef enum {
     DG_RESULT_U32 = 0, /* n / n_high: the count; FloatInt::Int, printed `{}`   (src/lib.rs:626-628) */
-    DG_RESULT_F64 = 1  /* raw/jc69/k80/tn93: IEEE bits; FloatInt::Float `{:.12}` (src/lib.rs:630-632) */
+    DG_RESULT_F64 = 1, /* raw/jc69/k80/tn93: IEEE bits; FloatInt::Float `{:.12}` (src/lib.rs:630-632) */
+    DG_RESULT_U16 = 2  /* n / n_high with DG_OPT_RESULT_U16: the same count in 16 bits (halves the D2H bytes) */
 } dg_result_kind;
 
 typedef enum {
@@ -102,7 +103,7 @@ typedef struct {
     uint64_t row_end;    /* one past the last major row */
     uint64_t n_cols;     /* RECT/STREAM: results per row; SQUARE: n (row i has n-1-i results) */
     uint64_t n_results;  /* total results in `data` */
-    const void *data;    /* uint32_t[n_results] or double[n_results]; pinned host memory */
+    const void *data;    /* uint32_t / double / uint16_t [n_results] per result_kind; pinned host memory */
 } dg_panel;
 
 /* Return 0 to continue, non-zero to abort the run (-> DG_ERR_SINK). */
@@ -120,6 +121,8 @@ typedef struct dg_ctx dg_ctx;
 #define DG_OPT_TILE_VARIANT 3 /* tuning: 0 = default tile shape per measure family, >0 = alternatives */
 #define DG_OPT_ENGINE 4      /* 0 = auto (per shape / ambiguity load), 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8
                                 one-hot GEMM.  Set it before dg_load_resident: it decides which operands are built. */
+#define DG_OPT_RESULT_U16 5  /* 0/1: deliver n / n_high panels as uint16_t (DG_RESULT_U16).  A count never exceeds
+                                the width, so this is lossless for width <= 65535 (else DG_ERR_INVALID_ARG). */
 
 typedef struct {
     double pack_ms;       /* pack_planes kernels, CUDA events on the launching stream */

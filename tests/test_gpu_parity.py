@@ -214,8 +214,6 @@ def test_rect_matches_oracle_both_orders(dg, oracle, measure):
 @pytest.mark.parametrize("measure", ALL)
 def test_stream_matches_oracle(dg, oracle, measure, engine):
     from distance_b200 import synth
-    if engine == "tc" and measure in ("n", "n_high", "raw", "jc69"):
-        pytest.skip("engine 2 streams k80 / tn93 only (the ambiguity correction index is per alignment)")
     rng = np.random.default_rng(1234)
     loaded = synth.random_codes(rng, 45, 500, p_ambig=0.2)
     streamed = synth.random_codes(rng, 210, 500, p_ambig=0.2)
@@ -252,6 +250,49 @@ def test_stream_tn93_uppercase_count_quirk(dg, oracle):
         # Paradis input + host-supplied counts gives the same
         got2 = e.stream([streamed[:9], streamed[9:]], acgt_batches=[s_acgt[:9], s_acgt[9:]])
         check("tn93", got2, want)
+
+
+@pytest.mark.parametrize("measure", ["n_high", "raw"])
+def test_no_partial_codes_direct_path(dg, oracle, measure):
+    """Alignments without partial ambiguity codes (only A,C,G,T,N,-,?) need no both-partial repair: the
+    tensor engine's n / n_high epilogue stores DIFF straight from TMEM.  Square, rect and stream."""
+    rng = np.random.default_rng(17)
+    pool = np.array([136, 72, 40, 24, 240, 244, 242], np.uint8)
+    a = pool[rng.choice(7, size=(300, 700), p=[.22, .22, .22, .22, .06, .03, .03])]
+    b = pool[rng.choice(7, size=(77, 700), p=[.22, .22, .22, .22, .06, .03, .03])]
+    with dg.Engine(measure, 700) as e:
+        e.load(0, a)
+        check(measure, e.run_square(), oracle_run(oracle, measure, "square", a))
+        e.load(1, b)
+        check(measure, e.run_rect(), oracle_run(oracle, measure, "rect", a, b))
+        got = e.stream([b[:50], b[50:]], max_batch=64)
+        check(measure, got, oracle_run(oracle, measure, "stream", a, b))
+
+
+@pytest.mark.parametrize("amb", [0.0, 0.3])
+def test_uint16_result_panels(dg, oracle, amb):
+    """DG_OPT_RESULT_U16: n / n_high panels as uint16 (lossless: a count never exceeds the width)."""
+    from distance_b200 import api, synth
+    rng = np.random.default_rng(23)
+    if amb:
+        a, b = synth.random_codes(rng, 520, 900, p_ambig=amb), synth.random_codes(rng, 64, 900, p_ambig=amb)
+    else:
+        pool = np.array([136, 72, 40, 24, 240], np.uint8)
+        a, b = pool[rng.integers(0, 5, size=(520, 900))], pool[rng.integers(0, 5, size=(64, 900))]
+    for measure in ("n", "n_high"):
+        with dg.Engine(measure, 900) as e:
+            e.set_option(api.DG_OPT_RESULT_U16, 1)
+            e.set_option(api.DG_OPT_PANEL_BYTES, 512 * 520 * 2)
+            e.load(0, a)
+            got = e.run_square()
+            assert got.dtype == np.uint16 and len(e.last_panels) >= 2
+            check(measure, got, oracle_run(oracle, measure, "square", a))
+            e.load(1, b)
+            check(measure, e.run_rect(), oracle_run(oracle, measure, "rect", a, b))
+            check(measure, e.stream([b]), oracle_run(oracle, measure, "stream", a, b))
+    with dg.Engine("n_high", 70000) as e:
+        with pytest.raises(dg.DistanceGpuError):
+            e.set_option(api.DG_OPT_RESULT_U16, 1)   # a count could exceed 65535
 
 
 def test_special_values(dg, oracle):
@@ -393,8 +434,6 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
             got = e.run_square()
             assert len(e.last_panels) >= 2 * ndev
             check(measure, got, want)
-            if engine == "tc" and measure == "n_high":
-                continue
             loaded, streamed = codes[:40], codes[40:400]
             e.load(0, loaded)
             got = e.stream([streamed[i:i + 50] for i in range(0, 360, 50)], max_batch=64)
