@@ -144,7 +144,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
         "pair_sites_per_s": value * WIDTH, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak" if args.n is None else "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH,
                    "reference_arm_sample": sample},
@@ -172,20 +172,32 @@ def run_ours(args):
     codes = make_workload(n)
     pinned = api.pinned_array(codes.shape, np.uint8)
     pinned[...] = codes
-    plan = api.plan_panels(MEASURE, api.DG_MODE_SQUARE, n, n, args.panel_bytes)
-    my_pairs = sum(p[2] for p in dist.my_panels(plan, rank, world))
     total_pairs = n * (n - 1) // 2
 
     eng = dg.Engine(MEASURE, WIDTH, gpus=[d.local_rank])
     eng.set_option(api.DG_OPT_PANEL_BYTES, args.panel_bytes)
     eng.set_option(api.DG_OPT_KEEP_CODES, 1)
-    if not args.u32_results:
+    if args.is_int and not args.u32_results:
         eng.set_option(api.DG_OPT_RESULT_U16, 1)   # counts <= width < 65536: lossless, half the D2H bytes
     if args.tile_variant:
         eng.set_option(api.DG_OPT_TILE_VARIANT, args.tile_variant)
     if args.engine:
         eng.set_option(api.DG_OPT_ENGINE, args.engine)
     eng.load(0, pinned)
+    plan = eng.plan(api.DG_MODE_SQUARE)
+    if world > 1:
+        # ranks own panels k % world == rank: pick the panel size (<= the default) whose largest share is smallest
+        best = None
+        for pct in range(100, 59, -4):
+            pb = args.panel_bytes * pct // 100
+            eng.set_option(api.DG_OPT_PANEL_BYTES, pb)
+            pl = eng.plan(api.DG_MODE_SQUARE)
+            worst = max(sum(p[2] for p in dist.my_panels(pl, r, world)) for r in range(world))
+            if best is None or worst < best[0]:
+                best = (worst, pb, pl)
+        args.panel_bytes, plan = best[1], best[2]
+        eng.set_option(api.DG_OPT_PANEL_BYTES, args.panel_bytes)
+    my_pairs = sum(p[2] for p in dist.my_panels(plan, rank, world))
 
     def sync_all():
         d.barrier()
@@ -318,15 +330,15 @@ def run_ours(args):
         line = {
             "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
             "pair_sites_per_s": value * WIDTH, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak" if args.n is None else "strong",
             "vs_baseline": None, "dtype": "i8 (int8 planes, int32 accumulation, tcgen05 kind::i8)" if int(tm.get("engine", 1)) == 2 else "u32 bit-planes (LOP3+POPC)", "data": "synthetic",
             "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
                        "weak_scaling": "n = round(20000*sqrt(N)) so pairs per GPU stay ~2.0e8",
                        "panel_bytes": args.panel_bytes, "panels": len(plan),
                        "l2": "inputs larger than L2 (bit-planes %.0f MB vs 126 MB L2)" % (n * 936 * 16 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
-                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * (4 if args.u32_results else 2)),
-                    "result_type": "u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)"},
+                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
+                    "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
             "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8"}.get(int(tm.get("engine", 0)), "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
         }
@@ -350,7 +362,17 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
+    ap.add_argument("--measure", default="n_high", choices=sorted(OPS_PER_PAIR_SITE),
+                    help="default n_high = BASELINE config 2 (the driver's workload); jc69 + --n 100000 = config 5")
     args = ap.parse_args()
+    global MEASURE, WORKLOAD
+    if args.measure != MEASURE or args.n is not None:
+        MEASURE = args.measure
+        WORKLOAD = (f"-m {MEASURE} all-vs-all, {args.n or BASE_N:,} x 29,903 nt, 1% N/ambiguity/gaps"
+                    + (" (BASELINE config 5)" if MEASURE == "jc69" and args.n == 100000 else ""))
+    args.is_int = MEASURE in ("n", "n_high")
+    if not args.is_int:
+        args.u32_results = True   # f64 panels; the uint16 option only exists for n / n_high
     if args.panel_bytes is None:
         args.panel_bytes = (256 << 20) if args.u32_results else (128 << 20)
     if args.impl == "reference":

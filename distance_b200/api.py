@@ -27,8 +27,8 @@ DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_S
 ABI_SYMBOLS = [
     "dg_abi_version", "dg_device_count", "dg_create", "dg_destroy", "dg_last_error", "dg_set_option",
     "dg_load_resident", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
-    "dg_stream_begin", "dg_stream_push", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
-    "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels",
+    "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
+    "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
     L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
     L.dg_stream_push.argtypes = [vp, vp, u64, i32, vp]
     L.dg_stream_end.argtypes = [vp]
+    L.dg_stream_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.dg_debug_counts.argtypes = [vp, i32, i32, vp]
     L.dg_debug_planes.argtypes = [vp, i32, vp, vp, vp, C.POINTER(u64)]
     L.dg_get_timings.argtypes = [vp, C.POINTER(Timings)]
@@ -118,8 +119,10 @@ def load_library():
     L.dg_free_pinned.restype = None
     L.dg_plan_panels.argtypes = [i32, i32, u64, u64, u64, i32, vp, vp, vp, u64]
     L.dg_plan_panels.restype = C.c_int64
+    L.dg_plan_ctx.argtypes = [vp, i32, vp, vp, vp, u64]
+    L.dg_plan_ctx.restype = C.c_int64
     for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_invalid_site", "dg_run_square",
-                 "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_end",
+                 "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end",
                  "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings"):
         getattr(L, name).restype = i32
     _lib = L
@@ -222,6 +225,16 @@ class Engine:
         r, s, b = C.c_uint64(), C.c_uint64(), C.c_uint8()
         self._check(self.L.dg_invalid_site(self.h, C.byref(r), C.byref(s), C.byref(b)))
         return int(r.value), int(s.value), int(b.value)
+
+    def plan(self, mode: int = DG_MODE_SQUARE):
+        """dg_plan_ctx: [(row_begin, row_end, n_results)] of the panels this engine will produce."""
+        n = self.L.dg_plan_ctx(self.h, mode, None, None, None, 0)
+        if n < 0:
+            self._check(int(n))
+        rb, re_, nr = (np.zeros(max(n, 1), dtype=np.uint64) for _ in range(3))
+        self.L.dg_plan_ctx(self.h, mode, rb.ctypes.data_as(C.c_void_p), re_.ctypes.data_as(C.c_void_p),
+                           nr.ctypes.data_as(C.c_void_p), n)
+        return [(int(rb[k]), int(re_[k]), int(nr[k])) for k in range(n)]
 
     # -- runs ------------------------------------------------------------------------------------
     def _collect(self, total: int):

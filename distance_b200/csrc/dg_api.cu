@@ -416,14 +416,26 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     // tile variants: 0 = cta_group::2 pairs (default): 512 x 256 block per CTA pair, each CTA stages half of B
     //                1 = 128 x 256 per CTA,  2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of B,
     //                3 = 256 x 256 block per CTA (two A sub-tiles, no cluster)
-    const int cl = (c->tile_variant == 2 || c->tile_variant == 0) ? 2 : 1;
-    const int mt = (c->tile_variant == 0 || c->tile_variant == 3) ? 2 : 1;
-    const bool pair = c->tile_variant == 0;
+    int variant = c->tile_variant;
+    const uint32_t nacc_launch = out_mode == tc::OUT_RAW_I32 ? (uint32_t)sch.nacc : 1u;
+    if (variant == 0) {
+        // Small launches cannot fill 74 CTA pairs with 512 x 256 blocks: fall back to 128 x 256 blocks on 148 CTAs
+        // when that finishes sooner (cost ~ rounds x rows per SM; the small tile needs ~1.6x the time per MAC).
+        const int sms = g_num_sms(d.id);
+        const uint64_t rows = p.row1 - p.row0;
+        const uint64_t items_p = (rows + 511) / 512 * tp.gx * nacc_launch, items_1 = (rows + 127) / 128 * tp.gx * nacc_launch;
+        const double cost_p = (double)((items_p + sms / 2 - 1) / (sms / 2)) * 256.0;
+        const double cost_1 = (double)((items_1 + sms - 1) / sms) * 128.0 * 1.6;
+        if (cost_1 < cost_p) variant = 1;
+    }
+    const int cl = (variant == 2 || variant == 0) ? 2 : 1;
+    const int mt = (variant == 0 || variant == 3) ? 2 : 1;
+    const bool pair = variant == 0;
     tp.gy = (uint32_t)((p.row1 - p.row0 + tc::TM * cl * mt - 1) / (tc::TM * cl * mt));
     tp.n_total = A.n; tp.out_base = p.out_base;
     tp.out = out;
     tp.wp8 = (uint32_t)A.tc_wp8; tp.nsb = (uint32_t)(A.tc_wp8 / tc::KB);
-    tp.nacc = out_mode == tc::OUT_RAW_I32 ? (uint32_t)sch.nacc : 1u;
+    tp.nacc = nacc_launch;
     for (uint32_t a = 0; a < tp.nacc; a++) {
         tp.npairs[a] = (uint32_t)sch.npairs[a];
         for (int i = 0; i < sch.npairs[a]; i++) { tp.pa[a][i] = sch.pa[a][i]; tp.pb[a][i] = sch.pb[a][i]; }
@@ -856,7 +868,7 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     Slot& s = d.slot[si];
     CUDA_CHECK(cudaSetDevice(d.id));
     const double th = wall_ms();
-    std::memcpy(s.h_in, codes, (size_t)nb * c->width);
+    if (codes != s.h_in) std::memcpy(s.h_in, codes, (size_t)nb * c->width);   // dg_stream_buffer: filled in place
     const bool host_counts = acgt != nullptr && c->fam == FAM_TN93;
     if (host_counts)
         for (uint64_t i = 0; i < nb * 4; i++) s.h_acgt[i] = (uint32_t)acgt[i];
@@ -1216,6 +1228,26 @@ int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n_cols, 
     return (int64_t)v.size();
 }
 
+int64_t dg_plan_ctx(dg_ctx* ctx, int mode, uint64_t* row_begin, uint64_t* row_end, uint64_t* n_results, uint64_t cap) {
+    if (!ctx) return DG_ERR_INVALID_ARG;
+    int64_t count = 0;
+    const int rc = guarded(ctx, [&] {
+        if (mode != DG_MODE_SQUARE && mode != DG_MODE_RECT) fail(DG_ERR_INVALID_ARG, "mode must be SQUARE or RECT");
+        const PlaneSet& A = ctx->devs[0].set[0];
+        const PlaneSet& B = ctx->devs[0].set[mode == DG_MODE_SQUARE ? 0 : 1];
+        if (A.n == 0 || B.n == 0) fail(DG_ERR_STATE, "alignment not loaded");
+        const TileShape ts = tile_shape(ctx->fam, ctx->tile_variant);
+        const std::vector<Panel> v = make_panels(ctx->panel_bytes, ctx->elem_bytes(), mode, A.n, B.n, ts.tm);
+        for (size_t k = 0; k < v.size() && k < cap; k++) {
+            if (row_begin) row_begin[k] = v[k].row0;
+            if (row_end) row_end[k] = v[k].row1;
+            if (n_results) n_results[k] = v[k].n_results;
+        }
+        count = (int64_t)v.size();
+    });
+    return rc != DG_OK ? rc : count;
+}
+
 int dg_stream_begin(dg_ctx* ctx, dg_sink_fn sink, void* user, uint64_t max_batch) {
     return guarded(ctx, [&] { stream_begin(ctx, sink, user, max_batch); });
 }
@@ -1231,6 +1263,21 @@ int dg_stream_push(dg_ctx* ctx, const uint8_t* codes, uint64_t n_batch, int inpu
             stream_push_one(ctx, codes + off * ctx->width, nb, input_kind,
                             acgt_counts ? acgt_counts + off * 4 : nullptr);
         }
+    });
+    if (rc != DG_OK && ctx && ctx->streaming) stream_abort(ctx);
+    return rc;
+}
+
+int dg_stream_buffer(dg_ctx* ctx, uint8_t** buf, uint64_t* capacity_records) {
+    int rc = guarded(ctx, [&] {
+        if (!ctx->streaming) fail(DG_ERR_STATE, "no stream session is open");
+        if (!buf) fail(DG_ERR_INVALID_ARG, "buf is NULL");
+        const int ndev = (int)ctx->devs.size();
+        // the staging slot of the NEXT batch; it is free once the batch that used it before has been sunk
+        while ((int)ctx->s_queue.size() >= 2 * ndev) stream_sink_front(ctx);
+        const uint64_t bi = ctx->s_batches;
+        *buf = ctx->devs[bi % ndev].slot[(bi / ndev) & 1].h_in;
+        if (capacity_records) *capacity_records = ctx->s_max_batch;
     });
     if (rc != DG_OK && ctx && ctx->streaming) stream_abort(ctx);
     return rc;

@@ -177,10 +177,16 @@ DG_API int dg_run_part(dg_ctx *ctx, int mode, uint32_t part, uint32_t n_parts, d
 /* The panel plan dg_run_square / dg_run_rect / dg_run_part follow, without touching a device (pure
  * host arithmetic; lets a multi-process launcher and CPU tests see the sharding).  mode SQUARE:
  * n_rows = n_cols = n.  Writes up to `cap` panels (row_begin, row_end, n_results) and returns the
- * total number of panels, or a negative DG_ERR_*.  Panel k belongs to part k % n_parts. */
+ * total number of panels, or a negative DG_ERR_*.  Panel k belongs to part k % n_parts.  Assumes the default
+ * result width (uint32 / double); with DG_OPT_RESULT_U16 use dg_plan_ctx. */
 DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n_cols, uint64_t panel_bytes,
                               int tile_variant, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
                               uint64_t cap);
+
+/* The same plan for THIS context: its loaded alignments, panel bytes, tile variant and result width
+ * (uint16 panels hold twice the rows of uint32 ones).  Returns the number of panels or a negative DG_ERR_*. */
+DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
+                           uint64_t cap);
 
 /* -s streaming (replaces stream(), src/lib.rs:269-365): alignment 0 is resident, batches of the
  * streamed alignment are pushed in file order.  Batches are staged through double-buffered pinned
@@ -189,6 +195,11 @@ DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n
 DG_API int dg_stream_begin(dg_ctx *ctx, dg_sink_fn sink, void *user, uint64_t max_batch);
 DG_API int dg_stream_push(dg_ctx *ctx, const uint8_t *codes, uint64_t n_batch, int input_kind,
                    const uint64_t *acgt_counts);
+/* Zero-copy producer: the pinned staging buffer the NEXT dg_stream_push will use (capacity in records =
+ * the session's batch size).  A parser that writes its records straight into *buf and then calls
+ * dg_stream_push(ctx, *buf, n <= capacity, ...) skips the host-side staging copy.  The pointer is valid
+ * until that push; the sink may run inside this call. */
+DG_API int dg_stream_buffer(dg_ctx *ctx, uint8_t **buf, uint64_t *capacity_records);
 DG_API int dg_stream_end(dg_ctx *ctx);
 
 /* Debug / parity: raw integer counts of every pair (a in alignment which_a, b in which_b), from
