@@ -545,7 +545,9 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
     cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
     cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
     cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
-    dim3 grid((unsigned)((B.n - cp.col0 + 255) / 256), (unsigned)std::min<uint64_t>(p.row1 - p.row0, 32768));
+    // ~16 CTAs per SM, each walking many rows of its 256-column strip (one element per thread and row: coalesced)
+    const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
+    dim3 grid(gx, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx))));
     if (grid.x == 0 || grid.y == 0) return;
     tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
     CUDA_CHECK(cudaGetLastError());
@@ -563,20 +565,48 @@ void ensure_scratch(dg_ctx* c, Slot& s, size_t pairs) {
 
 uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
 
+// Live 512 x 256 tiles (the tensor engine's CTA-pair block) of rows [r0, r1) against n_cols columns.
+uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols) {
+    const uint64_t col_blocks = (n_cols + 255) / 256;
+    if (mode != DG_MODE_SQUARE) return (r1 - r0 + 511) / 512 * col_blocks;
+    uint64_t live = 0;
+    for (uint64_t rs = r0; rs < r1; rs += 512) {
+        const uint64_t first = (rs + 1) / 256;   // first column block with a column > rs
+        live += col_blocks > first ? col_blocks - first : 0;
+    }
+    return live;
+}
+
 std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, uint64_t n_rows_total,
                                uint64_t n_cols, int tm) {
-    // rows per panel: a multiple of the tile height sized so one panel's results ~ panel_bytes
+    // rows per panel: a multiple of the tile height sized so one panel's results ~ panel_bytes.  Among the
+    // candidates between half and all of that budget, take the one whose tile count fills whole rounds of the
+    // 74 CTA pairs best (a panel is one persistent launch: a ragged last round idles SMs).
     std::vector<Panel> v;
     const uint64_t rows_major = mode == DG_MODE_SQUARE ? (n_rows_total ? n_rows_total - 1 : 0) : n_rows_total;
     if (rows_major == 0 || n_cols == 0) return v;
-    uint64_t per = panel_bytes / (elem_bytes * std::max<uint64_t>(1, n_cols));
-    per = std::min<uint64_t>(per, (uint64_t)tm * 32768);  // gridDim.y limit
     const uint64_t quantum = std::max<uint64_t>(tm, 512);  // a multiple of every tensor-engine block height (256 / 512 rows)
-    per = std::max<uint64_t>(quantum, per / quantum * quantum);
-    for (uint64_t r = 0; r < rows_major; r += per) {
+    const uint64_t SLOTS = 74;
+    for (uint64_t r = 0; r < rows_major;) {
+        // square rows get shorter as r grows: budget by the pairs left of row r
+        const uint64_t row_len = mode == DG_MODE_SQUARE ? n_rows_total - 1 - r : n_cols;
+        uint64_t per = panel_bytes / (elem_bytes * std::max<uint64_t>(1, row_len));
+        per = std::min<uint64_t>(per, (uint64_t)tm * 32768);  // gridDim.y limit
+        per = std::max<uint64_t>(quantum, per / quantum * quantum);
+        uint64_t best_rows = per;
+        if (r + per < rows_major) {
+            double best_fill = -1;
+            for (uint64_t cand = per; cand >= quantum && cand * 2 >= per; cand -= quantum) {
+                const uint64_t live = live_pair_tiles(mode, r, r + cand, n_cols);
+                const double fill = (double)live / (double)((live + SLOTS - 1) / SLOTS * SLOTS);
+                if (fill > best_fill + 1e-9) { best_fill = fill; best_rows = cand; }
+                if (cand == quantum) break;
+            }
+        }
+        if (r + best_rows < rows_major && rows_major - (r + best_rows) < quantum) best_rows = rows_major - r;  // no sliver panel
         Panel p;
         p.row0 = r;
-        p.row1 = std::min(rows_major, r + per);
+        p.row1 = std::min(rows_major, r + best_rows);
         if (mode == DG_MODE_SQUARE) {
             p.out_base = sq_off(n_rows_total, p.row0);
             p.n_results = sq_off(n_rows_total, p.row1) - p.out_base;
@@ -585,6 +615,7 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
             p.n_results = (p.row1 - p.row0) * n_cols;
         }
         v.push_back(p);
+        r = p.row1;
     }
     return v;
 }

@@ -275,14 +275,14 @@ def test_uint16_result_panels(dg, oracle, amb):
     from distance_b200 import api, synth
     rng = np.random.default_rng(23)
     if amb:
-        a, b = synth.random_codes(rng, 520, 900, p_ambig=amb), synth.random_codes(rng, 64, 900, p_ambig=amb)
+        a, b = synth.random_codes(rng, 1100, 900, p_ambig=amb), synth.random_codes(rng, 64, 900, p_ambig=amb)
     else:
         pool = np.array([136, 72, 40, 24, 240], np.uint8)
-        a, b = pool[rng.integers(0, 5, size=(520, 900))], pool[rng.integers(0, 5, size=(64, 900))]
+        a, b = pool[rng.integers(0, 5, size=(1100, 900))], pool[rng.integers(0, 5, size=(64, 900))]
     for measure in ("n", "n_high"):
         with dg.Engine(measure, 900) as e:
             e.set_option(api.DG_OPT_RESULT_U16, 1)
-            e.set_option(api.DG_OPT_PANEL_BYTES, 512 * 520 * 2)
+            e.set_option(api.DG_OPT_PANEL_BYTES, 512 * 1100 * 2)
             e.load(0, a)
             got = e.run_square()
             assert got.dtype == np.uint16 and len(e.last_panels) >= 2
@@ -326,7 +326,7 @@ def test_panels_and_parts_cover_the_triangle(dg, oracle, measure):
         e.set_option(api.DG_OPT_PANEL_BYTES, 512 * n * (4 if measure == "n_high" else 8))
         e.load(0, codes)
         got = e.run_square()
-        assert len(e.last_panels) >= 5
+        assert len(e.last_panels) >= 4
         check(measure, got, want)
         # two ranks, no collective: interleave their panels back into global order
         parts = e.run_part(api.DG_MODE_SQUARE, 0, 2) + e.run_part(api.DG_MODE_SQUARE, 1, 2)
@@ -424,7 +424,7 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
     if ndev < 2:
         pytest.skip("needs >= 2 GPUs")
     rng = np.random.default_rng(21)
-    n, width = 2100, 300
+    n, width = max(2100, 1100 * ndev), 300   # >= 2 panels of >= 512 rows per device
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     for measure in ("n_high", "tn93"):
         want = oracle_run(oracle, measure, "square", codes)

@@ -13,11 +13,14 @@ ap.add_argument("--n", type=int, default=20000)
 ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--panel-bytes", type=int, default=128 << 20)
+ap.add_argument("--u16", action="store_true", help="uint16 result panels (n / n_high), like bench.py")
 a = ap.parse_args()
 codes = synth.encode_ascii(synth.make_alignment(a.n, seed=20251018 + 2, ambiguity=True))
 e = dg.Engine(a.measure, synth.SC2_WIDTH)
 e.set_option(api.DG_OPT_PANEL_BYTES, a.panel_bytes)
 e.set_option(api.DG_OPT_KEEP_CODES, 1)
+if a.u16:
+    e.set_option(api.DG_OPT_RESULT_U16, 1)
 if a.variant:
     e.set_option(api.DG_OPT_TILE_VARIANT, a.variant)
 e.load(0, codes)
