@@ -279,36 +279,52 @@ def run_ours(args):
                 "tensor bound (SURVEY 8d); consecutive panel launches overlap on two streams, so achieved uses "
                 "the device time of the whole step; traffic = DRAM bytes of one profiled launch (see profiles/)",
     }
-    if int(tm.get("engine", 1)) == 2:
-        # tcgen05 engine: ALGORITHMIC int8 ops (5 MAC = 10 ops per pair-site for n / n_high) of this
-        # rank's launches / device time of the step, against the MEASURED kind::i8 issue rate.
+    engine_id = int(tm.get("engine", 1))
+    if engine_id in (2, 3):
+        # tcgen05 engines: executed ALGORITHMIC tensor ops (2 per MAC) of this rank's launches /
+        # device time of the step, against the MEASURED issue rate of the instruction kind that ran.
         i8ops = my_pairs * WIDTH * float(I8_OPS_PER_PAIR_SITE[MEASURE])
         ach = i8ops / (run_ms_step * 1e-3) / 1e12
-        pk8 = peaks.get("int8_tops_measured")
-        src8 = "measured: tools/ubench_tc (profiles/ubench_tc_r01.json), tcgen05.mma kind::i8 M128 N256 K32 SS on 148 SMs"
-        if not pk8:
-            pk8 = 2.0 * measured.get("bf16_tflops", 1590.0)
-            src8 = "2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json (kind::i8 is nominally 2 x bf16)"
+        if engine_id == 3:
+            pk8 = peaks.get("fp4_tops_measured")
+            src8 = ("measured: tools/ubench_fp4 (profiles/ubench_fp4_r01.json), tcgen05.mma kind::mxf4.block_scale M128 N256 K64 SS "
+                    "on 148 SMs; nominal dense fp4 = 9,000 TOPS")
+            kname, unit = "tc_gemm_kernel<FP4> (tcgen05.mma kind::mxf4.block_scale, unit scales, TMA, TMEM)", "TOP/s (fp4; the spec's TFLOP/s slot)"
+            if not pk8:
+                pk8, src8 = 9000.0, "nominal dense fp4 of B200_PROFILING.md (no measured file)"
+        else:
+            pk8 = peaks.get("int8_tops_measured")
+            src8 = "measured: tools/ubench_tc (profiles/ubench_tc_r01.json), tcgen05.mma kind::i8 M128 N256 K32 SS on 148 SMs"
+            kname, unit = "tc_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)", "TOP/s (int8; the spec's TFLOP/s slot)"
+            if not pk8:
+                pk8 = 2.0 * measured.get("bf16_tflops", 1590.0)
+                src8 = "2 x the measured bf16 cuBLAS figure of MEASURED_PEAKS.json (kind::i8 is nominally 2 x bf16)"
         roofline = {
-            "bound": "tensor", "kernel": "tc_gemm_kernel (tcgen05.mma kind::i8, TMA, TMEM)", "achieved": ach, "peak": pk8,
-            "unit": "TOP/s (int8; the spec's TFLOP/s slot)", "frac": ach / pk8,
+            "bound": "tensor", "kernel": kname, "achieved": ach, "peak": pk8,
+            "unit": unit, "frac": ach / pk8,
+            "frac_of_int8_peak": ach / peaks["int8_tops_measured"] if peaks.get("int8_tops_measured") else None,
             "traffic": peaks.get("tc_kernel_dram_bytes_per_launch"),
             "ops_per_pair_site": I8_OPS_PER_PAIR_SITE[MEASURE], "peak_source": src8,
             "frac_in_survey_units": ach / pk8 * 10.0 / I8_OPS_PER_PAIR_SITE[MEASURE],
             "padded_frac": ach / pk8 * (math.ceil(WIDTH / 128) * 128) / WIDTH,
             "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
-            "note": "achieved = executed algorithmic int8 ops (4 MAC per pair-site: DIFF as a rank-4 bilinear form, "
+            "note": "achieved = executed algorithmic tensor ops (4 MAC per pair-site: DIFF as a rank-4 bilinear form, "
                     "DESIGN.md 3.1) / device time of the whole step (operand re-pack included); frac_in_survey_units "
                     "scores the same time against SURVEY 8d's 5-MAC budget.  padded_frac counts the 49 zero-padded "
-                    "sites per 128-site K block as work done.  Engine chosen automatically (DG_OPT_ENGINE=0).",
+                    "sites per K block as work done.  Engine chosen automatically (DG_OPT_ENGINE=0): E2M1 operands "
+                    "with unit block scales and fp32 accumulation are exact for these integer sums (tools/ubench_fp4, "
+                    "parity suite), so the fp4 tensor rate applies; frac_of_int8_peak scores the same ops against kind::i8.",
         }
     else:
         roofline = roofline_lop3
     hbm = measured.get("hbm_gbs")
     pack_ms_step = tm["pack_ms"] / args.steps
-    if int(tm.get("engine", 1)) == 2:
+    if engine_id == 3:
+        pack_bytes = n * WIDTH + n * 8 * math.ceil(WIDTH / 256) * 128  # read 1 B/site, write 8 E2M1 planes (U, V), 2 sites per byte
+        pack_kernel = "pack_ops_kernel<FP4>"
+    elif engine_id == 2:
         pack_bytes = n * WIDTH + n * 8 * math.ceil(WIDTH / 128) * 128  # read 1 B/site, write 8 int8 planes (U, V)
-        pack_kernel = "pack_i8_kernel"
+        pack_kernel = "pack_ops_kernel<int8>"
     else:
         pack_bytes = n * WIDTH + n * math.ceil(WIDTH / 32) * 16  # read 1 B/site, write the 4 core bit-planes
         pack_kernel = "pack_planes_kernel"
@@ -331,15 +347,16 @@ def run_ours(args):
             "metric": "pairwise distances/sec", "value": value, "unit": "pairs/s",
             "pair_sites_per_s": value * WIDTH, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": step_ms, "wall_ms_per_step": wall_step_ms, "higher_is_better": True, "scaling": "weak" if args.n is None else "strong",
-            "vs_baseline": None, "dtype": "i8 (int8 planes, int32 accumulation, tcgen05 kind::i8)" if int(tm.get("engine", 1)) == 2 else "u32 bit-planes (LOP3+POPC)", "data": "synthetic",
+            "vs_baseline": None, "dtype": {3: "fp4 (E2M1 planes, unit UE8M0 block scales, fp32 accumulation: exact integer sums; tcgen05 kind::mxf4)",
+                                          2: "i8 (int8 planes, int32 accumulation, tcgen05 kind::i8)"}.get(engine_id, "u32 bit-planes (LOP3+POPC)"), "data": "synthetic",
             "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH, "pairs_per_step": total_pairs,
                        "weak_scaling": "n = round(20000*sqrt(N)) so pairs per GPU stay ~2.0e8",
                        "panel_bytes": args.panel_bytes, "panels": len(plan),
-                       "l2": "inputs larger than L2 (bit-planes %.0f MB vs 126 MB L2)" % (n * 936 * 16 / 1e6)},
+                       "l2": "inputs larger than L2 (operand planes %.0f MB vs 126 MB L2)" % (n * 8 * 14976 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
                     "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
-            "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8"}.get(int(tm.get("engine", 0)), "?"),
+            "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}.get(engine_id, "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -358,7 +375,7 @@ def main():
     ap.add_argument("--panel-bytes", type=int, default=None,
                     help="result panel size (default: 6.7e7 results per panel = 128 MiB of uint16 / 256 MiB of uint32)")
     ap.add_argument("--tile-variant", type=int, default=0)
-    ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05")
+    ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05 int8, 3 tcgen05 fp4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")

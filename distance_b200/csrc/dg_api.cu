@@ -101,6 +101,7 @@ struct PlaneSet {  // one alignment packed on one device
     bool tc_ready = false;    // tc_ops / pp hold the current alignment
     // tcgen05 engine (DG_OPT_ENGINE = 2): int8 one-hot operand planes, N-like counts, partial-code index
     int8_t* tc_ops = nullptr;
+    bool tc_fp4 = false;      // tc_ops hold E2M1 nibbles (engine 3) instead of int8 (engine 2)
     uint64_t tc_wp8 = 0;
     tc::PpIndex pp;
     CUtensorMap map_a{}, map_b{};  // box 128 rows / box 256 rows over tc_ops
@@ -171,7 +172,8 @@ struct dg_ctx {
     bool keep_codes = false;
     int tile_variant = 0;
     int engine = 0;       // DG_OPT_ENGINE
-    int last_engine = 0;  // engine the last run used (1 LOP3, 2 tcgen05)
+    int last_engine = 0;  // engine the last run used (1 LOP3, 2 tcgen05 int8, 3 tcgen05 fp4)
+    bool want_fp4() const { return engine == 0 || engine == 3; }   // operand format of the tensor engine
     // invalid-site report
     bool have_invalid = false;
     uint64_t inv_record = 0, inv_site = 0;
@@ -327,12 +329,15 @@ constexpr uint32_t TC_VPLANE0 = 4;
 
 void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
     const TcSchedule& sch = tc_schedule(c->fam);
-    const uint64_t wp8 = (c->width + tc::KB - 1) / tc::KB * tc::KB;
+    s.tc_fp4 = c->want_fp4();
+    // one 128-byte K block = 128 sites of int8 or 256 sites of E2M1 nibbles
+    const uint64_t sites_per_block = s.tc_fp4 ? 2 * tc::KB : tc::KB;
+    const uint64_t wp8 = (c->width + sites_per_block - 1) / sites_per_block * tc::KB;
     s.tc_wp8 = wp8;
     CUDA_CHECK(cudaMalloc(&s.tc_ops, (size_t)s.n_pad * sch.nplanes * wp8));
     const uint64_t row_bytes = (uint64_t)sch.nplanes * wp8;
     make_ops_map(&s.map_a, s.tc_ops, row_bytes, s.n_pad, tc::TM);
-    make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, tc::TN);
+    make_ops_map(&s.map_b, s.tc_ops, row_bytes, s.n_pad, s.tc_fp4 ? tc::TN_FP4 / 2 : tc::TN);  // fp4: one CTA's half of B
 }
 
 // Enqueue (no sync) the int8 operand planes (and, with count_acgt, the per-record A,T,G,C counts) of rows
@@ -350,7 +355,8 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
-    tc::pack_i8_kernel<<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
+    if (s.tc_fp4) tc::pack_ops_kernel<true><<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
+    else tc::pack_ops_kernel<false><<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
     CUDA_CHECK(cudaGetLastError());
     c->tm.pack_launches++;
 }
@@ -393,11 +399,11 @@ int g_num_sms(int dev) {
 // GEMM (adversarially ambiguous alignments stay on the LOP3 tiles, which need no correction).
 bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
     if (c->engine == 1) return false;
-    if (!A.tc_ready || !B.tc_ready) {
-        if (c->engine == 2) fail(DG_ERR_STATE, "tensor-engine operands were not built (set DG_OPT_ENGINE before loading)");
+    if (!A.tc_ready || !B.tc_ready || A.tc_fp4 != B.tc_fp4 || A.tc_fp4 != c->want_fp4()) {
+        if (c->engine >= 2) fail(DG_ERR_STATE, "tensor-engine operands were not built for this engine (set DG_OPT_ENGINE before loading)");
         return false;
     }
-    if (c->engine == 2) return true;
+    if (c->engine >= 2) return true;
     if (!tc_schedule(c->fam).needs_pp) return true;
     const double work = std::sqrt(A.pp.pair_work * B.pp.pair_work);
     return work <= 2.0 * (double)A.n * (double)B.n;
@@ -411,14 +417,16 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     tp.n_b = (uint32_t)B.n;
     tp.row0 = (uint32_t)p.row0; tp.row_end = (uint32_t)p.row1;
     tp.square = mode == DG_MODE_SQUARE ? 1 : 0;
-    tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tc::TN) : 0;
-    tp.gx = (uint32_t)((B.n + tc::TN - 1) / tc::TN) - tp.col_block0;
+    const bool fp4 = A.tc_fp4;
+    tp.tn = fp4 ? tc::TN_FP4 : tc::TN;
+    tp.col_block0 = tp.square ? (uint32_t)((p.row0 + 1) / tp.tn) : 0;
+    tp.gx = (uint32_t)((B.n + tp.tn - 1) / tp.tn) - tp.col_block0;
     // tile variants: 0 = cta_group::2 pairs (default): 512 x 256 block per CTA pair, each CTA stages half of B
     //                1 = 128 x 256 per CTA,  2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of B,
     //                3 = 256 x 256 block per CTA (two A sub-tiles, no cluster)
-    int variant = c->tile_variant;
+    int variant = fp4 ? 0 : c->tile_variant;   // the FP4 operands run on the cta_group::2 kernel only
     const uint32_t nacc_launch = out_mode == tc::OUT_RAW_I32 ? (uint32_t)sch.nacc : 1u;
-    if (variant == 0) {
+    if (variant == 0 && !fp4) {
         // Small launches cannot fill 74 CTA pairs with 512 x 256 blocks: fall back to 128 x 256 blocks on 148 CTAs
         // when that finishes sooner (cost ~ rounds x rows per SM; the small tile needs ~1.6x the time per MAC).
         const int sms = g_num_sms(d.id);
@@ -464,8 +472,8 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
             for (uint32_t bx = 0; bx < tp.gx; bx++)
                 for (uint32_t by = band0; by < band0 + gb; by++) {
                     const uint64_t rowS0 = (uint64_t)tp.row0 + (uint64_t)by * rows_per_block;
-                    const uint64_t rowB0 = (uint64_t)(tp.col_block0 + bx) * tc::TN;
-                    if (rowS0 >= tp.row_end || rowB0 + tc::TN <= rowS0 + 1) continue;
+                    const uint64_t rowB0 = (uint64_t)(tp.col_block0 + bx) * tp.tn;
+                    if (rowS0 >= tp.row_end || rowB0 + tp.tn <= rowS0 + 1) continue;
                     ws->h_tiles[n_live++] = (by << 20) | bx;
                 }
         }
@@ -482,7 +490,8 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         kern<<<grid, tc::THREADS, tc::SMEM_BYTES, st>>>(A.map_a, B.map_a, tp);
         CUDA_CHECK(cudaGetLastError());
     } else {
-        auto kern2 = pair ? tc::tc_gemm_kernel<2, 2, true> : tc::tc_gemm_kernel<2, 1, false>;
+        auto kern2 = fp4 ? tc::tc_gemm_kernel<2, 2, true, true>
+                         : (pair ? tc::tc_gemm_kernel<2, 2, true, false> : tc::tc_gemm_kernel<2, 1, false, false>);
         CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(2 * (unsigned)std::min<uint64_t>(tiles, (uint64_t)g_num_sms(d.id) / 2));
@@ -493,7 +502,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, A.map_a, B.map_a, tp));
+        CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, A.map_a, fp4 ? B.map_b : B.map_a, tp));
     }
     c->tm.count_launches++;
 }
@@ -528,7 +537,9 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
         if (a_is_batch) {
             cp.a_ops = A.tc_ops; cp.a_nplanes = (uint32_t)sch.nplanes; cp.a_wp8 = (uint32_t)A.tc_wp8; cp.a_vplane0 = TC_VPLANE0;
             const uint64_t units = (p.row1 - p.row0) * (A.tc_wp8 / 16);
-            tc::pp_correct_scan_kernel<<<(unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 16), 256, 0, st>>>(cp);
+            const unsigned gb = (unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 16);
+            if (A.tc_fp4) tc::pp_correct_scan_kernel<true><<<gb, 256, 0, st>>>(cp);
+            else tc::pp_correct_scan_kernel<false><<<gb, 256, 0, st>>>(cp);
         } else {
             cp.a_entries = A.pp.entries; cp.a_n = A.pp.n_entries;
             tc::pp_correct_kernel<<<(A.pp.n_entries + 255) / 256, 256, 0, st>>>(cp);
@@ -658,7 +669,7 @@ void harvest_kernel_time(dg_ctx* c, Slot& s) {
 // (Re)size the buffers of a resident alignment; buffers are kept when the new alignment fits.
 void reserve_resident(dg_ctx* c, PlaneSet& s, uint64_t n, bool want_tc) {
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
-    const bool fits = s.codes && s.cap_pad >= n_pad && (!want_tc || s.tc_ops);
+    const bool fits = s.codes && s.cap_pad >= n_pad && (!want_tc || (s.tc_ops && s.tc_fp4 == c->want_fp4()));
     if (!fits) {
         free_set(s);
         s.cap_pad = n_pad;
@@ -713,7 +724,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     }
 
     const bool tc_run = use_tc(c, c->devs[0].set[0], c->devs[0].set[wb]);
-    c->last_engine = tc_run ? 2 : 1;
+    c->last_engine = tc_run ? (c->devs[0].set[0].tc_fp4 ? 3 : 2) : 1;
     if (!tc_run)
         for (auto& d : c->devs)
             for (int w = 0; w <= wb; w++) ensure_lop3(c, d, d.set[w]);
@@ -854,7 +865,7 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     // so full of partial ambiguity codes that the repair would dominate; then the LOP3 tiles run.
     const PlaneSet& R0 = c->devs[0].set[0];
     const bool cheap_pp = !tc_schedule(c->fam).needs_pp || R0.pp.pair_work <= 2.0 * (double)R0.n * (double)R0.n;
-    const bool s_tc = c->engine != 1 && R0.tc_ready && (c->engine == 2 || cheap_pp);
+    const bool s_tc = c->engine != 1 && R0.tc_ready && R0.tc_fp4 == c->want_fp4() && (c->engine >= 2 || cheap_pp);
     if (!s_tc)
         for (auto& d : c->devs) ensure_lop3(c, d, d.set[0]);
     for (auto& d : c->devs) {
@@ -862,7 +873,8 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
         if (s_tc)
             for (auto& sl : d.slot) ensure_scratch(c, sl, (size_t)mb * n_res);
-        if (d.in_cap < mb || (s_tc && !d.slot[0].batch.tc_ops) || (!s_tc && !d.slot[0].batch.core)) {
+        if (d.in_cap < mb || (s_tc && (!d.slot[0].batch.tc_ops || d.slot[0].batch.tc_fp4 != c->want_fp4())) ||
+            (!s_tc && !d.slot[0].batch.core)) {
             for (auto& s : d.slot) {
                 if (s.h_in) cudaFreeHost(s.h_in);
                 if (s.d_in) cudaFree(s.d_in);
@@ -880,7 +892,7 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     }
     c->streaming = true;
     c->s_tc = s_tc;
-    c->last_engine = s_tc ? 2 : 1;
+    c->last_engine = s_tc ? (R0.tc_fp4 ? 3 : 2) : 1;
     c->s_sink = sink;
     c->s_user = user;
     c->s_rows_pushed = 0;
@@ -1107,7 +1119,7 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
     }
     if (const char* e = std::getenv("DG_ENGINE")) {  // developer override: 1 = LOP3+POPC tiles, 2 = tcgen05 int8 GEMM
         const int v = std::atoi(e);
-        if (v >= 0 && v <= 2) c->engine = v;
+        if (v >= 0 && v <= 3) c->engine = v;
     }
     *out = c;
     return DG_OK;
@@ -1133,7 +1145,7 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             ctx->result_u16 = value != 0;
             break;
         case DG_OPT_ENGINE:
-            if (value < 0 || value > 2) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
+            if (value < 0 || value > 3) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
             ctx->engine = (int)value;
             break;
         default: fail(DG_ERR_INVALID_ARG, "unknown option %d", key);

@@ -42,6 +42,7 @@ namespace tc {
 
 constexpr int TM = 128;          // tile rows    (UMMA M)
 constexpr int TN = 256;          // tile columns (UMMA N)
+constexpr int TN_FP4 = 240;      // tile columns of the FP4 variant
 constexpr int KB = 128;          // K bytes per stage = one 128B swizzle atom = 128 sites of one plane
 constexpr int STAGES = 4;        // barrier slots; MT = 1 uses 4 stages of 48 KB, MT = 2 uses 3 stages of 64 KB
 constexpr int A_BYTES = TM * KB;
@@ -168,6 +169,20 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr uint32_t IDESC_I8 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 constexpr uint32_t IDESC_I8_PAIR = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);  // M = 256 over two CTAs
 
+// kind::mxf4 block-scaled instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptorBlockScaled): a_format
+// [7,10) = b_format [10,13) = 1 (E2M1), both K-major, n_dim [17,23) = N >> 3, scale_format [23] = 1 (UE8M0), m_dim
+// [24,29) = M >> 4, scale-factor ids 0, k_size [31] = 0 (K = 64).  M = 256 over the CTA pair, N = 240.
+constexpr uint32_t IDESC_F4_PAIR = (1u << 7) | (1u << 10) | ((uint32_t)(TN_FP4 >> 3) << 17) | (1u << 23) | ((uint32_t)((2 * TM) >> 4) << 24);
+constexpr uint32_t SF_COL = TN_FP4;   // TMEM columns [240, 256) of the first accumulator's block hold the unit scale factors
+__device__ __forceinline__ void tc_mma_f4_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                               uint32_t sfa_tmem, uint32_t sfb_tmem) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem) : "memory");
+}
+
 // ---- operand packing ------------------------------------------------------------------------------
 // Plane ids.  A plane holds one int8 per site; every plane is 0 for N-like codes (N, '-', '?') and for the
 // zero padding beyond `width` / beyond the last record, so padding lands in no count.
@@ -183,7 +198,7 @@ constexpr int MAX_PLANES = 12;
 struct PackI8Params {
     const uint8_t* codes;  // n x width
     uint64_t n, n_pad, width;
-    uint64_t wp8;          // bytes per plane (width rounded up to 128)
+    uint64_t wp8;          // bytes per plane: width rounded up to 128 sites (int8) / 256 sites at 2 per byte (FP4)
     int8_t* ops;           // n_pad x nplanes x wp8
     uint32_t* acgt;        // n_pad x 4 (A,T,G,C) written per record, or NULL
     int ascii;
@@ -229,12 +244,107 @@ __device__ __forceinline__ uint32_t plane_word(const CodeBits& b, uint32_t id) {
     }
 }
 
-// One CTA per record (grid-stride), one thread per 16-site group: 16 code bytes are fetched with aligned
-// 32-bit loads + funnel shifts (rows are `width` bytes apart, so they are not 16-byte aligned), translated
-// through a 256-entry LUT in shared memory (ASCII -> Paradis, encoding.rs:4-41; or Paradis -> itself if
-// legal), expanded to every stored plane with byte-SIMD arithmetic and written as one 16-byte store per
-// plane.  Per-record A,T,G,C counts (count_bases, fastaio.rs:53-66) are reduced in the CTA: no atomics.
-__global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
+// ---- FP4 planes: the same plane values as E2M1 nibbles, computed 8 sites at a time in nibble lanes -------------
+// E2M1 codes of the values that occur: 0 -> 0x0, 1 -> 0x2, 2 -> 0x4, 3 -> 0x5, -1 -> 0xA, -2 -> 0xC.
+constexpr uint32_t N1 = 0x11111111u;
+// byte lanes (value < 16 in each of 4 bytes) -> 4 nibbles in the low 16 bits
+__device__ __forceinline__ uint32_t squeeze4(uint32_t x) {
+    x = (x | (x >> 4)) & 0x00FF00FFu;
+    return (x | (x >> 8)) & 0xFFFFu;
+}
+// Eight Paradis codes (two words) -> 0/1 nibble-lane words of the code bits, and the two bits of E = |S| - 1.
+struct NibBits { uint32_t A, G, C, T, K, e0, e1; };
+__device__ __forceinline__ NibBits nib_bits(uint32_t wlo, uint32_t whi) {
+    const uint32_t H = squeeze4((wlo >> 4) & 0x0F0F0F0Fu) | (squeeze4((whi >> 4) & 0x0F0F0F0Fu) << 16);  // nibble = A G C T
+    const uint32_t L = squeeze4(wlo & 0x0F0F0F0Fu) | (squeeze4(whi & 0x0F0F0F0Fu) << 16);                // nibble = K . . .
+    NibBits b;
+    b.A = (H >> 3) & N1; b.G = (H >> 2) & N1; b.C = (H >> 1) & N1; b.T = H & N1; b.K = (L >> 3) & N1;
+    const uint32_t E = b.A + b.G + b.C + b.T - N1;   // >= 1 possibility bit per valid code: no borrow between lanes
+    b.e0 = E & N1; b.e1 = (E >> 1) & N1;
+    return b;
+}
+__device__ __forceinline__ uint32_t nib_v(const NibBits& n, uint32_t b) {   // V_b = 3 b - E as E2M1
+    const uint32_t x = n.e1 & ~n.e0, y = n.e0 & ~n.e1, nz = n.e0 | n.e1;     // E == 2, E == 1, E != 0
+    const uint32_t b3 = nz & ~b;                       // negative: base impossible in an ambiguous code
+    const uint32_t b2 = (b & ~n.e1) | (~b & x);        // 3, 2 | -2
+    const uint32_t b1 = (b & x) | (~b & y);            // 1    | -1
+    const uint32_t b0 = b & ~nz;                       // 3
+    return (b0 & N1) | ((b1 & N1) << 1) | ((b2 & N1) << 2) | ((b3 & N1) << 3);
+}
+__device__ __forceinline__ uint32_t nib_pm(uint32_t pos, uint32_t neg) { return ((pos | neg) << 1) | (neg << 3); }  // +1 / -1
+// The eight E2M1 nibbles of plane `id`.
+__device__ __forceinline__ uint32_t plane_nib8(const NibBits& n, uint32_t id) {
+    switch (id) {
+    case P_UA: return (n.A ^ N1) << 1;
+    case P_UG: return (n.G ^ N1) << 1;
+    case P_UC: return (n.C ^ N1) << 1;
+    case P_UT: return (n.T ^ N1) << 1;
+    case P_VA: return nib_v(n, n.A);
+    case P_VG: return nib_v(n, n.G);
+    case P_VC: return nib_v(n, n.C);
+    case P_VT: return nib_v(n, n.T);
+    case P_KA: return (n.A & n.K) << 1;
+    case P_KG: return (n.G & n.K) << 1;
+    case P_KC: return (n.C & n.K) << 1;
+    case P_KT: return (n.T & n.K) << 1;
+    case P_PURK: return ((n.A | n.G) & n.K) << 1;
+    case P_PYRK: return ((n.C | n.T) & n.K) << 1;
+    case P_K: return n.K << 1;
+    case P_W: return nib_pm(n.A & n.K, n.G & n.K);
+    case P_Z: return nib_pm(n.C & n.K, n.T & n.K);
+    case P_PURC: return ((n.A | n.G) & ~(n.C | n.T)) << 1;
+    default: return ((n.C | n.T) & ~(n.A | n.G)) << 1;   // P_PYRC
+    }
+}
+
+// 16 code bytes of `row` starting at site s0 -> four words of valid Paradis codes (invalid bytes reported and
+// replaced by N; sites >= width are N).  raw[] = the untranslated bytes (for the upper-case ASCII count quirk).
+__device__ __forceinline__ void load_codes16(const PackI8Params& p, const uint8_t* row, uint64_t seq, uint64_t s0,
+                                             const uint8_t* lut, uint32_t (&w)[4], uint32_t (&raw)[4]) {
+    if (s0 + 20 <= p.width) {   // the aligned window [a & ~3, +20) stays inside this row
+        const uintptr_t a = reinterpret_cast<uintptr_t>(row + s0);
+        const uint32_t* ap = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8;
+        const uint32_t x0 = __ldg(ap), x1 = __ldg(ap + 1), x2 = __ldg(ap + 2), x3 = __ldg(ap + 3), x4 = __ldg(ap + 4);
+        raw[0] = __funnelshift_r(x0, x1, sh); raw[1] = __funnelshift_r(x1, x2, sh);
+        raw[2] = __funnelshift_r(x2, x3, sh); raw[3] = __funnelshift_r(x3, x4, sh);
+    } else {                    // last groups of the row: byte loads, bounded by width
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t s = s0 + 4 * k + j;
+                const uint32_t byte = s < p.width ? (uint32_t)row[s] : (p.ascii ? (uint32_t)'N' : 240u);
+                v |= byte << (8 * j);
+            }
+            raw[k] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t r = raw[k];
+        uint32_t t = (uint32_t)lut[r & 0xFF] | ((uint32_t)lut[(r >> 8) & 0xFF] << 8) |
+                     ((uint32_t)lut[(r >> 16) & 0xFF] << 16) | ((uint32_t)lut[r >> 24] << 24);
+        if ((t - M1) & ~t & 0x80808080u) {   // a zero byte = invalid nucleotide (fastaio.rs:111-113)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (((t >> (8 * j)) & 0xFFu) == 0) {
+                    if (p.invalid) atomicMin(p.invalid, ((unsigned long long)(p.seq0 + seq) << 32) | (unsigned long long)(s0 + 4 * k + j));
+                    t |= 0xF0u << (8 * j);
+                }
+        }
+        w[k] = t;
+    }
+}
+
+// One CTA per record (grid-stride), one thread per 16-byte store of every plane (16 sites of int8 planes, 32 sites of
+// FP4 planes): the code bytes are fetched with aligned 32-bit loads + funnel shifts (rows are `width` bytes apart,
+// so they are not 16-byte aligned), translated through a 256-entry LUT in shared memory (ASCII -> Paradis,
+// encoding.rs:4-41; or Paradis -> itself if legal) and expanded to every stored plane with byte-SIMD arithmetic.
+// Per-record A,T,G,C counts (count_bases, fastaio.rs:53-66) are reduced in the CTA: no atomics.
+template <bool FP4>
+__global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
     __shared__ uint8_t lut[256];
     __shared__ uint32_t red[8][4];
     {
@@ -242,71 +352,66 @@ __global__ void __launch_bounds__(256) pack_i8_kernel(PackI8Params p) {
         lut[t] = p.ascii ? c_ascii_lut[t] : (((c_valid_code[t >> 5] >> (t & 31)) & 1u) ? (uint8_t)t : (uint8_t)0);
     }
     __syncthreads();
+    constexpr int H = FP4 ? 2 : 1;            // 16-site halves per thread
+    constexpr uint32_t SITES = 16 * H;
     const uint32_t groups = (uint32_t)(p.wp8 / 16);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint64_t seq = blockIdx.x; seq < p.n_pad; seq += gridDim.x) {
         uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
         const uint8_t* row = p.codes + seq * p.width;
         for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
-            const uint64_t s0 = (uint64_t)g * 16;
-            uint32_t w[4] = {0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u};   // N-like padding
-            if (seq < p.n && s0 < p.width) {
-                uint32_t raw[4];
-                if (s0 + 20 <= p.width) {   // the aligned window [a & ~3, +20) stays inside this row
-                    const uintptr_t a = reinterpret_cast<uintptr_t>(row + s0);
-                    const uint32_t* ap = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
-                    const uint32_t sh = (uint32_t)(a & 3) * 8;
-                    const uint32_t x0 = __ldg(ap), x1 = __ldg(ap + 1), x2 = __ldg(ap + 2), x3 = __ldg(ap + 3), x4 = __ldg(ap + 4);
-                    raw[0] = __funnelshift_r(x0, x1, sh); raw[1] = __funnelshift_r(x1, x2, sh);
-                    raw[2] = __funnelshift_r(x2, x3, sh); raw[3] = __funnelshift_r(x3, x4, sh);
-                } else {                    // last groups of the row: byte loads, bounded by width
+            const uint64_t s0 = (uint64_t)g * SITES;
+            uint32_t w[4 * H];
+#pragma unroll
+            for (int h = 0; h < H; h++) {
+                uint32_t wh[4] = {0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u};   // N-like padding
+                if (seq < p.n && s0 + 16 * h < p.width) {
+                    uint32_t raw[4];
+                    load_codes16(p, row, seq, s0 + 16 * h, lut, wh, raw);
+                    if (p.acgt && p.count_upper_ascii) {   // the streamed tn93 records count raw upper-case letters only
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            cA += __popc(__vcmpeq4(raw[k], 0x41414141u)); cT += __popc(__vcmpeq4(raw[k], 0x54545454u));
+                            cG += __popc(__vcmpeq4(raw[k], 0x47474747u)); cC += __popc(__vcmpeq4(raw[k], 0x43434343u));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) w[4 * h + k] = wh[k];
+            }
+            int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + (uint64_t)g * 16;
+            if (FP4) {
+                NibBits nb[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) nb[k] = nib_bits(w[2 * k], w[2 * k + 1]);
+                if (p.acgt && !p.count_upper_ascii) {
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        uint32_t v = 0;
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint64_t s = s0 + 4 * k + j;
-                            const uint32_t byte = s < p.width ? (uint32_t)row[s] : (p.ascii ? (uint32_t)'N' : 240u);
-                            v |= byte << (8 * j);
-                        }
-                        raw[k] = v;
+                        cA += __popc(nb[k].A & nb[k].K); cT += __popc(nb[k].T & nb[k].K);
+                        cG += __popc(nb[k].G & nb[k].K); cC += __popc(nb[k].C & nb[k].K);
                     }
                 }
+                for (int pl = 0; pl < p.nplanes; pl++) {
+                    const uint32_t id = p.plane_id[pl];
+                    *reinterpret_cast<uint4*>(base + pl * p.wp8) =
+                        make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id));
+                }
+            } else {
+                CodeBits b[4];
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const uint32_t r = raw[k];
-                    uint32_t t = (uint32_t)lut[r & 0xFF] | ((uint32_t)lut[(r >> 8) & 0xFF] << 8) |
-                                 ((uint32_t)lut[(r >> 16) & 0xFF] << 16) | ((uint32_t)lut[r >> 24] << 24);
-                    if ((t - M1) & ~t & 0x80808080u) {   // a zero byte = invalid nucleotide (fastaio.rs:111-113)
+                for (int k = 0; k < 4; k++) b[k] = code_bits(w[k]);
+                if (p.acgt && !p.count_upper_ascii) {
 #pragma unroll
-                        for (int j = 0; j < 4; j++)
-                            if (((t >> (8 * j)) & 0xFFu) == 0) {
-                                if (p.invalid) atomicMin(p.invalid, ((unsigned long long)(p.seq0 + seq) << 32) | (unsigned long long)(s0 + 4 * k + j));
-                                t |= 0xF0u << (8 * j);
-                            }
-                    }
-                    w[k] = t;
-                    if (p.acgt && p.count_upper_ascii) {   // the streamed tn93 records count raw upper-case letters only
-                        cA += __popc(__vcmpeq4(r, 0x41414141u)); cT += __popc(__vcmpeq4(r, 0x54545454u));
-                        cG += __popc(__vcmpeq4(r, 0x47474747u)); cC += __popc(__vcmpeq4(r, 0x43434343u));
+                    for (int k = 0; k < 4; k++) {
+                        cA += __popc(b[k].A & b[k].K); cT += __popc(b[k].T & b[k].K);
+                        cG += __popc(b[k].G & b[k].K); cC += __popc(b[k].C & b[k].K);
                     }
                 }
-            }
-            CodeBits b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) b[k] = code_bits(w[k]);
-            if (p.acgt && !p.count_upper_ascii) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    cA += __popc(b[k].A & b[k].K); cT += __popc(b[k].T & b[k].K);
-                    cG += __popc(b[k].G & b[k].K); cC += __popc(b[k].C & b[k].K);
+                for (int pl = 0; pl < p.nplanes; pl++) {
+                    const uint32_t id = p.plane_id[pl];
+                    *reinterpret_cast<uint4*>(base + pl * p.wp8) =
+                        make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id));
                 }
-            }
-            int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + s0;
-            for (int pl = 0; pl < p.nplanes; pl++) {
-                const uint32_t id = p.plane_id[pl];
-                *reinterpret_cast<uint4*>(base + pl * p.wp8) =
-                    make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id));
             }
         }
         if (p.acgt) {   // uniform branch: CTA reduction of the four counts
@@ -420,26 +525,37 @@ __global__ void pp_correct_kernel(PpCorrParams p) {
     }
 }
 // rows found by scanning their V planes (stream batches have no index): a site holds a partial code iff
-// one of its V values is negative; its possibility nibble is then {b : V_b > 0}.
+// one of its V values is negative; its possibility nibble is then {b : V_b > 0}.  FP4 planes hold E2M1 nibbles
+// (two sites per byte): negative <=> bit 3, positive <=> non-zero without bit 3.
+template <bool FP4>
 __global__ void pp_correct_scan_kernel(PpCorrParams p) {
-    const uint32_t gpr = p.a_wp8 / 16;   // 16-site groups per record
+    const uint32_t gpr = p.a_wp8 / 16;   // 16-byte groups per record and plane
+    constexpr uint32_t SITES = FP4 ? 32 : 16;
     const uint64_t total = (uint64_t)(p.row_end - p.row0) * gpr;
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t row = p.row0 + (uint32_t)(u / gpr);
-        const uint32_t s0 = (uint32_t)(u % gpr) * 16;
-        const int8_t* base = p.a_ops + ((uint64_t)row * p.a_nplanes + p.a_vplane0) * p.a_wp8 + s0;
+        const uint32_t g = (uint32_t)(u % gpr);
+        const int8_t* base = p.a_ops + ((uint64_t)row * p.a_nplanes + p.a_vplane0) * p.a_wp8 + (uint64_t)g * 16;
         uint4 v[4];
 #pragma unroll
         for (int b = 0; b < 4; b++) v[b] = *reinterpret_cast<const uint4*>(base + (uint64_t)b * p.a_wp8);
+        const uint32_t neg = FP4 ? 0x88888888u : 0x80808080u;
         const uint32_t any = (v[0].x | v[1].x | v[2].x | v[3].x | v[0].y | v[1].y | v[2].y | v[3].y |
-                              v[0].z | v[1].z | v[2].z | v[3].z | v[0].w | v[1].w | v[2].w | v[3].w) & 0x80808080u;
+                              v[0].z | v[1].z | v[2].z | v[3].z | v[0].w | v[1].w | v[2].w | v[3].w) & neg;
         if (!any) continue;
-        const int8_t* vb[4] = {reinterpret_cast<const int8_t*>(&v[0]), reinterpret_cast<const int8_t*>(&v[1]),
-                               reinterpret_cast<const int8_t*>(&v[2]), reinterpret_cast<const int8_t*>(&v[3])};
-        for (int k = 0; k < 16; k++) {
-            if (vb[0][k] >= 0 && vb[1][k] >= 0 && vb[2][k] >= 0 && vb[3][k] >= 0) continue;
-            const uint32_t ma = (vb[0][k] > 0 ? 8u : 0u) | (vb[1][k] > 0 ? 4u : 0u) | (vb[2][k] > 0 ? 2u : 0u) | (vb[3][k] > 0 ? 1u : 0u);
-            pp_fix_row(p, row, s0 + k, ma);
+        const uint8_t* vb[4] = {reinterpret_cast<const uint8_t*>(&v[0]), reinterpret_cast<const uint8_t*>(&v[1]),
+                                reinterpret_cast<const uint8_t*>(&v[2]), reinterpret_cast<const uint8_t*>(&v[3])};
+        for (uint32_t k = 0; k < SITES; k++) {
+            uint32_t ma = 0, anyneg = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                uint32_t x, isneg;
+                if (FP4) { x = (vb[b][k >> 1] >> ((k & 1) * 4)) & 15u; isneg = x >> 3; }
+                else { x = vb[b][k]; isneg = x >> 7; }
+                anyneg |= isneg;
+                if (x != 0 && !isneg) ma |= 8u >> b;
+            }
+            if (anyneg) pp_fix_row(p, row, g * SITES + k, ma);
         }
     }
 }
@@ -447,7 +563,9 @@ __global__ void pp_correct_scan_kernel(PpCorrParams p) {
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
 enum OutMode { OUT_RAW_I32 = 0, OUT_DIV3_U32 = 1, OUT_DIV3_U16 = 2 };
 struct TcParams {
-    uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of TN
+    uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of tn
+    uint32_t tn;                               // tile columns: 256 (kind::i8) or 240 (kind::mxf4: 16 TMEM columns per
+                                               // accumulator are left for the scale factors)
     uint32_t gx, gy;                           // tiles: gx column blocks x gy row blocks (of TM * CL rows)
     const uint32_t* tile_list;                 // square panels: the LIVE tiles (by << 20 | bx) in raster order, so that
     uint32_t n_live;                           // the static round-robin deals only real work; NULL = all gx * gy tiles
@@ -481,10 +599,10 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
         bx = r / gb; by = band * RASTER_G + (r - bx * gb);
     }
     const uint32_t rowS0 = p.row0 + by * (TM * MT * CL);
-    rowB0 = (p.col_block0 + bx) * TN;
+    rowB0 = (p.col_block0 + bx) * p.tn;
     rowA0 = rowS0 + rank * (TM * MT);
     if (rowS0 >= p.row_end) return false;
-    if (p.square && rowB0 + TN <= rowS0 + 1) return false;   // decided per super-tile: identical in both CTAs
+    if (p.square && rowB0 + p.tn <= rowS0 + 1) return false;   // decided per super-tile: identical in both CTAs
     return true;
 }
 
@@ -503,9 +621,17 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
 // per SM and four stages fit again.  Both CTAs' TMA loads report to the leader's `full` barrier; the
 // leader's commits are multicast onto both CTAs' `empty` / `tfull` barriers; both CTAs' epilogue warps
 // arrive on the leader's `tempty`.
-template <int CL, int MT, bool PAIR = false>
+// FP4 (with PAIR): the same pipeline with tcgen05.mma kind::mxf4.block_scale: operands are E2M1 nibbles (every plane
+// value 0, 1, 2, 3, -1, -2 is representable), the UE8M0 scale factors are all 2^0 (one constant block of TMEM columns,
+// written once), accumulation is fp32 and exact for these integer sums (|sum| <= 3 x 4 x 29,952 << 2^24; checked on
+// the device by tools/ubench_fp4 and by the parity suite).  Twice the MACs per instruction (K = 64) at the same issue
+// rate; a tile is 512 x 240 because the scale factors need TMEM columns next to the two accumulators.
+template <int CL, int MT, bool PAIR = false, bool FP4 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+    static_assert(!FP4 || PAIR, "the FP4 variant exists for the cta_group::2 kernel only");
+    constexpr int TNX = FP4 ? TN_FP4 : TN;               // tile columns
+    constexpr int BH_BYTES = (TNX / 2) * KB;              // bytes of one CTA's half of the B tile (PAIR)
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle needs 1024-byte aligned tiles
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -542,9 +668,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (FP4) {
+        // scale factors: UE8M0 0x7F = 2^0 in every byte of TMEM columns [SF_COL, SF_COL + 16) on all 128 lanes of
+        // this CTA, so every block scale of A and B is 1 whatever the scale-factor layout
+        if (warp >= 2) {
+            const uint32_t one = 0x7F7F7F7Fu;
+            for (uint32_t c = 0; c < 16; c++)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};"
+                             ::"r"(tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + SF_COL + c), "r"(one) : "memory");
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+    if (CL > 1) cluster_sync_all();   // the peer's barriers (and scale factors) exist before anything is sent to them
+    tc_fence_after();
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -562,11 +702,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int xb = (int)(p.pb[a][pr] * p.wp8 + sb * KB);
                     if (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
-                        if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * STAGE_BYTES);
+                        if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * (MT * A_BYTES + BH_BYTES));
 #pragma unroll
                         for (int m = 0; m < MT; m++)
                             tma_load_2d_pair(sa + m * A_BYTES, &tmA, (int)(p.pa[a][pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);
-                        tma_load_2d_pair(sa + MT * A_BYTES, &tmB, xb, (int)(rowB0 + rank * (TN / 2)), full + stage);
+                        tma_load_2d_pair(sa + MT * A_BYTES, &tmB, xb, (int)(rowB0 + rank * (TNX / 2)), full + stage);
                         if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
@@ -609,7 +749,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (uint32_t k4 = 0; k4 < KB / 32; k4++)
 #pragma unroll
                         for (int m = 0; m < MT; m++) {
-                            if (PAIR) tc_mma_i8_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8_PAIR, (kt | k4) != 0);
+                            if (FP4) tc_mma_f4_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_F4_PAIR, (kt | k4) != 0,
+                                                    tmem_base + SF_COL, tmem_base + SF_COL + 8);
+                            else if (PAIR) tc_mma_i8_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8_PAIR, (kt | k4) != 0);
                             else tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
                         }
                     if (PAIR) tc_commit_pair(empty + stage, MC_MASK);   // frees the stage in both CTAs
@@ -647,22 +789,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t base0 = p.square ? (uint64_t)rq0 * (2 * p.n_total - rq0 - 1) / 2 - p.out_base
                                                 : (uint64_t)(rq0 - p.row0) * p.n_b;
 #pragma unroll 1
-                for (uint32_t c = 0; c < TN / 32; c++) {
+                for (uint32_t c = 0; c < (TNX + 31) / 32; c++) {
                     const uint32_t col0 = rowB0 + c * 32;
                     if (col0 >= p.n_b) break;                                   // warp-uniform
                     if (p.square && col0 + 32 <= rq0 + 1) continue;             // chunk entirely on / below the diagonal
                     uint32_t v[32];
                     tc_ld32(tmem_base + ((quad * 32u) << 16) + (ab + m) * TN + c * 32, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        ebuf[lane * EPI_PITCH + j] = p.out_mode == OUT_RAW_I32 ? v[j] : v[j] / 3u;
+                    for (int j = 0; j < 32; j++) {
+                        const uint32_t x = FP4 ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];   // fp32 sums are integers
+                        ebuf[lane * EPI_PITCH + j] = p.out_mode == OUT_RAW_I32 ? x : x / 3u;
+                    }
                     __syncwarp();
                     const uint32_t col = col0 + lane;
                     uint64_t rb = base0;
                     for (uint32_t r = 0; r < nrows; r++) {
                         const uint32_t row = rq0 + r;
                         const uint32_t val = ebuf[r * EPI_PITCH + lane];
-                        if (col < p.n_b && (!p.square || col > row)) {
+                        if (col < p.n_b && (!p.square || col > row) && (TNX % 32 == 0 || c * 32 + lane < TNX)) {
                             const uint64_t idx = p.square ? rb + (col - row - 1) : rb + col;
                             if (p.out_mode == OUT_DIV3_U16) reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)val;
                             else outw[idx] = val;

@@ -119,8 +119,10 @@ typedef struct dg_ctx dg_ctx;
 #define DG_OPT_PANEL_BYTES 1 /* target bytes of one result panel (default 256 MiB) */
 #define DG_OPT_KEEP_CODES 2  /* keep the raw code bytes on the device after dg_load_resident (0/1) */
 #define DG_OPT_TILE_VARIANT 3 /* tuning: 0 = default tile shape per measure family, >0 = alternatives */
-#define DG_OPT_ENGINE 4      /* 0 = auto (per shape / ambiguity load), 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8
-                                one-hot GEMM.  Set it before dg_load_resident: it decides which operands are built. */
+#define DG_OPT_ENGINE 4      /* 0 = auto (per shape / ambiguity load), 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 kind::i8
+                                GEMM (int8 planes, int32 accumulation), 3 = tcgen05 kind::mxf4 GEMM (the same planes as
+                                E2M1 nibbles, unit scale factors, fp32 accumulation: exact for these integer sums, twice
+                                the MAC rate).  Set it before dg_load_resident: it decides which operands are built. */
 #define DG_OPT_RESULT_U16 5  /* 0/1: deliver n / n_high panels as uint16_t (DG_RESULT_U16).  A count never exceeds
                                 the width, so this is lossless for width <= 65535 (else DG_ERR_INVALID_ARG). */
 
@@ -136,7 +138,7 @@ typedef struct {
     uint64_t pairs;       /* pairs computed by count kernels since the last reset */
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
-    uint64_t engine;      /* engine of the last run: 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 GEMM */
+    uint64_t engine;      /* engine of the last run: 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 GEMM, 3 = tcgen05 fp4 GEMM */
 } dg_timings;
 
 DG_API int dg_abi_version(void);

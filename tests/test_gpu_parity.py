@@ -13,11 +13,12 @@ REL_TOL = 1e-12  # BASELINE.json north_star: "raw/jc69/k80/tn93 must agree withi
 ALL = ["n", "n_high", "raw", "jc69", "k80", "tn93"]
 
 
-@pytest.fixture(autouse=True, params=["lop3", "tc", "auto"])
+@pytest.fixture(autouse=True, params=["lop3", "tc", "fp4", "auto"])
 def engine(request, monkeypatch):
-    """Every test runs on both count engines and on the automatic choice: DG_ENGINE overrides
-    DG_OPT_ENGINE at dg_create (1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 one-hot GEMM, 0 = auto)."""
-    monkeypatch.setenv("DG_ENGINE", {"lop3": "1", "tc": "2", "auto": "0"}[request.param])
+    """Every test runs on every count engine and on the automatic choice: DG_ENGINE overrides DG_OPT_ENGINE at
+    dg_create (1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 kind::i8 GEMM, 3 = tcgen05 kind::mxf4 GEMM with unit
+    scales, 0 = auto)."""
+    monkeypatch.setenv("DG_ENGINE", {"lop3": "1", "tc": "2", "fp4": "3", "auto": "0"}[request.param])
     return request.param
 
 
@@ -402,7 +403,7 @@ def test_auto_engine_choice(dg, oracle, engine):
     rng = np.random.default_rng(77)
     normal = synth.encode_ascii(synth.make_alignment(200, width=2000, seed=5, ambiguity=True))
     partial = np.array([192, 160, 144, 96, 80, 48, 224, 176, 208, 112], np.uint8)[rng.integers(0, 10, size=(200, 2000))]
-    for codes, want_engine in ((normal, 2), (partial, 1)):
+    for codes, want_engine in ((normal, 3), (partial, 1)):
         for measure in ("n_high", "raw"):
             with dg.Engine(measure, 2000) as e:
                 e.load(0, codes)
@@ -412,7 +413,7 @@ def test_auto_engine_choice(dg, oracle, engine):
     with dg.Engine("tn93", 2000) as e:  # k80 / tn93 need no correction: always tensor cores
         e.load(0, partial)
         got = e.run_square()
-        assert e.timings()["engine"] == 2
+        assert e.timings()["engine"] == 3
     check("tn93", got, oracle_run(oracle, "tn93", "square", partial))
 
 

@@ -94,3 +94,36 @@ def test_random_alignment_sums(oracle):
     acc = sum(int((P["U" + b][qi] * P["V" + b][ti]).sum()) for b in "AGCT")
     acc += sum(pp_corr(int(a) >> 4, int(b) >> 4) for a, b in zip(q, t) if is_partial(int(a)) and is_partial(int(b)))
     assert acc % 3 == 0 and acc // 3 == oracle.pair_counts(q, t)["snp"]
+
+
+E2M1 = {0: 0x0, 1: 0x2, 2: 0x4, 3: 0x5, -1: 0xA, -2: 0xC}
+
+
+def test_fp4_nibble_formulas_match_the_plane_values():
+    """Mirror of nib_v / nib_pm / plane_nib8 (bit formulas on 0/1 lanes): the nibble must be the E2M1 code of
+    the int8 plane value for every code and plane."""
+    for c in CODES:
+        A, G, C, T, K = (c >> 7) & 1, (c >> 6) & 1, (c >> 5) & 1, (c >> 4) & 1, (c >> 3) & 1
+        E = A + G + C + T - 1
+        e0, e1 = E & 1, (E >> 1) & 1
+        x, y, nz = e1 & (1 - e0), e0 & (1 - e1), e0 | e1
+
+        def nib_v(b):
+            b3 = nz & (1 - b)
+            b2 = (b & (1 - e1)) | ((1 - b) & x)
+            b1 = (b & x) | ((1 - b) & y)
+            b0 = b & (1 - nz)
+            return b0 | (b1 << 1) | (b2 << 2) | (b3 << 3)
+
+        def nib_pm(pos, neg):
+            return ((pos | neg) << 1) | (neg << 3)
+
+        p = planes(c)
+        got = {"UA": (A ^ 1) << 1, "UG": (G ^ 1) << 1, "UC": (C ^ 1) << 1, "UT": (T ^ 1) << 1,
+               "VA": nib_v(A), "VG": nib_v(G), "VC": nib_v(C), "VT": nib_v(T),
+               "KA": (A & K) << 1, "KG": (G & K) << 1, "KC": (C & K) << 1, "KT": (T & K) << 1,
+               "PURK": ((A | G) & K) << 1, "PYRK": ((C | T) & K) << 1, "K": K << 1,
+               "W": nib_pm(A & K, G & K), "Z": nib_pm(C & K, T & K),
+               "PURC": ((A | G) & (1 - (C | T))) << 1, "PYRC": ((C | T) & (1 - (A | G))) << 1}
+        for k, v in p.items():
+            assert got[k] == E2M1[v], (c, k, v, got[k])
