@@ -228,13 +228,34 @@ def run_ours(args):
     count_launch_ms = tm["count_ms"] / max(tm["count_launches"], 1)
 
     # ---- e2e: host buffers through the C ABI ----------------------------------------------------
+    if world > 1:
+        # N ranks: every code byte crosses PCIe ONCE (rank r uploads records [r*per, (r+1)*per) from pinned host
+        # memory), the ranks exchange their slices over NVLink (NCCL all-gather) and each library instance takes the
+        # gathered device buffer (dg_load_resident_device).  N = 1 keeps the plain host-pointer call.
+        import torch
+        per = (n + world - 1) // world
+        lo, hi = rank * per, min(n, rank * per + per)
+        host_slice = torch.full((per, WIDTH), 240, dtype=torch.uint8).pin_memory()
+        host_slice[:hi - lo] = torch.from_numpy(np.ascontiguousarray(codes[lo:hi]))
+        dev_slice = torch.empty((per, WIDTH), dtype=torch.uint8, device=d.device)
+        gathered = torch.empty((world * per, WIDTH), dtype=torch.uint8, device=d.device)
+
+        def load_step():
+            dev_slice.copy_(host_slice, non_blocking=True)
+            d.all_gather_into(gathered, dev_slice)
+            torch.cuda.synchronize()
+            eng.load_device(0, gathered.data_ptr(), d.local_rank, n)
+    else:
+        def load_step():
+            eng.load(0, pinned)                               # H2D from pinned host memory + pack
+
     for _ in range(2):
-        eng.load(0, pinned)
+        load_step()
         eng.run_discard(api.DG_MODE_SQUARE, rank, world)
     sync_all()
     t0 = time.time()
     for _ in range(args.steps):
-        eng.load(0, pinned)                                   # H2D from pinned host memory + pack
+        load_step()
         got = eng.run_discard(api.DG_MODE_SQUARE, rank, world)  # tiles + D2H + sink reads each panel
         assert got == my_pairs
     sync_all()
@@ -354,7 +375,9 @@ def run_ours(args):
                        "panel_bytes": args.panel_bytes, "panels": len(plan),
                        "l2": "inputs larger than L2 (operand planes %.0f MB vs 126 MB L2)" % (n * 8 * 14976 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
-                    "h2d_bytes_per_step": int(n * WIDTH * world), "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
+                    "h2d_bytes_per_step": int(n * WIDTH),
+                    "input_path": ("each rank uploads 1/N of the codes from pinned host memory, NCCL all-gather over NVLink, "
+                                   "dg_load_resident_device") if world > 1 else "dg_load_resident from pinned host memory", "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
                     "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
             "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}.get(engine_id, "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
@@ -371,7 +394,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="override the record count (debug)")
+    ap.add_argument("--records", "--n", dest="n", type=int, default=None,
+                    help="record count of the alignment (fixed total work: strong scaling); default 20000*sqrt(N)")
     ap.add_argument("--panel-bytes", type=int, default=None,
                     help="result panel size (default: 6.7e7 results per panel = 128 MiB of uint16 / 256 MiB of uint32)")
     ap.add_argument("--tile-variant", type=int, default=0)

@@ -26,7 +26,7 @@ DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_S
 # every symbol include/distance_gpu.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "dg_abi_version", "dg_device_count", "dg_create", "dg_destroy", "dg_last_error", "dg_set_option",
-    "dg_load_resident", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
+    "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
     "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
     "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
 ]
@@ -101,6 +101,7 @@ def load_library():
     L.dg_last_error.restype = C.c_char_p
     L.dg_set_option.argtypes = [vp, i32, C.c_int64]
     L.dg_load_resident.argtypes = [vp, i32, vp, u64, i32, vp]
+    L.dg_load_resident_device.argtypes = [vp, i32, vp, i32, u64, i32, vp]
     L.dg_invalid_site.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_uint8)]
     L.dg_run_square.argtypes = [vp, SINK_FN, vp, C.c_uint32]
     L.dg_run_rect.argtypes = [vp, SINK_FN, vp, C.c_uint32]
@@ -121,7 +122,7 @@ def load_library():
     L.dg_plan_panels.restype = C.c_int64
     L.dg_plan_ctx.argtypes = [vp, i32, vp, vp, vp, u64]
     L.dg_plan_ctx.restype = C.c_int64
-    for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_invalid_site", "dg_run_square",
+    for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square",
                  "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end",
                  "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings"):
         getattr(L, name).restype = i32
@@ -220,6 +221,11 @@ class Engine:
             self.h, which, codes.ctypes.data_as(C.c_void_p), codes.shape[0], input_kind,
             None if cnt is None else cnt.ctypes.data_as(C.c_void_p)))
         self._n[which] = codes.shape[0]
+
+    def load_device(self, which: int, device_ptr: int, src_device: int, n: int, input_kind: int = DG_INPUT_PARADIS):
+        """dg_load_resident_device: n x width code bytes already in device memory (e.g. a torch tensor's data_ptr())."""
+        self._check(self.L.dg_load_resident_device(self.h, which, C.c_void_p(device_ptr), src_device, n, input_kind, None))
+        self._n[which] = n
 
     def invalid_site(self):
         r, s, b = C.c_uint64(), C.c_uint64(), C.c_uint8()

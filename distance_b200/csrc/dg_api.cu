@@ -243,7 +243,7 @@ void enqueue_pack(dg_ctx* c, unsigned long long* d_inv, PlaneSet& s, const uint8
 }
 
 // After a sync: did pack_planes see an invalid byte?  `probe` fetches the byte for the report.
-void check_invalid(dg_ctx* c, Device& d, const uint8_t* host_codes, uint64_t row_offset) {
+void check_invalid(dg_ctx* c, Device& d, const uint8_t* dev_codes, uint64_t row_offset) {
     CUDA_CHECK(cudaMemcpy(d.h_invalid + 2, d.d_invalid + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     const unsigned long long key = d.h_invalid[2];
     if (key == ~0ull) return;
@@ -252,7 +252,8 @@ void check_invalid(dg_ctx* c, Device& d, const uint8_t* host_codes, uint64_t row
     c->have_invalid = true;
     c->inv_record = (key >> 32) + row_offset;
     c->inv_site = key & 0xffffffffull;
-    c->inv_byte = host_codes ? host_codes[(key >> 32) * c->width + c->inv_site] : 0;
+    c->inv_byte = 0;
+    if (dev_codes) CUDA_CHECK(cudaMemcpy(&c->inv_byte, dev_codes + (key >> 32) * c->width + c->inv_site, 1, cudaMemcpyDeviceToHost));
     fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in record %llu at site %llu", c->inv_byte,
          (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
 }
@@ -1153,8 +1154,10 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
     });
 }
 
-int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, int input_kind,
-                     const uint64_t* acgt_counts) {
+// codes: host memory (src_dev < 0) or device memory on CUDA device src_dev (then every device of the context gets
+// its replica through cudaMemcpyPeerAsync: NVLink when the devices are peers, no PCIe upload at all)
+static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int src_dev, uint64_t n, int input_kind,
+                              const uint64_t* acgt_counts) {
     return guarded(ctx, [&] {
         if (which < 0 || which > 1) fail(DG_ERR_INVALID_ARG, "which must be 0 or 1");
         if (!codes || n == 0) fail(DG_ERR_INVALID_ARG, "empty alignment");
@@ -1189,8 +1192,12 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
                 for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
                     const uint64_t nr = std::min(chunk, n - r0);
-                    CUDA_CHECK(cudaMemcpyAsync(s.codes + r0 * ctx->width, codes + r0 * ctx->width, (size_t)nr * ctx->width,
-                                               cudaMemcpyHostToDevice, d.copy_in));
+                    if (src_dev < 0)
+                        CUDA_CHECK(cudaMemcpyAsync(s.codes + r0 * ctx->width, codes + r0 * ctx->width, (size_t)nr * ctx->width,
+                                                   cudaMemcpyHostToDevice, d.copy_in));
+                    else
+                        CUDA_CHECK(cudaMemcpyPeerAsync(s.codes + r0 * ctx->width, d.id, codes + r0 * ctx->width, src_dev,
+                                                       (size_t)nr * ctx->width, d.copy_in));
                     cudaEvent_t ev = d.chunk_ev[n_ev++ & 31];
                     CUDA_CHECK(cudaEventRecord(ev, d.copy_in));
                     CUDA_CHECK(cudaStreamWaitEvent(d.compute, ev, 0));
@@ -1215,13 +1222,13 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
                 CUDA_CHECK(cudaStreamSynchronize(d.copy_in));
                 CUDA_CHECK(cudaStreamSynchronize(d.compute));
                 ctx->tm.h2d_ms += wall_ms() - th;
-                ctx->tm.h2d_bytes += n * ctx->width;
+                if (src_dev < 0) ctx->tm.h2d_bytes += n * ctx->width;
                 float ms = 0;
                 CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
                 ctx->tm.pack_ms += ms;  // device span of the pipelined upload + packing
                 s.tc_ready = want_tc;
                 if (!want_tc) ensure_lop3(ctx, d, s);  // engine 1: build the bit-planes now (also validates the bytes)
-                check_invalid(ctx, d, codes, 0);
+                check_invalid(ctx, d, s.codes, 0);
             } catch (...) {
                 s.n = 0; s.tc_ready = false; s.lop3_ready = false;
                 throw;
@@ -1229,6 +1236,17 @@ int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, i
         }
         if (trace) fprintf(stderr, "[dg_load_resident] %llu records: %.3f ms\n", (unsigned long long)n, wall_ms() - t_begin);
     });
+}
+
+int dg_load_resident(dg_ctx* ctx, int which, const uint8_t* codes, uint64_t n, int input_kind,
+                     const uint64_t* acgt_counts) {
+    return load_resident_impl(ctx, which, codes, -1, n, input_kind, acgt_counts);
+}
+
+int dg_load_resident_device(dg_ctx* ctx, int which, const uint8_t* d_codes, int src_device, uint64_t n, int input_kind,
+                            const uint64_t* acgt_counts) {
+    if (ctx && src_device < 0) { ctx->err = "src_device must be a CUDA device ordinal"; return DG_ERR_INVALID_ARG; }
+    return load_resident_impl(ctx, which, d_codes, src_device, n, input_kind, acgt_counts);
 }
 
 int dg_invalid_site(const dg_ctx* ctx, uint64_t* record, uint64_t* site, uint8_t* byte) {

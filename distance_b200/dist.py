@@ -26,6 +26,8 @@ class Dist:
                 self.device = torch.device("cuda", self.local_rank)
             else:
                 self.device = torch.device("cpu")
+            # NCCL logs (its version banner included) go to stdout by default: keep stdout to bench.py's one JSON line
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29511")
             td.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
@@ -42,6 +44,14 @@ class Dist:
         t = torch.tensor([float(value)], dtype=torch.float64, device=self.device)
         self.pg.all_reduce(t, op=getattr(self.pg.ReduceOp, op))
         return float(t.item())
+
+    def all_gather_into(self, out, inp):
+        """NCCL all-gather of equal-sized device tensors (the input alignment: each rank uploads 1/N of the code
+        bytes over PCIe and receives the rest over NVLink)."""
+        if self.pg is None:
+            out.copy_(inp)
+        else:
+            self.pg.all_gather_into_tensor(out, inp)
 
     def max(self, value: float) -> float:
         return self._reduce(value, "MAX")

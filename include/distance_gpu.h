@@ -162,6 +162,13 @@ DG_API int dg_set_option(dg_ctx *ctx, int key, int64_t value);
 DG_API int dg_load_resident(dg_ctx *ctx, int which, const uint8_t *codes, uint64_t n, int input_kind,
                      const uint64_t *acgt_counts);
 
+/* The same for codes that already sit in DEVICE memory of CUDA device `src_device` (e.g. gathered from the other
+ * ranks over NVLink / NCCL, or produced by a GPU parser): every device of the context takes its replica with
+ * cudaMemcpyPeerAsync, so no byte crosses PCIe.  The caller's work on d_codes must be complete (synchronised)
+ * before the call; the buffer may be reused when the call returns. */
+DG_API int dg_load_resident_device(dg_ctx *ctx, int which, const uint8_t *d_codes, int src_device, uint64_t n,
+                                   int input_kind, const uint64_t *acgt_counts);
+
 /* When a call failed with DG_ERR_INVALID_CODE: the first offending (record, site, byte), from which
  * the host formats "Invalid nucleotide character in record '<id>': '<c>'" (src/fastaio.rs:89-91). */
 DG_API int dg_invalid_site(const dg_ctx *ctx, uint64_t *record, uint64_t *site, uint8_t *byte);

@@ -336,6 +336,28 @@ def test_panels_and_parts_cover_the_triangle(dg, oracle, measure):
         check(measure, np.concatenate([p[2] for p in parts]), want)
 
 
+def test_load_from_device_memory(dg, oracle):
+    """dg_load_resident_device: the codes already sit in HBM (a torch tensor here; a NCCL all-gather in bench.py)."""
+    import torch
+    from distance_b200 import synth
+    rng = np.random.default_rng(41)
+    a = synth.random_codes(rng, 300, 777, p_ambig=0.2)
+    t = torch.from_numpy(a).cuda()
+    torch.cuda.synchronize()
+    for measure in ("n_high", "tn93"):
+        with dg.Engine(measure, 777) as e:
+            e.load_device(0, t.data_ptr(), 0, 300)
+            check(measure, e.run_square(), oracle_run(oracle, measure, "square", a))
+    bad = a.copy()
+    bad[7, 5] = 3
+    tb = torch.from_numpy(bad).cuda()
+    torch.cuda.synchronize()
+    with dg.Engine("raw", 777) as e:
+        with pytest.raises(dg.DistanceGpuError):
+            e.load_device(0, tb.data_ptr(), 0, 300)
+        assert e.invalid_site() == (7, 5, 3)
+
+
 def test_single_record_and_errors(dg):
     with dg.Engine("raw", 10) as e:
         e.load(0, np.full((1, 10), 136, np.uint8))
