@@ -18,7 +18,8 @@ MEASURES = {"n": 0, "n_high": 1, "raw": 2, "jc69": 3, "k80": 4, "tn93": 5}
 DG_INPUT_PARADIS, DG_INPUT_ASCII = 0, 1
 DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
 DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
-DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16 = 1, 2, 3, 4, 5
+DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16, DG_OPT_PIPE_PANELS = 1, 2, 3, 4, 5, 6
+DG_OPT_PIPE_CHUNK_BYTES = 7
 DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
           -4: "DG_ERR_INVALID_CODE", -5: "DG_ERR_SINK", -6: "DG_ERR_NOMEM"}
@@ -29,6 +30,7 @@ ABI_SYMBOLS = [
     "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
     "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
     "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
+    "dg_square_begin", "dg_square_next", "dg_square_push", "dg_square_end", "dg_run_square_host",
 ]
 
 
@@ -106,6 +108,11 @@ def load_library():
     L.dg_run_square.argtypes = [vp, SINK_FN, vp, C.c_uint32]
     L.dg_run_rect.argtypes = [vp, SINK_FN, vp, C.c_uint32]
     L.dg_run_part.argtypes = [vp, i32, C.c_uint32, C.c_uint32, SINK_FN, vp, C.c_uint32]
+    L.dg_square_begin.argtypes = [vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
+    L.dg_square_next.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    L.dg_square_push.argtypes = [vp, vp, i32, u64, u64]
+    L.dg_square_end.argtypes = [vp]
+    L.dg_run_square_host.argtypes = [vp, vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
     L.dg_stream_push.argtypes = [vp, vp, u64, i32, vp]
     L.dg_stream_end.argtypes = [vp]
@@ -124,7 +131,8 @@ def load_library():
     L.dg_plan_ctx.restype = C.c_int64
     for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square",
                  "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end",
-                 "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings"):
+                 "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings", "dg_square_begin",
+                 "dg_square_next", "dg_square_push", "dg_square_end", "dg_run_square_host"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -306,6 +314,70 @@ class Engine:
             return 0
 
         self._check(self.L.dg_run_part(self.h, mode, part, n_parts, SINK_FN(sink), None, 0))
+        return state["n"]
+
+    # -- pipelined all-vs-all (dg_square_*) --------------------------------------------------------
+    def square_pipelined(self, codes: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None, part: int = 0,
+                         n_parts: int = 1, one_call: bool = False, push=None):
+        """dg_square_begin / next / push / end over host codes.  Returns (values, panels): the packed upper
+        triangle with this part's panels placed by row (other parts' positions stay 0) and the panels in the
+        order the sink saw them.  `push(lo, hi)` may replace the default host-pointer push (multi-rank tests)."""
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        n = codes.shape[0]
+        assert codes.ndim == 2 and codes.shape[1] == self.width
+        dtype = self._dtype()
+        out = np.zeros(n * (n - 1) // 2, dtype=dtype)
+        panels = []
+
+        def sink(user, pp):
+            p = pp.contents
+            cnt = int(p.n_results)
+            r0 = int(p.row_begin)
+            base = r0 * (2 * n - r0 - 1) // 2
+            src = np.frombuffer((C.c_uint8 * (cnt * out.itemsize)).from_address(p.data), dtype=dtype, count=cnt)
+            out[base:base + cnt] = src
+            panels.append((int(p.mode), r0, int(p.row_end), int(p.n_cols), cnt))
+            return 0
+
+        cb = SINK_FN(sink)
+        cnt = None if acgt is None else np.ascontiguousarray(acgt, dtype=np.uint64)
+        cptr = None if cnt is None else cnt.ctypes.data_as(C.c_void_p)
+        if one_call:
+            self._check(self.L.dg_run_square_host(self.h, codes.ctypes.data_as(C.c_void_p), n, input_kind, cptr,
+                                                  part, n_parts, cb, None))
+        else:
+            self._check(self.L.dg_square_begin(self.h, n, input_kind, cptr, part, n_parts, cb, None))
+            lo, hi = C.c_uint64(), C.c_uint64()
+            while True:
+                self._check(self.L.dg_square_next(self.h, C.byref(lo), C.byref(hi)))
+                if hi.value == lo.value:
+                    break
+                if push is not None:
+                    push(int(lo.value), int(hi.value))
+                else:
+                    self._check(self.L.dg_square_push(self.h, C.c_void_p(codes.ctypes.data + lo.value * self.width), -1,
+                                                      lo.value, hi.value))
+            self._check(self.L.dg_square_end(self.h))
+        self._n[0] = n
+        self.last_panels = panels
+        return out, panels
+
+    def square_pipelined_discard(self, pinned_codes: np.ndarray, part: int = 0, n_parts: int = 1,
+                                 input_kind: int = DG_INPUT_PARADIS):
+        """dg_run_square_host with a sink that reads one word per panel (bench.py's e2e step)."""
+        state = {"n": 0, "acc": 0}
+
+        def sink(user, pp):
+            p = pp.contents
+            state["n"] += int(p.n_results)
+            if p.n_results:
+                state["acc"] ^= C.c_uint32.from_address(p.data).value
+            return 0
+
+        n = pinned_codes.shape[0]
+        self._check(self.L.dg_run_square_host(self.h, C.c_void_p(pinned_codes.ctypes.data), n, input_kind, None,
+                                              part, n_parts, SINK_FN(sink), None))
+        self._n[0] = n
         return state["n"]
 
     def stream(self, batches, input_kind: int = DG_INPUT_PARADIS, max_batch: int = 1 << 20, acgt_batches=None):

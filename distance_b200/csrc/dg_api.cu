@@ -99,6 +99,7 @@ struct PlaneSet {  // one alignment packed on one device
     uint64_t cap_pad = 0;     // resident sets: record capacity of codes / acgt / tc_ops (buffers are reused across loads)
     bool lop3_ready = false;  // core / aux hold the current alignment (built lazily: only when the LOP3 engine runs)
     bool tc_ready = false;    // tc_ops / pp hold the current alignment
+    bool pp_stale = false;    // loaded by a dg_square_* session: pp (the per-site index) is rebuilt on first use
     // tcgen05 engine (DG_OPT_ENGINE = 2): int8 one-hot operand planes, N-like counts, partial-code index
     int8_t* tc_ops = nullptr;
     bool tc_fp4 = false;      // tc_ops hold E2M1 nibbles (engine 3) instead of int8 (engine 2)
@@ -139,11 +140,37 @@ struct Device {
     uint32_t* pp_cnt = nullptr;     // [width] partial codes per site
     uint32_t* pp_cursor = nullptr;  // [width]
     double* pp_work = nullptr;
+    uint64_t* pp_hits = nullptr;    // partial codes met by pack_ops_kernel (unsorted entries)
+    uint32_t pp_hit_cap = 0;
+    uint32_t* pp_hit_count = nullptr;
     uint32_t* h_pp_total = nullptr; // pinned {entries}
     double* h_pp_work = nullptr;    // pinned
     cudaEvent_t chunk_ev[32] = {};
     unsigned long long* d_invalid = nullptr;  // [3]: ring slot 0, ring slot 1, resident loads
     unsigned long long* h_invalid = nullptr;  // [3] pinned mirror
+    // pipelined all-vs-all session (dg_square_*): a deeper result ring of small panels + the chunked index
+    static constexpr int NPS = 4;
+    Slot pslot[NPS];
+    size_t pout_cap = 0;
+    uint32_t* sq_off = nullptr;      // [chunks][width + 1] offsets into sq_entries
+    size_t sq_off_chunks = 0;
+    uint32_t* sq_cum = nullptr;      // [width] partial codes per site over every chunk so far
+    uint32_t* sq_total = nullptr;    // [1] running entry count
+    uint64_t* sq_entries = nullptr;
+    uint32_t sq_entries_cap = 0;
+    std::vector<void*> sq_retired;   // outgrown entry buffers, freed when the session ends
+    uint32_t* h_sq_total = nullptr;  // pinned [chunks]
+    double* h_sq_work = nullptr;     // pinned [chunks]
+    unsigned long long* h_sq_invalid = nullptr;  // pinned [chunks]
+    std::vector<cudaEvent_t> sq_ev;  // per chunk: index scanned (or just packed)
+    cudaEvent_t sq_ready = nullptr;  // entries of the chunks pumped so far are in place
+    cudaStream_t prep = nullptr;     // packing + index scan of a session: highest priority, so it slips in between
+                                     // the persistent tile launches instead of queueing behind them
+    cudaStream_t fill = nullptr;     // entry scatter of pumped chunks (not behind the packing of later chunks)
+    // DG_TRACE: device timeline of a session (timing events, ms relative to tr_base)
+    cudaEvent_t tr_base = nullptr;
+    std::vector<cudaEvent_t> tr_copy, tr_prep;             // per chunk: copy landed, pack + scan done
+    std::vector<cudaEvent_t> tr_k0, tr_k1, tr_d2h;         // per launched panel
 };
 
 struct Panel {
@@ -187,6 +214,26 @@ struct dg_ctx {
     uint64_t s_max_batch = 0, s_rows_pushed = 0, s_batches = 0;
     std::vector<InFlight> s_queue;  // FIFO of batches not yet sunk
     double s_t0 = 0;
+
+    // pipelined all-vs-all session (dg_square_*)
+    struct SqChunk { uint64_t lo, hi; };
+    bool sq_open = false;
+    bool sq_tc = false, sq_fallback = false, sq_needs_pp = false;
+    std::vector<Panel> sq_panels;      // this part's panels, ascending rows; launched from the back
+    int sq_next = -1;                  // next panel to launch
+    std::vector<SqChunk> sq_chunks;    // descending record ranges, pushed in this order
+    size_t sq_pushed = 0, sq_pumped = 0;
+    std::vector<uint32_t> sq_base;     // entries before chunk g (size chunks + 1), known once chunk g-1 is pumped
+    uint64_t sq_n = 0, sq_launched = 0;
+    int sq_input_kind = 0;
+    dg_sink_fn sq_sink = nullptr;
+    void* sq_user = nullptr;
+    std::vector<InFlight> sq_queue;
+    double sq_t0 = 0;
+    int pipe_panels = 24;              // DG_OPT_PIPE_PANELS
+    uint64_t pipe_chunk_bytes = 0;     // DG_OPT_PIPE_CHUNK_BYTES (0 = automatic)
+    bool sq_trace = false;
+    std::vector<int> sq_trace_panel;   // panel index of the n-th launch
 
     bool result_u16 = false;  // DG_OPT_RESULT_U16: n / n_high panels hold uint16 counts (needs width <= 65535)
     bool u16() const { return measure <= 1 && result_u16; }
@@ -344,7 +391,8 @@ void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
 // Enqueue (no sync) the int8 operand planes (and, with count_acgt, the per-record A,T,G,C counts) of rows
 // [row0, row0 + n) of the set; the chunk's padding rows up to a multiple of 128 are zero-filled.
 void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, bool count_acgt,
-                     cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr, bool upper_ascii = false) {
+                     cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr, bool upper_ascii = false,
+                     Device* pp_dev = nullptr) {
     const TcSchedule& sch = tc_schedule(c->fam);
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     tc::PackI8Params pp{};
@@ -353,6 +401,10 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     pp.acgt = count_acgt ? s.acgt + row0 * 4 : nullptr;
     pp.count_upper_ascii = upper_ascii && input_kind == DG_INPUT_ASCII ? 1 : 0;
     pp.invalid = d_inv; pp.seq0 = row0;
+    if (pp_dev) {   // also collect the partial ambiguity codes (per-site counts + unsorted entries) for the repair index
+        pp.pp_site_cnt = pp_dev->pp_cnt; pp.pp_hits = pp_dev->pp_hits;
+        pp.pp_hit_count = pp_dev->pp_hit_count; pp.pp_hit_cap = pp_dev->pp_hit_cap;
+    }
     pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
@@ -362,10 +414,22 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     c->tm.pack_launches++;
 }
 
+// Buffer for the partial codes pack_ops_kernel meets: room for 1 site in 128 (real data: ~1 in 1000; alignments with
+// more than ~0.8 % partial codes run on the LOP3 engine anyway).  If it overflows, the index is filled by rescanning.
+void ensure_pp_hits(dg_ctx* c, Device& d, uint64_t n) {
+    const uint64_t want = std::min<uint64_t>(std::max<uint64_t>(1u << 20, n * c->width / 128), 0xFFFFFFF0ull);
+    if (!d.pp_hit_count) CUDA_CHECK(cudaMalloc(&d.pp_hit_count, 4));
+    if (d.pp_hit_cap >= want) return;
+    if (d.pp_hits) cudaFree(d.pp_hits);
+    d.pp_hits = nullptr; d.pp_hit_cap = 0;
+    CUDA_CHECK(cudaMalloc(&d.pp_hits, want * 8));
+    d.pp_hit_cap = (uint32_t)want;
+}
+
 // Inverted index of the partial ambiguity codes of a resident alignment: the per-site counts were
 // accumulated by pp_count_kernel while the chunks arrived; scan them, then scatter the entries
 // (counting sort by site).  Synchronises the stream: the entry count sizes the allocation.
-void finish_pp_index(dg_ctx* c, Device& d, PlaneSet& s, cudaStream_t st) {
+void finish_pp_index(dg_ctx* c, Device& d, PlaneSet& s, cudaStream_t st, bool from_hits = false) {
     if (!s.pp.site_off) CUDA_CHECK(cudaMalloc(&s.pp.site_off, (size_t)(c->width + 1) * 4));
     const int ascii = s.input_kind == DG_INPUT_ASCII;
     tc::pp_scan_kernel<<<1, 1024, 0, st>>>(d.pp_cnt, c->width, s.pp.site_off, d.pp_cursor, d.pp_work);
@@ -381,7 +445,11 @@ void finish_pp_index(dg_ctx* c, Device& d, PlaneSet& s, cudaStream_t st) {
         s.pp.cap_entries = std::max<uint32_t>(1024, s.pp.n_entries + s.pp.n_entries / 4);
         CUDA_CHECK(cudaMalloc(&s.pp.entries, (size_t)s.pp.cap_entries * 8));
     }
-    if (s.pp.n_entries) {
+    if (s.pp.n_entries && from_hits && s.pp.n_entries <= d.pp_hit_cap) {   // scatter what pack_ops_kernel collected
+        tc::pp_scatter_kernel<<<(unsigned)std::min<uint32_t>((s.pp.n_entries + 255) / 256, 148 * 8), 256, 0, st>>>(
+            d.pp_hits, 0, s.pp.n_entries, d.pp_cursor, s.pp.entries);
+        CUDA_CHECK(cudaGetLastError());
+    } else if (s.pp.n_entries) {
         const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
         tc::pp_fill_kernel<<<gb, 256, 0, st>>>(s.codes, s.n, c->width, ascii, d.pp_cursor, s.pp.entries);
         CUDA_CHECK(cudaGetLastError());
@@ -514,6 +582,28 @@ bool tc_pp_pending(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B, bool a
     return tc_schedule(c->fam).needs_pp && B.pp.n_entries != 0 && (a_is_batch || A.pp.n_entries != 0);
 }
 
+// Raw int32 sums of every accumulator (scratch[accumulator][panel pair]) -> the reference's counts -> the result
+// (uint16 / uint32 count, f64 distance through the epi_* epilogues, or the debug counts).
+void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p, void* d_out,
+                    int* scratch, bool swap_roles, bool counts, cudaStream_t st) {
+    tc::CombineParams cp{};
+    cp.acc = scratch; cp.acc_stride = p.n_results;
+    cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
+    cp.n_b = (uint32_t)B.n; cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
+    cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
+    cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
+    cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
+    cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
+    cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
+    // ~16 CTAs per SM, each walking many rows of its 256-column strip (one element per thread and row: coalesced)
+    const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
+    dim3 grid(gx, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx))));
+    if (grid.x == 0 || grid.y == 0) return;
+    tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.count_launches++;
+}
+
 // tcgen05 variant of enqueue_panel_kernel.  n / n_high with no correction pending: one GEMM writes the result
 // directly.  Otherwise (and for the debug counts): one GEMM per accumulator into `scratch`, the both-partial
 // repair of accumulator 0, then tc_combine_kernel.
@@ -548,22 +638,7 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
         CUDA_CHECK(cudaGetLastError());
         c->tm.count_launches++;
     }
-    tc::CombineParams cp{};
-    cp.acc = scratch; cp.acc_stride = stride;
-    cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
-    cp.n_b = (uint32_t)B.n; cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
-    cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
-    cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
-    cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
-    cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
-    cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
-    // ~16 CTAs per SM, each walking many rows of its 256-column strip (one element per thread and row: coalesced)
-    const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
-    dim3 grid(gx, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx))));
-    if (grid.x == 0 || grid.y == 0) return;
-    tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
-    CUDA_CHECK(cudaGetLastError());
-    c->tm.count_launches++;
+    launch_combine(c, d, A, B, mode, p, d_out, scratch, swap_roles, counts, st);
 }
 
 void ensure_scratch(dg_ctx* c, Slot& s, size_t pairs) {
@@ -705,9 +780,13 @@ void ensure_lop3(dg_ctx* c, Device& d, PlaneSet& s) {
 }
 
 // ---- square / rect runs ------------------------------------------------------------------------
+void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc_run, dg_sink_fn sink, void* user,
+                    bool device_only);
+void ensure_pp_index(dg_ctx* c, Device& d, PlaneSet& s);
+
 void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user,
               uint32_t flags) {
-    if (c->streaming) fail(DG_ERR_STATE, "a stream session is open");
+    if (c->streaming || c->sq_open) fail(DG_ERR_STATE, "a session is open");
     if (n_parts == 0 || part >= n_parts) fail(DG_ERR_INVALID_ARG, "bad part %u of %u", part, n_parts);
     const int wb = mode == DG_MODE_SQUARE ? 0 : 1;
     for (auto& d : c->devs) {
@@ -724,6 +803,8 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         CUDA_CHECK(cudaStreamWaitEvent(d.compute2, d.run_start, 0));
     }
 
+    for (auto& d : c->devs)
+        for (int w = 0; w <= wb; w++) ensure_pp_index(c, d, d.set[w]);
     const bool tc_run = use_tc(c, c->devs[0].set[0], c->devs[0].set[wb]);
     c->last_engine = tc_run ? (c->devs[0].set[0].tc_fp4 ? 3 : 2) : 1;
     if (!tc_run)
@@ -753,6 +834,29 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     std::vector<Panel> mine;
     for (size_t k = 0; k < all.size(); k++)
         if (k % n_parts == part) mine.push_back(all[k]);
+    run_panel_list(c, mode, mine, tc_run, sink, user, device_only);
+    c->tm.run_ms = 0;
+    for (auto& d : c->devs) {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        CUDA_CHECK(cudaEventRecord(d.slot[1].in_ready, d.compute2));
+        CUDA_CHECK(cudaStreamWaitEvent(d.compute, d.slot[1].in_ready, 0));
+        CUDA_CHECK(cudaEventRecord(d.run_stop, d.compute));
+        CUDA_CHECK(cudaEventSynchronize(d.run_stop));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, d.run_start, d.run_stop));
+        c->tm.run_ms = std::max<double>(c->tm.run_ms, ms);
+    }
+    c->tm.total_ms = wall_ms() - t0;
+}
+
+// The panels of `mine` in order: panel k on device k % ndev, two ring slots per device (the D2H of a panel and
+// its sink call overlap the tiles of the next ones); the sink sees the panels serially, in list order.
+void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc_run, dg_sink_fn sink, void* user,
+                    bool device_only) {
+    const int wb = mode == DG_MODE_SQUARE ? 0 : 1;
+    const int ndev = (int)c->devs.size();
+    const PlaneSet& A0 = c->devs[0].set[0];
+    const PlaneSet& B0 = c->devs[0].set[wb];
     size_t max_bytes = 0;
     for (auto& p : mine) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
     for (auto& d : c->devs) {
@@ -808,18 +912,392 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
             }
         }
     }
-    c->tm.run_ms = 0;
-    for (auto& d : c->devs) {
-        CUDA_CHECK(cudaSetDevice(d.id));
-        CUDA_CHECK(cudaEventRecord(d.slot[1].in_ready, d.compute2));
-        CUDA_CHECK(cudaStreamWaitEvent(d.compute, d.slot[1].in_ready, 0));
-        CUDA_CHECK(cudaEventRecord(d.run_stop, d.compute));
-        CUDA_CHECK(cudaEventSynchronize(d.run_stop));
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, d.run_start, d.run_stop));
-        c->tm.run_ms = std::max<double>(c->tm.run_ms, ms);
+}
+
+// Rebuild the classic per-site index of a resident alignment that was loaded by a dg_square_* session
+// (the session keeps a chunked index of its own; see sq_pump).
+void ensure_pp_index(dg_ctx* c, Device& d, PlaneSet& s) {
+    if (!s.pp_stale) return;
+    s.pp_stale = false;
+    if (!s.tc_ready || !tc_schedule(c->fam).needs_pp) return;
+    CUDA_CHECK(cudaSetDevice(d.id));
+    CUDA_CHECK(cudaMemsetAsync(d.pp_cnt, 0, (size_t)c->width * 4, d.compute));
+    const unsigned gb = (unsigned)std::min<uint64_t>((s.n * c->width + 255) / 256, 148 * 32);
+    tc::pp_count_kernel<<<gb, 256, 0, d.compute>>>(s.codes, s.n, c->width, s.input_kind == DG_INPUT_ASCII, d.pp_cnt);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.pack_launches++;
+    finish_pp_index(c, d, s, d.compute);
+}
+
+// ---- pipelined all-vs-all session (dg_square_*) -------------------------------------------------------
+// The caller pushes the alignment in chunks, HIGHEST records first.  Row i of the upper triangle needs the
+// records j > i only, so once the records [lo, n) have landed every panel whose rows start at or above lo can
+// run: upload (PCIe H2D), packing + tiles, and the D2H of finished panels all overlap, and panels reach the sink
+// in completion order (descending rows).  The both-partial repair of n / n_high / raw / jc69 uses a chunked
+// index (one per-site offset table per chunk over one shared entry buffer) that grows with the chunks.
+void ensure_pipe_ring(dg_ctx* c, Device& d, size_t bytes, bool scratch) {
+    if (d.pout_cap < bytes) {
+        for (auto& s : d.pslot) {
+            if (s.d_out) cudaFree(s.d_out);
+            if (s.h_out) cudaFreeHost(s.h_out);
+            s.d_out = s.h_out = nullptr;
+        }
+        d.pout_cap = 0;
+        for (auto& s : d.pslot) {
+            CUDA_CHECK(cudaMalloc(&s.d_out, bytes));
+            CUDA_CHECK(cudaHostAlloc(&s.h_out, bytes, cudaHostAllocDefault));
+        }
+        d.pout_cap = bytes;
     }
-    c->tm.total_ms = wall_ms() - t0;
+    if (scratch)
+        for (auto& s : d.pslot) ensure_scratch(c, s, std::max<size_t>(bytes / c->elem_bytes(), 64));
+}
+
+void sq_abort(dg_ctx* c) {
+    for (auto& d : c->devs) {
+        cudaSetDevice(d.id);
+        cudaDeviceSynchronize();
+        cudaMemset(d.d_invalid, 0xff, 3 * sizeof(unsigned long long));
+        for (int i = 0; i < 3; i++) d.h_invalid[i] = ~0ull;
+        for (void* q : d.sq_retired) cudaFree(q);
+        d.sq_retired.clear();
+        d.set[0].n = 0; d.set[0].tc_ready = false; d.set[0].lop3_ready = false;
+    }
+    c->sq_queue.clear();
+    c->sq_open = false;
+}
+
+void sq_sink_front(dg_ctx* c) {
+    InFlight f = c->sq_queue.front();
+    Device& d = c->devs[0];
+    Slot& s = d.pslot[f.slot];
+    CUDA_CHECK(cudaEventSynchronize(s.copied));
+    harvest_kernel_time(c, s);
+    c->tm.pairs += f.pairs;
+    c->tm.d2h_bytes += f.desc.n_results * c->elem_bytes();
+    f.desc.data = s.h_out;
+    c->sq_queue.erase(c->sq_queue.begin());
+    if (c->sq_sink(c->sq_user, &f.desc) != 0) fail(DG_ERR_SINK, "sink aborted the session");
+}
+
+void sq_report_invalid(dg_ctx* c, Device& d, unsigned long long key) {
+    const unsigned long long reset = ~0ull;
+    CUDA_CHECK(cudaMemcpy(d.d_invalid + 2, &reset, sizeof reset, cudaMemcpyHostToDevice));
+    c->have_invalid = true;
+    c->inv_record = key >> 32;
+    c->inv_site = key & 0xffffffffull;
+    c->inv_byte = 0;
+    CUDA_CHECK(cudaMemcpy(&c->inv_byte, d.set[0].codes + c->inv_record * c->width + c->inv_site, 1, cudaMemcpyDeviceToHost));
+    fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in record %llu at site %llu", c->inv_byte,
+         (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
+}
+
+void sq_launch_panel(dg_ctx* c, int k) {
+    Device& d = c->devs[0];
+    PlaneSet& S = d.set[0];
+    while ((int)c->sq_queue.size() >= Device::NPS) sq_sink_front(c);
+    const int si = (int)(c->sq_launched % Device::NPS);
+    c->sq_launched++;
+    Slot& s = d.pslot[si];
+    const Panel& p = c->sq_panels[k];
+    cudaStream_t st = d.cs(si & 1);
+    CUDA_CHECK(cudaStreamWaitEvent(st, d.sq_ready, 0));
+    CUDA_CHECK(cudaEventRecord(s.k_start, st));
+    const size_t li = c->sq_trace_panel.size();
+    if (c->sq_trace) {
+        c->sq_trace_panel.push_back(k);
+        for (auto* v : {&d.tr_k0, &d.tr_k1, &d.tr_d2h})
+            while (v->size() <= li) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); v->push_back(e); }
+        CUDA_CHECK(cudaEventRecord(d.tr_k0[li], st));
+    }
+    const uint32_t n_entries = c->sq_base[c->sq_pumped];   // entries of every chunk pumped so far
+    const bool repair = c->sq_needs_pp && n_entries != 0;
+    if (c->fam == FAM_SNP && !repair) {
+        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s);
+    } else {
+        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s);
+        if (repair) {
+            // the panel's rows live in the chunks [ga0, ga1): chunks are descending, find those that overlap the rows
+            size_t ga0 = c->sq_pumped, ga1 = 0;
+            for (size_t g = 0; g < c->sq_pumped; g++)
+                if (c->sq_chunks[g].lo < p.row1 && c->sq_chunks[g].hi > p.row0) { ga0 = std::min(ga0, g); ga1 = std::max(ga1, g + 1); }
+            tc::PpChunkParams cp{};
+            cp.entries = d.sq_entries; cp.off = d.sq_off; cp.off_stride = (uint32_t)(c->width + 1);
+            cp.n_chunks = (uint32_t)c->sq_pumped;
+            cp.a_begin = ga0 < ga1 ? c->sq_base[ga0] : 0; cp.a_end = ga0 < ga1 ? c->sq_base[ga1] : 0;
+            cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
+            cp.n_total = S.n; cp.out_base = p.out_base; cp.out = s.d_scratch;
+            if (cp.a_end > cp.a_begin) {
+                const unsigned gb = (unsigned)std::min<uint32_t>((cp.a_end - cp.a_begin + 127) / 128, 148 * 8);
+                tc::pp_correct_chunks_kernel<<<gb, 128, 0, st>>>(cp);
+                CUDA_CHECK(cudaGetLastError());
+                c->tm.count_launches++;
+            }
+        }
+        launch_combine(c, d, S, S, DG_MODE_SQUARE, p, s.d_out, s.d_scratch, false, false, st);
+    }
+    CUDA_CHECK(cudaEventRecord(s.k_stop, st));
+    if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_k1[li], st));
+    CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
+    CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(), cudaMemcpyDeviceToHost, d.copy));
+    CUDA_CHECK(cudaEventRecord(s.copied, d.copy));
+    if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_d2h[li], d.copy));
+    InFlight f;
+    f.dev = 0; f.slot = si; f.pairs = p.n_results;
+    f.desc.mode = DG_MODE_SQUARE;
+    f.desc.result_kind = c->result_kind();
+    f.desc.row_begin = p.row0; f.desc.row_end = p.row1;
+    f.desc.n_cols = S.n; f.desc.n_results = p.n_results;
+    c->sq_queue.push_back(f);
+}
+
+// Chunk g has been pushed (its packing and index scan are enqueued): finish its part of the index and launch
+// every panel whose rows now have all their columns on the device.
+void sq_pump(dg_ctx* c, size_t g) {
+    Device& d = c->devs[0];
+    PlaneSet& S = d.set[0];
+    const auto& ch = c->sq_chunks[g];
+    CUDA_CHECK(cudaEventSynchronize(d.sq_ev[g]));
+    if (d.h_sq_invalid[g] != ~0ull) sq_report_invalid(c, d, d.h_sq_invalid[g]);
+    uint32_t total = c->sq_base[g];
+    if (c->sq_tc && c->sq_needs_pp) {
+        total = d.h_sq_total[g];
+        if (total > d.sq_entries_cap) {   // grow the shared entry buffer (old one is freed when the session ends)
+            const uint32_t cap = std::max<uint32_t>(total + total / 2, 1u << 20);
+            uint64_t* fresh = nullptr;
+            CUDA_CHECK(cudaMalloc(&fresh, (size_t)cap * 8));
+            if (d.sq_entries) {
+                CUDA_CHECK(cudaMemcpyAsync(fresh, d.sq_entries, (size_t)c->sq_base[g] * 8, cudaMemcpyDeviceToDevice, d.fill));
+                d.sq_retired.push_back(d.sq_entries);
+            }
+            d.sq_entries = fresh; d.sq_entries_cap = cap;
+        }
+        uint32_t* cursor = d.sq_off + g * (size_t)(c->width + 1) + 1;
+        if (total > c->sq_base[g] && total <= d.pp_hit_cap) {
+            // the pack kernel appended this chunk's partial codes at hits[base_g, total): the running hit count is the
+            // running entry count
+            tc::pp_scatter_kernel<<<(unsigned)std::min<uint32_t>((total - c->sq_base[g] + 255) / 256, 148 * 4), 256, 0, d.fill>>>(
+                d.pp_hits, c->sq_base[g], total, cursor, d.sq_entries);
+            CUDA_CHECK(cudaGetLastError());
+            c->tm.pack_launches++;
+        } else if (total > c->sq_base[g]) {   // hit buffer overflowed: rescan the chunk's codes
+            const uint64_t nr = ch.hi - ch.lo;
+            const unsigned gb = (unsigned)std::min<uint64_t>((nr * c->width + 255) / 256, 148 * 32);
+            tc::pp_fill_kernel<<<gb, 256, 0, d.fill>>>(S.codes + ch.lo * c->width, nr, c->width, c->sq_input_kind == DG_INPUT_ASCII,
+                                                      cursor, d.sq_entries, ch.lo);
+            CUDA_CHECK(cudaGetLastError());
+            c->tm.pack_launches++;
+        }
+        // auto engine: an alignment so full of partial codes that the repair would cost more than the tiles finishes
+        // on the LOP3 engine (same rule as use_tc)
+        const double m = (double)(c->sq_n - ch.lo);
+        if (c->engine == 0 && d.h_sq_work[g] > 2.0 * m * m && m >= 1024) c->sq_fallback = true;
+    }
+    c->sq_base[g + 1] = total;
+    c->sq_pumped = g + 1;
+    CUDA_CHECK(cudaEventRecord(d.sq_ready, d.fill));   // the host has waited for chunk g's scan: nothing else to order
+    if (!c->sq_tc || c->sq_fallback) return;
+    while (c->sq_next >= 0 && c->sq_panels[c->sq_next].row0 >= ch.lo) sq_launch_panel(c, c->sq_next--);
+}
+
+void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
+              dg_sink_fn sink, void* user) {
+    if (c->streaming || c->sq_open) fail(DG_ERR_STATE, "a session is already open");
+    if (c->devs.size() != 1) fail(DG_ERR_STATE, "dg_square_* sessions drive one device per context (one process per GPU)");
+    if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
+    if (n == 0 || n >= (1ull << 31)) fail(DG_ERR_INVALID_ARG, "bad record count");
+    if (n_parts == 0 || part >= n_parts) fail(DG_ERR_INVALID_ARG, "bad part %u of %u", part, n_parts);
+    if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+    Device& d = c->devs[0];
+    CUDA_CHECK(cudaSetDevice(d.id));
+    c->have_invalid = false;
+    PlaneSet& S = d.set[0];
+    const bool want_tc = c->engine != 1;
+    reserve_resident(c, S, n, want_tc);
+    S.input_kind = input_kind;
+    S.acgt_from_host = acgt_counts != nullptr;
+    S.pp_stale = true;
+    c->sq_tc = want_tc;
+    c->sq_fallback = false;
+    c->sq_needs_pp = tc_schedule(c->fam).needs_pp;
+    c->sq_n = n;
+    c->sq_input_kind = input_kind;
+    c->sq_sink = sink; c->sq_user = user;
+    c->sq_queue.clear();
+    c->sq_launched = 0;
+    c->last_engine = want_tc ? (c->want_fp4() ? 3 : 2) : 1;
+    if (acgt_counts) {
+        std::vector<uint32_t> c32(n * 4);
+        for (uint64_t i = 0; i < n * 4; i++) c32[i] = (uint32_t)acgt_counts[i];
+        CUDA_CHECK(cudaMemsetAsync(S.acgt, 0, (size_t)S.n_pad * 16, d.compute));
+        CUDA_CHECK(cudaMemcpyAsync(S.acgt, c32.data(), (size_t)n * 16, cudaMemcpyHostToDevice, d.compute));
+        CUDA_CHECK(cudaStreamSynchronize(d.compute));
+    }
+    // panels: the whole triangle in ~pipe_panels x n_parts pieces (small panels keep the D2H stream fed from early on)
+    const TileShape ts = tile_shape(c->fam, c->tile_variant);
+    const uint64_t total_bytes = n * (n - 1) / 2 * c->elem_bytes();
+    const size_t pb = (size_t)std::min<uint64_t>(c->panel_bytes,
+                          std::max<uint64_t>(8ull << 20, total_bytes / ((uint64_t)std::max(1, c->pipe_panels) * n_parts)));  // DG_OPT_PANEL_BYTES caps it
+    std::vector<Panel> all = make_panels(pb, c->elem_bytes(), DG_MODE_SQUARE, n, n, ts.tm);
+    c->sq_panels.clear();
+    for (size_t k = 0; k < all.size(); k++)
+        if (k % n_parts == part) c->sq_panels.push_back(all[k]);
+    c->sq_next = (int)c->sq_panels.size() - 1;
+    size_t max_bytes = 256;
+    for (auto& p : c->sq_panels) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
+    if (want_tc) ensure_pipe_ring(c, d, max_bytes, c->fam != FAM_SNP || c->sq_needs_pp);
+    // chunks: the same for every part (a multi-rank launcher broadcasts them): <= ~40 pieces of >= 24 MB, descending,
+    // every boundary but n itself a multiple of ROW_ALIGN (the pack kernel zero-fills whole 128-row groups)
+    const uint64_t target = c->pipe_chunk_bytes ? c->pipe_chunk_bytes : std::max<uint64_t>(24ull << 20, n * c->width / 40);
+    const uint64_t rows = std::max<uint64_t>(ROW_ALIGN, target / c->width / ROW_ALIGN * ROW_ALIGN);
+    c->sq_chunks.clear();
+    for (uint64_t hi = n; hi > 0;) {
+        uint64_t lo = hi > rows ? (hi - rows) / ROW_ALIGN * ROW_ALIGN : 0;
+        if (lo < ROW_ALIGN * 2) lo = 0;   // no sliver at the bottom
+        c->sq_chunks.push_back({lo, hi});
+        hi = lo;
+    }
+    const size_t G = c->sq_chunks.size();
+    c->sq_pushed = c->sq_pumped = 0;
+    c->sq_base.assign(G + 1, 0);
+    if (d.sq_ev.size() < G) {
+        const size_t old = d.sq_ev.size();
+        d.sq_ev.resize(G, nullptr);
+        for (size_t g = old; g < G; g++) CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ev[g], cudaEventDisableTiming));
+    }
+    if (d.sq_off_chunks < G) {
+        if (d.sq_off) cudaFree(d.sq_off);
+        if (d.h_sq_total) cudaFreeHost(d.h_sq_total);
+        if (d.h_sq_work) cudaFreeHost(d.h_sq_work);
+        if (d.h_sq_invalid) cudaFreeHost(d.h_sq_invalid);
+        d.sq_off = nullptr; d.h_sq_total = nullptr; d.h_sq_work = nullptr; d.h_sq_invalid = nullptr; d.sq_off_chunks = 0;
+        CUDA_CHECK(cudaMalloc(&d.sq_off, G * (size_t)(c->width + 1) * 4));
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_total, G * 4, cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_work, G * 8, cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_invalid, G * 8, cudaHostAllocDefault));
+        d.sq_off_chunks = G;
+    }
+    if (!d.sq_cum) CUDA_CHECK(cudaMalloc(&d.sq_cum, (size_t)c->width * 4));
+    if (!d.sq_total) CUDA_CHECK(cudaMalloc(&d.sq_total, 4));
+    if (!d.sq_ready) CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ready, cudaEventDisableTiming));
+    if (!d.prep) {
+        int lo_pri = 0, hi_pri = 0;
+        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&d.prep, cudaStreamNonBlocking, hi_pri));
+        CUDA_CHECK(cudaStreamCreateWithPriority(&d.fill, cudaStreamNonBlocking, hi_pri));
+    }
+    CUDA_CHECK(cudaMemsetAsync(d.sq_cum, 0, (size_t)c->width * 4, d.prep));
+    CUDA_CHECK(cudaMemsetAsync(d.sq_total, 0, 4, d.prep));
+    if (want_tc && c->sq_needs_pp) {
+        ensure_pp_hits(c, d, n);
+        CUDA_CHECK(cudaMemsetAsync(d.pp_hit_count, 0, 4, d.prep));
+    }
+    c->sq_trace = std::getenv("DG_TRACE") != nullptr;
+    c->sq_trace_panel.clear();
+    if (c->sq_trace) {
+        if (!d.tr_base) CUDA_CHECK(cudaEventCreate(&d.tr_base));
+        for (auto* v : {&d.tr_copy, &d.tr_prep})
+            while (v->size() < G) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); v->push_back(e); }
+        CUDA_CHECK(cudaEventRecord(d.tr_base, d.copy_in));
+    }
+    c->sq_t0 = wall_ms();
+    c->sq_open = true;
+}
+
+void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t hi) {
+    if (!c->sq_open) fail(DG_ERR_STATE, "no dg_square session is open");
+    if (c->sq_pushed >= c->sq_chunks.size()) fail(DG_ERR_STATE, "every chunk of the session has been pushed");
+    const auto ch = c->sq_chunks[c->sq_pushed];
+    if (lo != ch.lo || hi != ch.hi)
+        fail(DG_ERR_INVALID_ARG, "the session expects records [%llu, %llu) next (dg_square_next), got [%llu, %llu)",
+             (unsigned long long)ch.lo, (unsigned long long)ch.hi, (unsigned long long)lo, (unsigned long long)hi);
+    if (!codes) fail(DG_ERR_INVALID_ARG, "codes is NULL");
+    Device& d = c->devs[0];
+    PlaneSet& S = d.set[0];
+    CUDA_CHECK(cudaSetDevice(d.id));
+    const size_t g = c->sq_pushed;
+    const uint64_t nr = hi - lo;
+    uint8_t* dst = S.codes + lo * c->width;
+    if (src_dev < 0) {
+        CUDA_CHECK(cudaMemcpyAsync(dst, codes, (size_t)nr * c->width, cudaMemcpyHostToDevice, d.copy_in));
+        c->tm.h2d_bytes += nr * c->width;
+    } else {
+        CUDA_CHECK(cudaMemcpyPeerAsync(dst, d.id, codes, src_dev, (size_t)nr * c->width, d.copy_in));
+    }
+    cudaEvent_t ev = d.chunk_ev[g & 31];
+    CUDA_CHECK(cudaEventRecord(ev, d.copy_in));
+    if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_copy[g], d.copy_in));
+    // packing + index scan of this chunk: enqueued now, runs as soon as the copy has landed
+    CUDA_CHECK(cudaStreamWaitEvent(d.prep, ev, 0));
+    if (c->sq_tc) {
+        if (c->sq_needs_pp) CUDA_CHECK(cudaMemsetAsync(d.pp_cnt, 0, (size_t)c->width * 4, d.prep));
+        enqueue_tc_pack(c, S, S.codes, nr, c->sq_input_kind, !S.acgt_from_host && c->fam == FAM_TN93, d.prep, lo,
+                        d.d_invalid + 2, false, c->sq_needs_pp ? &d : nullptr);
+        if (c->sq_needs_pp) {
+            tc::pp_scan_chunk_kernel<<<1, 1024, 0, d.prep>>>(d.pp_cnt, d.sq_cum, c->width, d.sq_off + g * (size_t)(c->width + 1),
+                                                             d.sq_total, d.pp_work);
+            CUDA_CHECK(cudaGetLastError());
+            c->tm.pack_launches++;
+            CUDA_CHECK(cudaMemcpyAsync(d.h_sq_total + g, d.sq_total, 4, cudaMemcpyDeviceToHost, d.prep));
+            CUDA_CHECK(cudaMemcpyAsync(d.h_sq_work + g, d.pp_work, 8, cudaMemcpyDeviceToHost, d.prep));
+        }
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d.h_sq_invalid + g, d.d_invalid + 2, 8, cudaMemcpyDeviceToHost, d.prep));
+    CUDA_CHECK(cudaEventRecord(d.sq_ev[g], d.prep));
+    if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_prep[g], d.prep));
+    c->sq_pushed = g + 1;
+    // Finish chunk g - LOOKAHEAD (a short host wait: its copy landed a few chunks ago) and launch the panels it
+    // completes; the copies queued meanwhile keep PCIe busy.
+    if (c->sq_pushed > (size_t)DG_SQUARE_LOOKAHEAD) sq_pump(c, c->sq_pushed - 1 - DG_SQUARE_LOOKAHEAD);
+}
+
+void sq_end(dg_ctx* c) {
+    if (!c->sq_open) fail(DG_ERR_STATE, "no dg_square session is open");
+    if (c->sq_pushed != c->sq_chunks.size())
+        fail(DG_ERR_STATE, "dg_square_end: %zu of %zu chunks were pushed", c->sq_pushed, c->sq_chunks.size());
+    Device& d = c->devs[0];
+    PlaneSet& S = d.set[0];
+    CUDA_CHECK(cudaSetDevice(d.id));
+    while (c->sq_pumped < c->sq_pushed) sq_pump(c, c->sq_pumped);
+    while (!c->sq_queue.empty()) sq_sink_front(c);
+    if (c->sq_trace) {
+        CUDA_CHECK(cudaDeviceSynchronize());
+        auto at = [&](cudaEvent_t e) { float ms = 0; cudaEventElapsedTime(&ms, d.tr_base, e); return ms; };
+        fprintf(stderr, "[dg_square] %zu chunks, %zu panels launched, wall %.3f ms\n", c->sq_chunks.size(),
+                c->sq_trace_panel.size(), wall_ms() - c->sq_t0);
+        for (size_t g = 0; g < c->sq_chunks.size(); g++)
+            fprintf(stderr, "  chunk %2zu [%6llu,%6llu) copied %7.3f  prepped %7.3f\n", g, (unsigned long long)c->sq_chunks[g].lo,
+                    (unsigned long long)c->sq_chunks[g].hi, at(d.tr_copy[g]), at(d.tr_prep[g]));
+        for (size_t i = 0; i < c->sq_trace_panel.size(); i++) {
+            const Panel& p = c->sq_panels[c->sq_trace_panel[i]];
+            fprintf(stderr, "  panel %2d rows [%6llu,%6llu) %9llu pairs  tiles %7.3f - %7.3f  d2h done %7.3f\n", c->sq_trace_panel[i],
+                    (unsigned long long)p.row0, (unsigned long long)p.row1, (unsigned long long)p.n_results, at(d.tr_k0[i]),
+                    at(d.tr_k1[i]), at(d.tr_d2h[i]));
+        }
+    }
+    S.tc_ready = c->sq_tc;
+    if (c->sq_next >= 0) {
+        // LOP3 engine (forced, or chosen because the alignment is full of partial ambiguity codes): the remaining
+        // panels run the classic way on the now-resident alignment
+        CUDA_CHECK(cudaStreamSynchronize(d.prep));
+        CUDA_CHECK(cudaStreamSynchronize(d.fill));
+        std::vector<Panel> rest(c->sq_panels.begin(), c->sq_panels.begin() + c->sq_next + 1);
+        c->sq_next = -1;
+        if (c->sq_tc) ensure_pp_index(c, d, S);
+        const bool tc_run = use_tc(c, S, S);
+        if (!tc_run) {
+            ensure_lop3(c, d, S);
+            check_invalid(c, d, S.codes, 0);
+        }
+        c->last_engine = tc_run ? (S.tc_fp4 ? 3 : 2) : 1;
+        run_panel_list(c, DG_MODE_SQUARE, rest, tc_run, c->sq_sink, c->sq_user, false);
+    }
+    CUDA_CHECK(cudaStreamSynchronize(d.prep));
+    CUDA_CHECK(cudaStreamSynchronize(d.fill));
+    for (void* q : d.sq_retired) cudaFree(q);
+    d.sq_retired.clear();
+    c->tm.total_ms = wall_ms() - c->sq_t0;
+    c->sq_open = false;
 }
 
 // ---- stream session ----------------------------------------------------------------------------
@@ -850,11 +1328,12 @@ void stream_sink_front(dg_ctx* c) {
 }
 
 void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
-    if (c->streaming) fail(DG_ERR_STATE, "a stream session is already open");
+    if (c->streaming || c->sq_open) fail(DG_ERR_STATE, "a session is already open");
     if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
     if (max_batch == 0) fail(DG_ERR_INVALID_ARG, "max_batch is 0");
     for (auto& d : c->devs)
         if (d.set[0].n == 0) fail(DG_ERR_STATE, "alignment 0 is not loaded");
+    for (auto& d : c->devs) ensure_pp_index(c, d, d.set[0]);
     const uint64_t n_res = c->devs[0].set[0].n;
     // keep one batch's results within the panel budget
     const uint64_t cap_rows = std::max<uint64_t>(1, c->panel_bytes / (c->elem_bytes() * n_res));
@@ -1002,7 +1481,33 @@ void destroy_device(Device& d) {
         for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop})
             if (e) cudaEventDestroy(e);
     }
+    for (auto& s : d.pslot) {
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_scratch) cudaFree(s.d_scratch);
+        if (s.d_tiles) cudaFree(s.d_tiles);
+        if (s.h_tiles) cudaFreeHost(s.h_tiles);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied})
+            if (e) cudaEventDestroy(e);
+    }
+    if (d.sq_off) cudaFree(d.sq_off);
+    if (d.sq_cum) cudaFree(d.sq_cum);
+    if (d.sq_total) cudaFree(d.sq_total);
+    if (d.sq_entries) cudaFree(d.sq_entries);
+    for (void* q : d.sq_retired) cudaFree(q);
+    if (d.h_sq_total) cudaFreeHost(d.h_sq_total);
+    if (d.h_sq_work) cudaFreeHost(d.h_sq_work);
+    if (d.h_sq_invalid) cudaFreeHost(d.h_sq_invalid);
+    for (auto& e : d.sq_ev) if (e) cudaEventDestroy(e);
+    for (auto* v : {&d.tr_copy, &d.tr_prep, &d.tr_k0, &d.tr_k1, &d.tr_d2h})
+        for (auto& e : *v) if (e) cudaEventDestroy(e);
+    if (d.tr_base) cudaEventDestroy(d.tr_base);
+    if (d.prep) cudaStreamDestroy(d.prep);
+    if (d.fill) cudaStreamDestroy(d.fill);
+    if (d.sq_ready) cudaEventDestroy(d.sq_ready);
     if (d.pp_cnt) cudaFree(d.pp_cnt);
+    if (d.pp_hits) cudaFree(d.pp_hits);
+    if (d.pp_hit_count) cudaFree(d.pp_hit_count);
     if (d.pp_cursor) cudaFree(d.pp_cursor);
     if (d.pp_work) cudaFree(d.pp_work);
     if (d.h_pp_total) cudaFreeHost(d.h_pp_total);
@@ -1093,6 +1598,9 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
             for (auto& s : d.slot)
                 for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.in_ready, &s.p_start, &s.p_stop})
                     CUDA_CHECK(cudaEventCreate(e));
+            for (auto& s : d.pslot)
+                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied})
+                    CUDA_CHECK(cudaEventCreate(e));
             CUDA_CHECK(cudaEventCreate(&d.run_start));
             CUDA_CHECK(cudaEventCreate(&d.run_stop));
             CUDA_CHECK(cudaMalloc(&d.pp_cnt, (size_t)width * 4));
@@ -1145,6 +1653,14 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             if (value != 0 && ctx->width > 65535) fail(DG_ERR_INVALID_ARG, "uint16 results need width <= 65535");
             ctx->result_u16 = value != 0;
             break;
+        case DG_OPT_PIPE_PANELS:
+            if (value < 1 || value > 4096) fail(DG_ERR_INVALID_ARG, "pipe panels must be in [1, 4096]");
+            ctx->pipe_panels = (int)value;
+            break;
+        case DG_OPT_PIPE_CHUNK_BYTES:
+            if (value < 0) fail(DG_ERR_INVALID_ARG, "chunk bytes must be >= 0");
+            ctx->pipe_chunk_bytes = (uint64_t)value;
+            break;
         case DG_OPT_ENGINE:
             if (value < 0 || value > 3) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
             ctx->engine = (int)value;
@@ -1163,7 +1679,7 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
         if (!codes || n == 0) fail(DG_ERR_INVALID_ARG, "empty alignment");
         if (n >= (1ull << 31)) fail(DG_ERR_INVALID_ARG, "too many records");
         if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
-        if (ctx->streaming) fail(DG_ERR_STATE, "a stream session is open");
+        if (ctx->streaming || ctx->sq_open) fail(DG_ERR_STATE, "a session is open");
         ctx->have_invalid = false;
         std::vector<uint32_t> c32;
         if (acgt_counts) {
@@ -1186,8 +1702,13 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
             const uint64_t chunk = std::max<uint64_t>(ROW_ALIGN, (target / ctx->width + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN);
             uint32_t* pp_cnt = d.pp_cnt;
             int n_ev = 0;
+            s.pp_stale = false;
             try {
-                if (want_tc && needs_pp) CUDA_CHECK(cudaMemsetAsync(pp_cnt, 0, (size_t)ctx->width * 4, d.compute));
+                if (want_tc && needs_pp) {
+                    ensure_pp_hits(ctx, d, n);
+                    CUDA_CHECK(cudaMemsetAsync(pp_cnt, 0, (size_t)ctx->width * 4, d.compute));
+                    CUDA_CHECK(cudaMemsetAsync(d.pp_hit_count, 0, 4, d.compute));
+                }
                 const double th = wall_ms();
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
                 for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
@@ -1203,21 +1724,14 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
                     CUDA_CHECK(cudaStreamWaitEvent(d.compute, ev, 0));
                     if (want_tc) {
                         enqueue_tc_pack(ctx, s, s.codes, nr, input_kind, !acgt_counts && ctx->fam == FAM_TN93, d.compute, r0,
-                                        d.d_invalid + 2);
-                        if (needs_pp) {
-                            const unsigned gb = (unsigned)std::min<uint64_t>((nr * ctx->width + 255) / 256, 148 * 32);
-                            tc::pp_count_kernel<<<gb, 256, 0, d.compute>>>(s.codes + r0 * ctx->width, nr, ctx->width,
-                                                                           input_kind == DG_INPUT_ASCII, pp_cnt);
-                            CUDA_CHECK(cudaGetLastError());
-                            ctx->tm.pack_launches++;
-                        }
+                                        d.d_invalid + 2, false, needs_pp ? &d : nullptr);   // also collects the partial codes
                     }
                 }
                 if (acgt_counts) {
                     CUDA_CHECK(cudaMemsetAsync(s.acgt, 0, (size_t)s.n_pad * 16, d.compute));
                     CUDA_CHECK(cudaMemcpyAsync(s.acgt, c32.data(), (size_t)n * 16, cudaMemcpyHostToDevice, d.compute));
                 }
-                if (want_tc && needs_pp) finish_pp_index(ctx, d, s, d.compute);   // scan + fill (one sync for the entry count)
+                if (want_tc && needs_pp) finish_pp_index(ctx, d, s, d.compute, true);   // scan + scatter (one sync for the entry count)
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_stop, d.compute));
                 CUDA_CHECK(cudaStreamSynchronize(d.copy_in));
                 CUDA_CHECK(cudaStreamSynchronize(d.compute));
@@ -1309,6 +1823,48 @@ int64_t dg_plan_ctx(dg_ctx* ctx, int mode, uint64_t* row_begin, uint64_t* row_en
     return rc != DG_OK ? rc : count;
 }
 
+int dg_square_begin(dg_ctx* ctx, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
+                    dg_sink_fn sink, void* user) {
+    const int rc = guarded(ctx, [&] { sq_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user); });
+    if (rc != DG_OK && ctx && !ctx->streaming && !ctx->sq_open && rc != DG_ERR_STATE) sq_abort(ctx);
+    return rc;
+}
+
+int dg_square_next(dg_ctx* ctx, uint64_t* lo, uint64_t* hi) {
+    return guarded(ctx, [&] {
+        if (!ctx->sq_open) fail(DG_ERR_STATE, "no dg_square session is open");
+        if (!lo || !hi) fail(DG_ERR_INVALID_ARG, "lo / hi is NULL");
+        if (ctx->sq_pushed < ctx->sq_chunks.size()) { *lo = ctx->sq_chunks[ctx->sq_pushed].lo; *hi = ctx->sq_chunks[ctx->sq_pushed].hi; }
+        else { *lo = 0; *hi = 0; }
+    });
+}
+
+int dg_square_push(dg_ctx* ctx, const uint8_t* codes, int src_device, uint64_t lo, uint64_t hi) {
+    const int rc = guarded(ctx, [&] { sq_push(ctx, codes, src_device, lo, hi); });
+    if (rc != DG_OK && ctx && ctx->sq_open) sq_abort(ctx);
+    return rc;
+}
+
+int dg_square_end(dg_ctx* ctx) {
+    const int rc = guarded(ctx, [&] { sq_end(ctx); });
+    if (rc != DG_OK && ctx && ctx->sq_open) sq_abort(ctx);
+    return rc;
+}
+
+int dg_run_square_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_kind, const uint64_t* acgt_counts,
+                       uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user) {
+    if (ctx && !codes) { ctx->err = "codes is NULL"; return DG_ERR_INVALID_ARG; }
+    int rc = dg_square_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user);
+    if (rc != DG_OK) return rc;
+    for (;;) {
+        uint64_t lo = 0, hi = 0;
+        if ((rc = dg_square_next(ctx, &lo, &hi)) != DG_OK) return rc;
+        if (hi == lo) break;
+        if ((rc = dg_square_push(ctx, codes + lo * ctx->width, -1, lo, hi)) != DG_OK) return rc;
+    }
+    return dg_square_end(ctx);
+}
+
 int dg_stream_begin(dg_ctx* ctx, dg_sink_fn sink, void* user, uint64_t max_batch) {
     return guarded(ctx, [&] { stream_begin(ctx, sink, user, max_batch); });
 }
@@ -1360,6 +1916,9 @@ int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
         if (which_a < 0 || which_a > 1 || which_b < 0 || which_b > 1 || !out) fail(DG_ERR_INVALID_ARG, "bad arguments");
         Device& d = ctx->devs[0];
         CUDA_CHECK(cudaSetDevice(d.id));
+        if (ctx->streaming || ctx->sq_open) fail(DG_ERR_STATE, "a session is open");
+        ensure_pp_index(ctx, d, d.set[which_a]);
+        ensure_pp_index(ctx, d, d.set[which_b]);
         const PlaneSet& A = d.set[which_a];
         const PlaneSet& B = d.set[which_b];
         if (A.n == 0 || B.n == 0) fail(DG_ERR_STATE, "alignment not loaded");

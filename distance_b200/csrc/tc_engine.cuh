@@ -207,6 +207,11 @@ struct PackI8Params {
     uint8_t plane_id[MAX_PLANES];
     unsigned long long* invalid;  // min over ((seq0 + record) << 32 | site) of invalid bytes; or NULL
     uint64_t seq0;                // global index of record 0 of this chunk
+    // partial ambiguity codes (R Y M W S K V H D B) met while packing, for the both-partial repair index; or NULL:
+    uint32_t* pp_site_cnt;        // [width] += 1 per partial code at that site
+    uint64_t* pp_hits;            // unsorted entries (site << 36 | record << 4 | possibility nibble) ...
+    uint32_t* pp_hit_count;       // ... appended at atomicAdd(pp_hit_count, 1) while that is < pp_hit_cap
+    uint32_t pp_hit_cap;
 };
 
 constexpr uint32_t M1 = 0x01010101u;
@@ -368,6 +373,24 @@ __global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
                 if (seq < p.n && s0 + 16 * h < p.width) {
                     uint32_t raw[4];
                     load_codes16(p, row, seq, s0 + 16 * h, lut, wh, raw);
+                    if (p.pp_site_cnt) {
+                        // partial code <=> "known" bit clear and possibility nibble != 1111 (0.1 % of real data: rare path)
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t x = wh[k];
+                            const uint32_t allf = x & (x >> 1) & (x >> 2) & (x >> 3) & 0x10101010u;
+                            uint32_t m = ((~x & 0x08080808u) << 1) & ~allf;
+                            while (m) {
+                                const int j = (__ffs(m) - 1) >> 3;
+                                m &= m - 1;
+                                const uint64_t site = s0 + 16 * h + 4 * k + j;
+                                atomicAdd(p.pp_site_cnt + site, 1u);
+                                const uint32_t pos = atomicAdd(p.pp_hit_count, 1u);
+                                if (pos < p.pp_hit_cap)
+                                    p.pp_hits[pos] = (site << 36) | ((p.seq0 + seq) << 4) | (uint64_t)((x >> (8 * j + 4)) & 15u);
+                            }
+                        }
+                    }
                     if (p.acgt && p.count_upper_ascii) {   // the streamed tn93 records count raw upper-case letters only
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
@@ -472,17 +495,62 @@ __global__ void pp_scan_kernel(const uint32_t* site_cnt, uint64_t width, uint32_
     uint32_t run = part[threadIdx.x];
     for (uint64_t i = b; i < e; i++) { site_off[i] = run; cursor[i] = run; run += site_cnt[i]; }
 }
-__global__ void pp_fill_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* cursor, uint64_t* entries) {
+// `codes` = the bytes of records rec0 .. rec0 + n - 1; entries carry the GLOBAL record index
+__global__ void pp_fill_kernel(const uint8_t* codes, uint64_t n, uint64_t width, int ascii, uint32_t* cursor, uint64_t* entries,
+                               uint64_t rec0 = 0) {
     const uint64_t total = n * width;
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
         uint32_t c = codes[u];
         if (ascii) c = c_ascii_lut[c];
         if (is_partial(c)) {
-            const uint64_t site = u % width, rec = u / width;
+            const uint64_t site = u % width, rec = rec0 + u / width;
             const uint32_t pos = atomicAdd(cursor + site, 1u);
             entries[pos] = (site << 36) | (rec << 4) | (uint64_t)(c >> 4);
         }
     }
+}
+
+// hits[begin, end) (unsorted, written by pack_ops_kernel) -> entries grouped by site through the per-site cursor
+__global__ void pp_scatter_kernel(const uint64_t* hits, uint32_t begin, uint32_t end, uint32_t* cursor, uint64_t* entries) {
+    for (uint32_t i = begin + blockIdx.x * blockDim.x + threadIdx.x; i < end; i += gridDim.x * blockDim.x) {
+        const uint64_t h = hits[i];
+        entries[atomicAdd(cursor + (h >> 36), 1u)] = h;
+    }
+}
+
+// ---- chunked index of the pipelined all-vs-all session (dg_square_*) ------------------------------------------
+// Records arrive in chunks (highest records first); chunk g gets its own per-site offsets off[g][0 .. width] into
+// ONE shared entry buffer: off[g][s] = base_g + (exclusive scan of chunk g's site counts), base_g = the entries of
+// all earlier chunks (*total, the running count).  The row doubles as the fill cursor: the scan stores
+// off[0] = base_g and off[1 + s] = start of site s; pp_fill_kernel (cursor = off + 1) advances off[1 + s] to the
+// END of site s = the start of site s + 1, which leaves exactly the width + 1 offsets.
+// *work = sum over sites of (count over every chunk so far)^2: the cost of the both-partial repair
+// (decides the engine like PpIndex::pair_work).  site_cnt = this chunk's counts, cum_cnt = all chunks so far.
+__global__ void pp_scan_chunk_kernel(const uint32_t* site_cnt, uint32_t* cum_cnt, uint64_t width, uint32_t* off,
+                                     uint32_t* total, double* work) {
+    __shared__ uint32_t part[1024];
+    __shared__ double wpart[1024];
+    const uint64_t per = (width + 1023) / 1024;
+    const uint64_t b = min(width, threadIdx.x * per), e = min(width, b + per);
+    uint32_t s = 0; double w = 0;
+    for (uint64_t i = b; i < e; i++) {
+        s += site_cnt[i];
+        const uint32_t cc = cum_cnt[i] + site_cnt[i];
+        cum_cnt[i] = cc;
+        w += (double)cc * cc;
+    }
+    part[threadIdx.x] = s; wpart[threadIdx.x] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = *total; double tw = 0;
+        off[0] = run;
+        for (int i = 0; i < 1024; i++) { const uint32_t t = part[i]; part[i] = run; run += t; tw += wpart[i]; }
+        *total = run;
+        *work = tw;
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; i++) { off[1 + i] = run; run += site_cnt[i]; }
 }
 
 // DIFF is computed as sum_b U_b(q) V_b(t) = 3 [Sq, St disjoint] whenever at least one code is a known base or
@@ -522,6 +590,35 @@ __global__ void pp_correct_kernel(PpCorrParams p) {
         const uint32_t row = (uint32_t)((ea >> 4) & 0xFFFFFFFFull);
         if (row < p.row0 || row >= p.row_end) continue;
         pp_fix_row(p, row, (uint32_t)(ea >> 36), (uint32_t)(ea & 15));
+    }
+}
+// Session variant: the row entries are entries[a_begin, a_end) (the chunks that hold the panel's rows) and the column
+// side is the list of chunk indexes 0 .. n_chunks-1 (offsets off + g * off_stride) over the same entry buffer.
+struct PpChunkParams {
+    const uint64_t* entries;
+    const uint32_t* off; uint32_t off_stride, n_chunks;
+    uint32_t a_begin, a_end;
+    uint32_t row0, row_end;
+    uint64_t n_total, out_base;
+    int* out;
+};
+__global__ void pp_correct_chunks_kernel(PpChunkParams p) {
+    for (uint32_t e = p.a_begin + blockIdx.x * blockDim.x + threadIdx.x; e < p.a_end; e += gridDim.x * blockDim.x) {
+        const uint64_t ea = p.entries[e];
+        const uint32_t row = (uint32_t)((ea >> 4) & 0xFFFFFFFFull);
+        if (row < p.row0 || row >= p.row_end) continue;
+        const uint32_t site = (uint32_t)(ea >> 36), ma = (uint32_t)(ea & 15);
+        const uint64_t row_base = (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base;
+        for (uint32_t g = 0; g < p.n_chunks; g++) {
+            const uint32_t* off = p.off + (uint64_t)g * p.off_stride;
+            for (uint32_t k = off[site]; k < off[site + 1]; k++) {
+                const uint64_t eb = p.entries[k];
+                const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
+                if (col <= row) continue;
+                const int c = pp_corr(ma, (uint32_t)(eb & 15));
+                if (c) atomicAdd(p.out + row_base + (col - row - 1), c);
+            }
+        }
     }
 }
 // rows found by scanning their V planes (stream batches have no index): a site holds a partial code iff

@@ -126,6 +126,11 @@ typedef struct dg_ctx dg_ctx;
 #define DG_OPT_RESULT_U16 5  /* 0/1: deliver n / n_high panels as uint16_t (DG_RESULT_U16).  A count never exceeds
                                 the width, so this is lossless for width <= 65535 (else DG_ERR_INVALID_ARG). */
 
+#define DG_OPT_PIPE_PANELS 6 /* dg_square_* sessions: how many result panels (per part) the triangle is cut into
+                                (default 24; smaller panels start the D2H stream earlier, larger ones fill the SMs better) */
+#define DG_OPT_PIPE_CHUNK_BYTES 7 /* dg_square_* sessions: target bytes of one upload chunk (0 = automatic:
+                                     max(24 MiB, alignment bytes / 40)); chunks are whole multiples of 128 records */
+
 typedef struct {
     double pack_ms;       /* pack_planes kernels, CUDA events on the launching stream */
     double count_ms;      /* count-tile kernels (incl. fused epilogue), CUDA events */
@@ -196,6 +201,36 @@ DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n
  * (uint16 panels hold twice the rows of uint32 ones).  Returns the number of panels or a negative DG_ERR_*. */
 DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
                            uint64_t cap);
+
+/* Pipelined all-vs-all (the same work as dg_load_resident + dg_run_part on alignment 0, overlapped): the caller
+ * hands the alignment over in chunks, HIGHEST records first.  Row i of the upper triangle (src/lib.rs:512-513)
+ * only needs the records j > i, so as soon as the records [lo, n) are on the device every result panel whose rows
+ * start at or above lo runs: the PCIe upload, packing + tiles and the D2H of finished panels overlap.
+ *   - dg_square_begin plans the session: this part's panels (panel k of the session's plan belongs to part
+ *     k % n_parts, as in dg_run_part) and the chunk sequence, which is the same for every part.
+ *   - dg_square_next returns the record range [*lo, *hi) the next dg_square_push must deliver (*lo == *hi: done).
+ *   - dg_square_push takes that chunk: `codes` points at the first byte of record lo; src_device < 0 = host memory
+ *     (pinned memory makes the copy asynchronous), otherwise the CUDA device that holds it (peer copy, e.g. a chunk
+ *     another rank uploaded and broadcast over NVLink).  Copies are asynchronous: a pinned or device buffer must
+ *     stay untouched until DG_SQUARE_LOOKAHEAD further pushes, or dg_square_end, have returned (so a staging ring of
+ *     DG_SQUARE_LOOKAHEAD + 1 chunk buffers is enough); pageable host memory may be reused at once.
+ *   - the sink runs inside push / end calls, serially, once per panel, in COMPLETION order (descending rows), not
+ *     in the reference's output order: each dg_panel says which rows it holds, so a consumer that needs the order of
+ *     src/lib.rs:616-637 places panels by row_begin (or uses dg_load_resident + dg_run_square, which deliver in order).
+ *   - when dg_square_end returns, alignment 0 is resident exactly as after dg_load_resident.
+ * acgt_counts as in dg_load_resident.  One device per context.  Any failing call closes the session.  An invalid
+ * nucleotide byte fails the push / end call that notices it (DG_ERR_INVALID_CODE) before any panel that depends on
+ * it is delivered; dg_invalid_site then names the lowest (record, site) among the chunks seen so far, which need
+ * not be the first in file order. */
+#define DG_SQUARE_LOOKAHEAD 3
+DG_API int dg_square_begin(dg_ctx *ctx, uint64_t n, int input_kind, const uint64_t *acgt_counts, uint32_t part,
+                           uint32_t n_parts, dg_sink_fn sink, void *user);
+DG_API int dg_square_next(dg_ctx *ctx, uint64_t *lo, uint64_t *hi);
+DG_API int dg_square_push(dg_ctx *ctx, const uint8_t *codes, int src_device, uint64_t lo, uint64_t hi);
+DG_API int dg_square_end(dg_ctx *ctx);
+/* The whole session for an alignment in host memory: begin, push every chunk from `codes` (n x width), end. */
+DG_API int dg_run_square_host(dg_ctx *ctx, const uint8_t *codes, uint64_t n, int input_kind,
+                              const uint64_t *acgt_counts, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void *user);
 
 /* -s streaming (replaces stream(), src/lib.rs:269-365): alignment 0 is resident, batches of the
  * streamed alignment are pushed in file order.  Batches are staged through double-buffered pinned
