@@ -228,40 +228,84 @@ def run_ours(args):
     count_launch_ms = tm["count_ms"] / max(tm["count_launches"], 1)
 
     # ---- e2e: host buffers through the C ABI ----------------------------------------------------
-    if world > 1:
-        # N ranks: every code byte crosses PCIe ONCE (rank r uploads records [r*per, (r+1)*per) from pinned host
-        # memory), the ranks exchange their slices over NVLink (NCCL all-gather) and each library instance takes the
-        # gathered device buffer (dg_load_resident_device).  N = 1 keeps the plain host-pointer call.
-        import torch
-        per = (n + world - 1) // world
-        lo, hi = rank * per, min(n, rank * per + per)
-        host_slice = torch.full((per, WIDTH), 240, dtype=torch.uint8).pin_memory()
-        host_slice[:hi - lo] = torch.from_numpy(np.ascontiguousarray(codes[lo:hi]))
-        dev_slice = torch.empty((per, WIDTH), dtype=torch.uint8, device=d.device)
-        gathered = torch.empty((world * per, WIDTH), dtype=torch.uint8, device=d.device)
+    # The pipelined session (dg_square_*): chunks of the alignment go up highest records first, so the PCIe upload,
+    # packing + tiles and the D2H of finished panels overlap; the sink reads every panel in pinned host memory.
+    #   N = 1 : dg_run_square_host on the pinned host alignment.
+    #   N > 1 : every code byte crosses PCIe ONCE: for each chunk every rank uploads 1/N of it from pinned host
+    #           memory, the ranks all-gather the chunk over NVLink (NCCL) and hand the gathered device buffer to
+    #           dg_square_push together with the CUDA event that marks it ready (no host synchronisation).
+    import ctypes as C
+    e2e_state = {"n": 0, "acc": 0}
 
-        def load_step():
-            dev_slice.copy_(host_slice, non_blocking=True)
-            d.all_gather_into(gathered, dev_slice)
-            torch.cuda.synchronize()
-            eng.load_device(0, gathered.data_ptr(), d.local_rank, n)
+    def e2e_sink(user, pp):
+        p = pp.contents
+        e2e_state["n"] += int(p.n_results)
+        if p.n_results:
+            e2e_state["acc"] ^= C.c_uint32.from_address(p.data).value
+        return 0
+
+    e2e_cb = api.SINK_FN(e2e_sink)
+    if world > 1:
+        import torch
+        import torch.distributed as td
+        host_codes = torch.from_numpy(codes).pin_memory()
+        RING = api.DG_SQUARE_LOOKAHEAD + 1
+        side = [torch.cuda.Stream(device=d.device) for _ in range(2)]
+        ring_piece, ring_gath, ring_ev = None, None, [torch.cuda.Event() for _ in range(RING)]
+
+        def e2e_step():
+            nonlocal ring_piece, ring_gath
+            e2e_state["n"] = 0
+            eng.square_begin(n, e2e_cb, rank, world)
+            g = 0
+            while True:
+                lo, hi = eng.square_next()
+                if hi == lo:
+                    break
+                nr = hi - lo
+                per = (nr + world - 1) // world
+                if ring_piece is None or ring_piece[0].shape[0] < per:
+                    ring_piece = [torch.empty((per, WIDTH), dtype=torch.uint8, device=d.device) for _ in range(RING)]
+                    ring_gath = [torch.empty((per * world, WIDTH), dtype=torch.uint8, device=d.device) for _ in range(RING)]
+                k = g % RING
+                r0, r1 = min(hi, lo + rank * per), min(hi, lo + (rank + 1) * per)
+                with torch.cuda.stream(side[g % 2]):
+                    if r1 > r0:
+                        ring_piece[k][:r1 - r0].copy_(host_codes[r0:r1], non_blocking=True)
+                    td.all_gather_into_tensor(ring_gath[k][:per * world], ring_piece[k][:per])
+                    ring_ev[k].record()
+                eng.square_push(ring_gath[k].data_ptr(), d.local_rank, lo, hi, ring_ev[k].cuda_event)
+                g += 1
+            eng.square_end()
+            return e2e_state["n"]
     else:
-        def load_step():
-            eng.load(0, pinned)                               # H2D from pinned host memory + pack
+        def e2e_step():
+            return eng.square_pipelined_discard(pinned, rank, world)
 
     for _ in range(2):
-        load_step()
-        eng.run_discard(api.DG_MODE_SQUARE, rank, world)
+        got = e2e_step()
+        # the session cuts the triangle into its own (smaller) panels, part k % world per rank: together they cover it once
+        assert int(d.sum(got)) == total_pairs, (got, total_pairs)
     sync_all()
     t0 = time.time()
     for _ in range(args.steps):
-        load_step()
-        got = eng.run_discard(api.DG_MODE_SQUARE, rank, world)  # tiles + D2H + sink reads each panel
-        assert got == my_pairs
+        e2e_step()
     sync_all()
     t1 = time.time()
     e2e_step_ms = d.max(1e3 * (t1 - t0) / args.steps)
     e2e_value = total_pairs / (e2e_step_ms * 1e-3)
+
+    # the in-order path (dg_load_resident, then dg_run_part: panels reach the sink in the reference's output order)
+    e2e_inorder_ms = None
+    if world == 1:
+        for _ in range(2):
+            eng.load(0, pinned); eng.run_discard(api.DG_MODE_SQUARE, rank, world)
+        t0i = time.time()
+        for _ in range(max(3, args.steps // 3)):
+            eng.load(0, pinned)
+            assert eng.run_discard(api.DG_MODE_SQUARE, rank, world) == my_pairs
+        e2e_inorder_ms = 1e3 * (time.time() - t0i) / max(3, args.steps // 3)
+        t1 = time.time()
     clocks = sampler.stop(t_wall0, t1)
 
     # ---- roofline of the dominant kernel (count_tile_kernel) ------------------------------------
@@ -376,8 +420,13 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (operand planes %.0f MB vs 126 MB L2)" % (n * 8 * 14976 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(n * WIDTH),
-                    "input_path": ("each rank uploads 1/N of the codes from pinned host memory, NCCL all-gather over NVLink, "
-                                   "dg_load_resident_device") if world > 1 else "dg_load_resident from pinned host memory", "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
+                    "input_path": ("pipelined session (dg_square_*): per chunk every rank uploads 1/N from pinned host memory, NCCL "
+                                   "all-gather over NVLink, dg_square_push(device buffer, ready event); panels in completion order")
+                    if world > 1 else "pipelined session (dg_run_square_host) from pinned host memory: upload, tiles and D2H overlap; "
+                                      "panels reach the sink in completion order (descending rows)",
+                    "in_order_ms_per_step": e2e_inorder_ms,
+                    "in_order_note": "dg_load_resident + dg_run_square: same bytes, panels in the reference's output order (no overlap of upload and tiles)",
+                    "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
                     "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
             "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}.get(engine_id, "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,

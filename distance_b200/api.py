@@ -20,6 +20,7 @@ DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
 DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
 DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16, DG_OPT_PIPE_PANELS = 1, 2, 3, 4, 5, 6
 DG_OPT_PIPE_CHUNK_BYTES = 7
+DG_SQUARE_LOOKAHEAD = 3
 DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
           -4: "DG_ERR_INVALID_CODE", -5: "DG_ERR_SINK", -6: "DG_ERR_NOMEM"}
@@ -110,7 +111,7 @@ def load_library():
     L.dg_run_part.argtypes = [vp, i32, C.c_uint32, C.c_uint32, SINK_FN, vp, C.c_uint32]
     L.dg_square_begin.argtypes = [vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_square_next.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
-    L.dg_square_push.argtypes = [vp, vp, i32, u64, u64]
+    L.dg_square_push.argtypes = [vp, vp, i32, u64, u64, vp]
     L.dg_square_end.argtypes = [vp]
     L.dg_run_square_host.argtypes = [vp, vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
@@ -356,7 +357,7 @@ class Engine:
                     push(int(lo.value), int(hi.value))
                 else:
                     self._check(self.L.dg_square_push(self.h, C.c_void_p(codes.ctypes.data + lo.value * self.width), -1,
-                                                      lo.value, hi.value))
+                                                      lo.value, hi.value, None))
             self._check(self.L.dg_square_end(self.h))
         self._n[0] = n
         self.last_panels = panels
@@ -379,6 +380,24 @@ class Engine:
                                               part, n_parts, SINK_FN(sink), None))
         self._n[0] = n
         return state["n"]
+
+    def square_begin(self, n: int, sink, part: int = 0, n_parts: int = 1, input_kind: int = DG_INPUT_PARADIS):
+        """dg_square_begin with a raw SINK_FN; returns the chunk plan [(lo, hi)] by walking dg_square_next is not
+        possible without pushing, so callers use square_chunks() for the plan."""
+        self._check(self.L.dg_square_begin(self.h, n, input_kind, None, part, n_parts, sink, None))
+        self._n[0] = n
+
+    def square_next(self):
+        lo, hi = C.c_uint64(), C.c_uint64()
+        self._check(self.L.dg_square_next(self.h, C.byref(lo), C.byref(hi)))
+        return int(lo.value), int(hi.value)
+
+    def square_push(self, ptr: int, src_device: int, lo: int, hi: int, ready_event: int = 0):
+        self._check(self.L.dg_square_push(self.h, C.c_void_p(ptr), src_device, lo, hi,
+                                          C.c_void_p(ready_event) if ready_event else None))
+
+    def square_end(self):
+        self._check(self.L.dg_square_end(self.h))
 
     def stream(self, batches, input_kind: int = DG_INPUT_PARADIS, max_batch: int = 1 << 20, acgt_batches=None):
         """Stream an iterable of (n_b x width) uint8 arrays against alignment 0."""

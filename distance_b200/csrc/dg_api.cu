@@ -480,7 +480,8 @@ bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
 
 // One launch computes every accumulator of the family's schedule: work items = accumulators x tiles.
 void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                    int out_mode, void* out, uint64_t acc_stride, cudaStream_t st, Slot* ws = nullptr) {
+                    int out_mode, void* out, uint64_t acc_stride, cudaStream_t st, Slot* ws = nullptr,
+                    bool tiles_on_device = false) {
     const TcSchedule& sch = tc_schedule(c->fam);
     tc::TcParams tp{};
     tp.n_b = (uint32_t)B.n;
@@ -547,7 +548,13 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
                 }
         }
         if (n_live == 0) return;
-        CUDA_CHECK(cudaMemcpyAsync(ws->d_tiles, ws->h_tiles, (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
+        if (tiles_on_device) {   // sessions: no small H2D copy behind the bulk uploads on the copy engine
+            tc::build_tile_list_kernel<<<1, 1024, 0, st>>>(tp.gx, tp.gy, tc::RASTER_G, tp.row0, tp.row_end, rows_per_block,
+                                                          tp.col_block0, tp.tn, ws->d_tiles);
+            CUDA_CHECK(cudaGetLastError());
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(ws->d_tiles, ws->h_tiles, (size_t)n_live * 4, cudaMemcpyHostToDevice, st));
+        }
         tp.tile_list = ws->d_tiles; tp.n_live = n_live;
         live = n_live;
     }
@@ -1013,9 +1020,9 @@ void sq_launch_panel(dg_ctx* c, int k) {
     const uint32_t n_entries = c->sq_base[c->sq_pumped];   // entries of every chunk pumped so far
     const bool repair = c->sq_needs_pp && n_entries != 0;
     if (c->fam == FAM_SNP && !repair) {
-        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s);
+        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s, true);
     } else {
-        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s);
+        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s, true);
         if (repair) {
             // the panel's rows live in the chunks [ga0, ga1): chunks are descending, find those that overlap the rows
             size_t ga0 = c->sq_pumped, ga1 = 0;
@@ -1172,9 +1179,9 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
         if (d.h_sq_invalid) cudaFreeHost(d.h_sq_invalid);
         d.sq_off = nullptr; d.h_sq_total = nullptr; d.h_sq_work = nullptr; d.h_sq_invalid = nullptr; d.sq_off_chunks = 0;
         CUDA_CHECK(cudaMalloc(&d.sq_off, G * (size_t)(c->width + 1) * 4));
-        CUDA_CHECK(cudaHostAlloc(&d.h_sq_total, G * 4, cudaHostAllocDefault));
-        CUDA_CHECK(cudaHostAlloc(&d.h_sq_work, G * 8, cudaHostAllocDefault));
-        CUDA_CHECK(cudaHostAlloc(&d.h_sq_invalid, G * 8, cudaHostAllocDefault));
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_total, G * 4, cudaHostAllocMapped));   // written by kernels (see pp_scan_chunk_kernel)
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_work, G * 8, cudaHostAllocMapped));
+        CUDA_CHECK(cudaHostAlloc(&d.h_sq_invalid, G * 8, cudaHostAllocMapped));
         d.sq_off_chunks = G;
     }
     if (!d.sq_cum) CUDA_CHECK(cudaMalloc(&d.sq_cum, (size_t)c->width * 4));
@@ -1204,7 +1211,7 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
     c->sq_open = true;
 }
 
-void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t hi) {
+void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t hi, void* ready_event) {
     if (!c->sq_open) fail(DG_ERR_STATE, "no dg_square session is open");
     if (c->sq_pushed >= c->sq_chunks.size()) fail(DG_ERR_STATE, "every chunk of the session has been pushed");
     const auto ch = c->sq_chunks[c->sq_pushed];
@@ -1218,6 +1225,7 @@ void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t
     const size_t g = c->sq_pushed;
     const uint64_t nr = hi - lo;
     uint8_t* dst = S.codes + lo * c->width;
+    if (ready_event) CUDA_CHECK(cudaStreamWaitEvent(d.copy_in, (cudaEvent_t)ready_event, 0));
     if (src_dev < 0) {
         CUDA_CHECK(cudaMemcpyAsync(dst, codes, (size_t)nr * c->width, cudaMemcpyHostToDevice, d.copy_in));
         c->tm.h2d_bytes += nr * c->width;
@@ -1235,14 +1243,16 @@ void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t
                         d.d_invalid + 2, false, c->sq_needs_pp ? &d : nullptr);
         if (c->sq_needs_pp) {
             tc::pp_scan_chunk_kernel<<<1, 1024, 0, d.prep>>>(d.pp_cnt, d.sq_cum, c->width, d.sq_off + g * (size_t)(c->width + 1),
-                                                             d.sq_total, d.pp_work);
+                                                             d.sq_total, d.h_sq_total + g, d.h_sq_work + g, d.d_invalid + 2,
+                                                             d.h_sq_invalid + g);
             CUDA_CHECK(cudaGetLastError());
             c->tm.pack_launches++;
-            CUDA_CHECK(cudaMemcpyAsync(d.h_sq_total + g, d.sq_total, 4, cudaMemcpyDeviceToHost, d.prep));
-            CUDA_CHECK(cudaMemcpyAsync(d.h_sq_work + g, d.pp_work, 8, cudaMemcpyDeviceToHost, d.prep));
         }
     }
-    CUDA_CHECK(cudaMemcpyAsync(d.h_sq_invalid + g, d.d_invalid + 2, 8, cudaMemcpyDeviceToHost, d.prep));
+    if (!(c->sq_tc && c->sq_needs_pp)) {
+        tc::publish_invalid_kernel<<<1, 1, 0, d.prep>>>(d.d_invalid + 2, d.h_sq_invalid + g);
+        CUDA_CHECK(cudaGetLastError());
+    }
     CUDA_CHECK(cudaEventRecord(d.sq_ev[g], d.prep));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_prep[g], d.prep));
     c->sq_pushed = g + 1;
@@ -1839,8 +1849,8 @@ int dg_square_next(dg_ctx* ctx, uint64_t* lo, uint64_t* hi) {
     });
 }
 
-int dg_square_push(dg_ctx* ctx, const uint8_t* codes, int src_device, uint64_t lo, uint64_t hi) {
-    const int rc = guarded(ctx, [&] { sq_push(ctx, codes, src_device, lo, hi); });
+int dg_square_push(dg_ctx* ctx, const uint8_t* codes, int src_device, uint64_t lo, uint64_t hi, void* ready_event) {
+    const int rc = guarded(ctx, [&] { sq_push(ctx, codes, src_device, lo, hi, ready_event); });
     if (rc != DG_OK && ctx && ctx->sq_open) sq_abort(ctx);
     return rc;
 }
@@ -1860,7 +1870,7 @@ int dg_run_square_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_
         uint64_t lo = 0, hi = 0;
         if ((rc = dg_square_next(ctx, &lo, &hi)) != DG_OK) return rc;
         if (hi == lo) break;
-        if ((rc = dg_square_push(ctx, codes + lo * ctx->width, -1, lo, hi)) != DG_OK) return rc;
+        if ((rc = dg_square_push(ctx, codes + lo * ctx->width, -1, lo, hi, nullptr)) != DG_OK) return rc;
     }
     return dg_square_end(ctx);
 }

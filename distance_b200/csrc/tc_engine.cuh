@@ -526,8 +526,16 @@ __global__ void pp_scatter_kernel(const uint64_t* hits, uint32_t begin, uint32_t
 // END of site s = the start of site s + 1, which leaves exactly the width + 1 offsets.
 // *work = sum over sites of (count over every chunk so far)^2: the cost of the both-partial repair
 // (decides the engine like PpIndex::pair_work).  site_cnt = this chunk's counts, cum_cnt = all chunks so far.
+// h_total / h_work / h_inv point into MAPPED pinned host memory: the kernel publishes the running entry total, the
+// repair cost and the invalid-byte flag itself, because a tiny cudaMemcpyAsync would queue behind the bulk panel
+// copies on the D2H copy engine.
+__global__ void publish_invalid_kernel(const unsigned long long* d_inv, unsigned long long* h_inv) {
+    *h_inv = *d_inv;
+    __threadfence_system();
+}
 __global__ void pp_scan_chunk_kernel(const uint32_t* site_cnt, uint32_t* cum_cnt, uint64_t width, uint32_t* off,
-                                     uint32_t* total, double* work) {
+                                     uint32_t* total, uint32_t* h_total, double* h_work, const unsigned long long* d_inv,
+                                     unsigned long long* h_inv) {
     __shared__ uint32_t part[1024];
     __shared__ double wpart[1024];
     const uint64_t per = (width + 1023) / 1024;
@@ -546,7 +554,8 @@ __global__ void pp_scan_chunk_kernel(const uint32_t* site_cnt, uint32_t* cum_cnt
         off[0] = run;
         for (int i = 0; i < 1024; i++) { const uint32_t t = part[i]; part[i] = run; run += t; tw += wpart[i]; }
         *total = run;
-        *work = tw;
+        *h_total = run; *h_work = tw; *h_inv = *d_inv;
+        __threadfence_system();
     }
     __syncthreads();
     uint32_t run = part[threadIdx.x];
@@ -655,6 +664,38 @@ __global__ void pp_correct_scan_kernel(PpCorrParams p) {
             if (anyneg) pp_fix_row(p, row, g * SITES + k, ma);
         }
     }
+}
+
+// The live-tile list of an upper-triangle panel built on the device (same order as the host loop in
+// launch_tc_gemm: bands of `raster_g` row blocks, column-major inside a band), for launches that must not queue a
+// host-to-device copy behind bulk uploads.  One block; `n_live` (computed by the host) is only checked.
+__global__ void build_tile_list_kernel(uint32_t gx, uint32_t gy, uint32_t raster_g, uint32_t row0, uint32_t row_end,
+                                       uint32_t rows_per_block, uint32_t col_block0, uint32_t tn, uint32_t* tiles) {
+    __shared__ uint32_t part[1024];
+    const uint32_t total = gx * gy;
+    const uint32_t per = (total + blockDim.x - 1) / blockDim.x;
+    const uint32_t q0 = min(total, threadIdx.x * per), q1 = min(total, q0 + per);
+    auto live_code = [&](uint32_t q, uint32_t& code) {
+        const uint32_t band = q / (raster_g * gx), r = q - band * (raster_g * gx);
+        const uint32_t gb = min(raster_g, gy - band * raster_g);
+        const uint32_t bx = r / gb, by = band * raster_g + (r - bx * gb);
+        const uint64_t rowS0 = (uint64_t)row0 + (uint64_t)by * rows_per_block;
+        const uint64_t rowB0 = (uint64_t)(col_block0 + bx) * tn;
+        code = (by << 20) | bx;
+        return !(rowS0 >= row_end || rowB0 + tn <= rowS0 + 1);
+    };
+    uint32_t cnt = 0, code;
+    for (uint32_t q = q0; q < q1; q++) cnt += live_code(q, code) ? 1u : 0u;
+    part[threadIdx.x] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t t = part[i]; part[i] = run; run += t; }
+    }
+    __syncthreads();
+    uint32_t pos = part[threadIdx.x];
+    for (uint32_t q = q0; q < q1; q++)
+        if (live_code(q, code)) tiles[pos++] = code;
 }
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------

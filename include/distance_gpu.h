@@ -211,7 +211,9 @@ DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t 
  *   - dg_square_next returns the record range [*lo, *hi) the next dg_square_push must deliver (*lo == *hi: done).
  *   - dg_square_push takes that chunk: `codes` points at the first byte of record lo; src_device < 0 = host memory
  *     (pinned memory makes the copy asynchronous), otherwise the CUDA device that holds it (peer copy, e.g. a chunk
- *     another rank uploaded and broadcast over NVLink).  Copies are asynchronous: a pinned or device buffer must
+ *     another rank uploaded and broadcast over NVLink).  ready_event: NULL, or a cudaEvent_t of this process that
+ *     the copy must wait for (e.g. recorded after the collective that fills the buffer), so the caller never has to
+ *     block the host on its own stream.  Copies are asynchronous: a pinned or device buffer must
  *     stay untouched until DG_SQUARE_LOOKAHEAD further pushes, or dg_square_end, have returned (so a staging ring of
  *     DG_SQUARE_LOOKAHEAD + 1 chunk buffers is enough); pageable host memory may be reused at once.
  *   - the sink runs inside push / end calls, serially, once per panel, in COMPLETION order (descending rows), not
@@ -226,7 +228,8 @@ DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t 
 DG_API int dg_square_begin(dg_ctx *ctx, uint64_t n, int input_kind, const uint64_t *acgt_counts, uint32_t part,
                            uint32_t n_parts, dg_sink_fn sink, void *user);
 DG_API int dg_square_next(dg_ctx *ctx, uint64_t *lo, uint64_t *hi);
-DG_API int dg_square_push(dg_ctx *ctx, const uint8_t *codes, int src_device, uint64_t lo, uint64_t hi);
+DG_API int dg_square_push(dg_ctx *ctx, const uint8_t *codes, int src_device, uint64_t lo, uint64_t hi,
+                          void *ready_event);
 DG_API int dg_square_end(dg_ctx *ctx);
 /* The whole session for an alignment in host memory: begin, push every chunk from `codes` (n x width), end. */
 DG_API int dg_run_square_host(dg_ctx *ctx, const uint8_t *codes, uint64_t n, int input_kind,

@@ -131,7 +131,7 @@ def test_pipelined_invalid_byte_and_protocol_errors(dg):
         # a push that is not the chunk dg_square_next announced is refused and closes the session
         sink = api.SINK_FN(lambda u, p: 0)
         assert e.L.dg_square_begin(e.h, n, 0, None, 0, 1, sink, None) == 0
-        rc = e.L.dg_square_push(e.h, C.c_void_p(good.ctypes.data), -1, 0, 128)
+        rc = e.L.dg_square_push(e.h, C.c_void_p(good.ctypes.data), -1, 0, 128, None)
         assert rc == -1
         assert e.L.dg_square_end(e.h) == -3
         # no session open: push / next / end report DG_ERR_STATE

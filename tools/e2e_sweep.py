@@ -37,8 +37,8 @@ with dg.Engine(a.measure, synth.SC2_WIDTH) as e:
         assert e.run_discard() == pairs
     best, med = timed(classic, a.reps)
     print(json.dumps({"path": "in-order (load + run_square)", "ms_min": best, "ms_median": med, "pairs_per_s": pairs / med * 1e3}), flush=True)
-    for panels in (8, 16, 24, 32, 48, 64):
-        for chunk_mb in (0, 12, 48):
+    for panels in (12, 24, 32, 48):
+        for chunk_mb in (0, 16, 32):
             e.set_option(api.DG_OPT_PIPE_PANELS, panels)
             e.set_option(api.DG_OPT_PIPE_CHUNK_BYTES, chunk_mb << 20)
 
