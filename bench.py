@@ -31,6 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT = sys.stdout
 MEASURE = "n_high"
 BASE_N = 20000
 WIDTH = 29903
@@ -152,7 +153,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (C oracle), not the Rust binary: no Rust toolchain in this image",
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     return 0
 
 
@@ -431,13 +432,19 @@ def run_ours(args):
             "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}.get(engine_id, "?"),
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), file=OUT, flush=True)
     eng.close()
     d.close()
     return 0
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner under torchrun) are sent to
+    # stderr, and the line goes out through a private duplicate of the original stdout.
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
