@@ -203,6 +203,16 @@ def run_ours(args):
     def sync_all():
         d.barrier()
 
+    # ---- pack kernel alone (roofline_pack): a few steps with the packing serialised in front of the tiles ------
+    eng.set_option(api.DG_OPT_REPACK_OVERLAP, 0)
+    eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
+    eng.reset_timings()
+    for _ in range(3):
+        eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
+    pack_ms_step = eng.timings()["pack_ms"] / 3
+    serial_step_ms = eng.timings()["run_ms"]
+    eng.set_option(api.DG_OPT_REPACK_OVERLAP, 0 if args.no_repack_overlap else 1)
+
     # ---- warm-up ------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
@@ -384,7 +394,6 @@ def run_ours(args):
     else:
         roofline = roofline_lop3
     hbm = measured.get("hbm_gbs")
-    pack_ms_step = tm["pack_ms"] / args.steps
     if engine_id == 3:
         pack_bytes = n * WIDTH + n * 8 * math.ceil(WIDTH / 256) * 128  # read 1 B/site, write 8 E2M1 planes (U, V), 2 sites per byte
         pack_kernel = "pack_ops_kernel<FP4>"
@@ -396,7 +405,9 @@ def run_ours(args):
         pack_kernel = "pack_planes_kernel"
     roofline_pack = {"bound": "hbm", "kernel": pack_kernel, "achieved": pack_bytes / (pack_ms_step * 1e-3) / 1e9,
                      "peak": hbm, "unit": "GB/s", "frac": (pack_bytes / (pack_ms_step * 1e-3) / 1e9 / hbm) if hbm else None,
-                     "ms": pack_ms_step}
+                     "ms": pack_ms_step,
+                     "note": "timed alone (DG_OPT_REPACK_OVERLAP=0: %.3f ms per step with the packing serialised in front of the tiles); in the "
+                             "timed steps the packing of the next panel's records overlaps the tiles of the current one" % serial_step_ms}
 
     line = None
     if rank == 0:
@@ -458,6 +469,7 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05 int8, 3 tcgen05 fp4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-repack-overlap", action="store_true", help="pack every operand plane before the first tile (DG_OPT_REPACK_OVERLAP=0)")
     ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
     ap.add_argument("--measure", default="n_high", choices=sorted(OPS_PER_PAIR_SITE),
                     help="default n_high = BASELINE config 2 (the driver's workload); jc69 + --n 100000 = config 5")

@@ -20,6 +20,7 @@ DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
 DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
 DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16, DG_OPT_PIPE_PANELS = 1, 2, 3, 4, 5, 6
 DG_OPT_PIPE_CHUNK_BYTES = 7
+DG_OPT_REPACK_OVERLAP = 8
 DG_SQUARE_LOOKAHEAD = 3
 DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",

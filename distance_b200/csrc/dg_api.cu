@@ -232,6 +232,7 @@ struct dg_ctx {
     double sq_t0 = 0;
     int pipe_panels = 24;              // DG_OPT_PIPE_PANELS
     uint64_t pipe_chunk_bytes = 0;     // DG_OPT_PIPE_CHUNK_BYTES (0 = automatic)
+    bool repack_overlap = true;        // DG_OPT_REPACK_OVERLAP
     bool sq_trace = false;
     std::vector<int> sq_trace_panel;   // panel index of the n-th launch
 
@@ -788,7 +789,7 @@ void ensure_lop3(dg_ctx* c, Device& d, PlaneSet& s) {
 
 // ---- square / rect runs ------------------------------------------------------------------------
 void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc_run, dg_sink_fn sink, void* user,
-                    bool device_only);
+                    bool device_only, bool repack_descending = false);
 void ensure_pp_index(dg_ctx* c, Device& d, PlaneSet& s);
 
 void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user,
@@ -817,7 +818,13 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     if (!tc_run)
         for (auto& d : c->devs)
             for (int w = 0; w <= wb; w++) ensure_lop3(c, d, d.set[w]);
-    if (flags & DG_RUN_REPACK) {  // re-run the operand packing of the engine in use from the resident codes
+    const bool overlap_repack = (flags & DG_RUN_REPACK) && device_only && tc_run && mode == DG_MODE_SQUARE && c->repack_overlap;
+    if (overlap_repack) {
+        for (auto& d : c->devs) {
+            CUDA_CHECK(cudaSetDevice(d.id));
+            CUDA_CHECK(cudaStreamWaitEvent(d.prep, d.run_start, 0));
+        }
+    } else if (flags & DG_RUN_REPACK) {  // re-run the operand packing of the engine in use from the resident codes
         for (auto& d : c->devs) {
             CUDA_CHECK(cudaSetDevice(d.id));
             for (int w = 0; w <= wb; w++) {
@@ -841,7 +848,8 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     std::vector<Panel> mine;
     for (size_t k = 0; k < all.size(); k++)
         if (k % n_parts == part) mine.push_back(all[k]);
-    run_panel_list(c, mode, mine, tc_run, sink, user, device_only);
+    if (overlap_repack) std::reverse(mine.begin(), mine.end());
+    run_panel_list(c, mode, mine, tc_run, sink, user, device_only, overlap_repack);
     c->tm.run_ms = 0;
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
@@ -858,9 +866,14 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
 
 // The panels of `mine` in order: panel k on device k % ndev, two ring slots per device (the D2H of a panel and
 // its sink call overlap the tiles of the next ones); the sink sees the panels serially, in list order.
+// repack_descending (kernel-only square runs with DG_RUN_REPACK): `mine` is in DESCENDING row order and the operand
+// planes are re-packed on the way: before a panel starts, the records from its first row up to what is already packed
+// are packed on the high-priority prep stream, so the HBM-bound packing of the next panel's rows overlaps the
+// tensor-bound tiles of this one (a panel needs the records at or above its first row only).
 void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc_run, dg_sink_fn sink, void* user,
-                    bool device_only) {
+                    bool device_only, bool repack_descending) {
     const int wb = mode == DG_MODE_SQUARE ? 0 : 1;
+    std::vector<uint64_t> packed_lo(c->devs.size(), c->devs[0].set[0].n);
     const int ndev = (int)c->devs.size();
     const PlaneSet& A0 = c->devs[0].set[0];
     const PlaneSet& B0 = c->devs[0].set[wb];
@@ -907,6 +920,17 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
             Slot& s = d.slot[si];
             CUDA_CHECK(cudaSetDevice(d.id));
             const Panel& p = mine[k];
+            if (repack_descending) {
+                uint64_t& lo = packed_lo[k % ndev];
+                if (p.row0 < lo) {
+                    PlaneSet& ps = d.set[0];
+                    enqueue_tc_pack(c, ps, ps.codes, lo - p.row0, ps.input_kind, !ps.acgt_from_host && c->fam == FAM_TN93, d.prep,
+                                    p.row0);
+                    CUDA_CHECK(cudaEventRecord(d.sq_ready, d.prep));
+                    lo = p.row0;
+                }
+                CUDA_CHECK(cudaStreamWaitEvent(d.cs(si), d.sq_ready, 0));
+            }
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
             if (tc_run) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si), false, &s);
             else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
@@ -1186,13 +1210,6 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
     }
     if (!d.sq_cum) CUDA_CHECK(cudaMalloc(&d.sq_cum, (size_t)c->width * 4));
     if (!d.sq_total) CUDA_CHECK(cudaMalloc(&d.sq_total, 4));
-    if (!d.sq_ready) CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ready, cudaEventDisableTiming));
-    if (!d.prep) {
-        int lo_pri = 0, hi_pri = 0;
-        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&d.prep, cudaStreamNonBlocking, hi_pri));
-        CUDA_CHECK(cudaStreamCreateWithPriority(&d.fill, cudaStreamNonBlocking, hi_pri));
-    }
     CUDA_CHECK(cudaMemsetAsync(d.sq_cum, 0, (size_t)c->width * 4, d.prep));
     CUDA_CHECK(cudaMemsetAsync(d.sq_total, 0, 4, d.prep));
     if (want_tc && c->sq_needs_pp) {
@@ -1605,6 +1622,13 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.compute2, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy_in, cudaStreamNonBlocking));
+            {
+                int lo_pri = 0, hi_pri = 0;
+                CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+                CUDA_CHECK(cudaStreamCreateWithPriority(&d.prep, cudaStreamNonBlocking, hi_pri));
+                CUDA_CHECK(cudaStreamCreateWithPriority(&d.fill, cudaStreamNonBlocking, hi_pri));
+                CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ready, cudaEventDisableTiming));
+            }
             for (auto& s : d.slot)
                 for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.in_ready, &s.p_start, &s.p_stop})
                     CUDA_CHECK(cudaEventCreate(e));
@@ -1667,6 +1691,7 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             if (value < 1 || value > 4096) fail(DG_ERR_INVALID_ARG, "pipe panels must be in [1, 4096]");
             ctx->pipe_panels = (int)value;
             break;
+        case DG_OPT_REPACK_OVERLAP: ctx->repack_overlap = value != 0; break;
         case DG_OPT_PIPE_CHUNK_BYTES:
             if (value < 0) fail(DG_ERR_INVALID_ARG, "chunk bytes must be >= 0");
             ctx->pipe_chunk_bytes = (uint64_t)value;

@@ -130,6 +130,9 @@ typedef struct dg_ctx dg_ctx;
                                 (default 24; smaller panels start the D2H stream earlier, larger ones fill the SMs better) */
 #define DG_OPT_PIPE_CHUNK_BYTES 7 /* dg_square_* sessions: target bytes of one upload chunk (0 = automatic:
                                      max(24 MiB, alignment bytes / 40)); chunks are whole multiples of 128 records */
+#define DG_OPT_REPACK_OVERLAP 8 /* 0/1 (default 1): kernel-only square runs with DG_RUN_REPACK re-pack the operand planes
+                                  chunk by chunk, overlapped with the tiles (panels then run in descending row order);
+                                  0 = pack everything first (dg_timings.pack_ms then times the pack kernel alone) */
 
 typedef struct {
     double pack_ms;       /* pack_planes kernels, CUDA events on the launching stream */

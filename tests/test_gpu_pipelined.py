@@ -163,3 +163,23 @@ def test_pipelined_sars_cov_2_width(dg, oracle):
         base = i * (2 * n - i - 1) // 2
         for j in rng.choice(np.arange(i + 1, n), min(8, n - 1 - i), replace=False):
             assert int(got[base + j - i - 1]) == oracle.pair_counts(codes[i], codes[j])["snp"]
+
+
+@pytest.mark.parametrize("measure", ["n_high", "raw", "tn93"])
+def test_overlapped_repack_keeps_the_operands(dg, oracle, measure):
+    """Kernel-only runs with DG_RUN_REPACK re-pack the planes chunk by chunk in descending panel order: afterwards
+    the resident operands must be what a plain load left (the next ordered run still matches the oracle)."""
+    from distance_b200 import api, synth
+    n, width = 2600, 200
+    rng = np.random.default_rng(17)
+    codes = synth.random_codes(rng, n, width, p_ambig=0.05)
+    want = oracle_run(oracle, measure, "square", codes)
+    with dg.Engine(measure, width) as e:
+        e.set_option(api.DG_OPT_PANEL_BYTES, 1 << 20)
+        e.set_option(api.DG_OPT_KEEP_CODES, 1)
+        e.load(0, codes)
+        for overlap in (1, 0, 1):
+            e.set_option(api.DG_OPT_REPACK_OVERLAP, overlap)
+            e.run_device_only(repack=True)
+            e.run_device_only(api.DG_MODE_SQUARE, 1, 3, repack=True)
+            check(measure, e.run_square(), want)
