@@ -1,8 +1,13 @@
 #include "fasta.hpp"
 
+#include <atomic>
 #include <cctype>
+#include <chrono>
 #include <cerrno>
 #include <cstring>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <thread>
 #include <unistd.h>
 
 namespace host {
@@ -98,9 +103,20 @@ void validate_record(const std::string& id, const uint8_t* seq, uint64_t len) {
 
 FastaReader::FastaReader(int fd, bool validate) : fd_(fd), buf_(8u << 20), validate_(validate) {}
 
+FastaReader::FastaReader(const char* data, size_t size, bool validate)
+    : fd_(-1), mem_(data), mem_size_(size), buf_(1u << 20), validate_(validate) {}
+
 bool FastaReader::fill() {
     if (eof_) return false;
     pos_ = end_ = 0;
+    if (fd_ < 0) {
+        const size_t n = std::min(buf_.size(), mem_size_ - mem_pos_);
+        if (n == 0) { eof_ = true; return false; }
+        std::memcpy(buf_.data(), mem_ + mem_pos_, n);
+        mem_pos_ += n;
+        end_ = n;
+        return true;
+    }
     for (;;) {
         ssize_t r = ::read(fd_, buf_.data(), buf_.size());
         if (r < 0) {
@@ -164,9 +180,204 @@ bool FastaReader::next(std::string& id, std::vector<uint8_t>& seq) {
     return true;
 }
 
-Alignment load_fasta(int fd) {
+namespace {
+
+// The whole input in memory.  Regular files: a huge-page backed buffer filled by parallel pread() calls (page-cache
+// copies scale with threads, where first-touch faults on an mmap of the file serialise); pipes / stdin: read to EOF.
+struct InputBytes {
+    const char* data = nullptr;
+    size_t size = 0;
+    void* big = nullptr;
+    std::vector<char> owned;
+    InputBytes(int fd, int threads) {
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0 && lseek(fd, 0, SEEK_CUR) == 0) {
+            const size_t bytes = ((size_t)st.st_size + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+            if (posix_memalign(&big, 2u << 20, bytes) != 0) throw std::bad_alloc();
+            madvise(big, bytes, MADV_HUGEPAGE);
+            const size_t total = (size_t)st.st_size;
+            int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+            T = (int)std::min<size_t>((size_t)std::min(T, 64), std::max<size_t>(1, total / (8u << 20)));
+            std::atomic<int> err{0};
+            std::atomic<size_t> got{0};
+            auto rd = [&](int t) {
+                size_t lo = total / T * t, hi = t == T - 1 ? total : total / T * (t + 1);
+                while (lo < hi) {
+                    ssize_t r = ::pread(fd, static_cast<char*>(big) + lo, std::min<size_t>(hi - lo, 64u << 20), (off_t)lo);
+                    if (r < 0) { if (errno == EINTR) continue; err.store(errno); return; }
+                    if (r == 0) break;   // the file shrank
+                    lo += (size_t)r;
+                    got += (size_t)r;
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; t++) th.emplace_back(rd, t);
+            rd(0);
+            for (auto& x : th) x.join();
+            if (err.load()) throw io_error_os(err.load());
+            data = static_cast<const char*>(big);
+            size = got.load() == total ? total : 0;
+            if (size == total) return;
+            std::free(big); big = nullptr;   // the file changed under us: fall through to the sequential read
+            lseek(fd, 0, SEEK_SET);
+        }
+        owned.resize(1u << 20);
+        size_t used = 0;
+        for (;;) {
+            if (used == owned.size()) owned.resize(owned.size() * 2);
+            ssize_t r = ::read(fd, owned.data() + used, owned.size() - used);
+            if (r < 0) {
+                if (errno == EINTR) continue;
+                throw io_error_os(errno);
+            }
+            if (r == 0) break;
+            used += (size_t)r;
+        }
+        data = owned.data(); size = used;
+    }
+    ~InputBytes() { if (big) std::free(big); }
+    InputBytes(const InputBytes&) = delete;
+    InputBytes& operator=(const InputBytes&) = delete;
+};
+
+inline bool is_space(unsigned char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+
+// One record starting at `p` (which points at '>'): header, then sequence lines up to the next line that starts with
+// '>' or `end`.  Calls line(ptr, trimmed_len) for every sequence line.  Returns the start of the next record (or end).
+template <typename F>
+inline const char* walk_record(const char* p, const char* end, const char*& id0, size_t& id_len, bool& has_desc, F&& line) {
+    const char* nl = static_cast<const char*>(std::memchr(p, '\n', (size_t)(end - p)));
+    const char* hend = nl ? nl : end;
+    const char* t = hend;
+    while (t > p && is_space((unsigned char)t[-1])) t--;
+    const char* q = p + 1;
+    while (q < t && !std::isspace((unsigned char)*q)) q++;
+    id0 = p + 1; id_len = (size_t)(q - (p + 1)); has_desc = q < t;
+    p = nl ? nl + 1 : end;
+    while (p < end && *p != '>') {
+        nl = static_cast<const char*>(std::memchr(p, '\n', (size_t)(end - p)));
+        const char* lend = nl ? nl : end;
+        const char* e = lend;
+        while (e > p && is_space((unsigned char)e[-1])) e--;
+        line(p, (size_t)(e - p));
+        p = nl ? nl + 1 : end;
+    }
+    return p;
+}
+
+// The parallel pass.  false = "not a clean alignment": the caller re-reads sequentially for the exact error / edge case.
+bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
+    if (size == 0 || data[0] != '>') return false;
+    const char* end = data + size;
+    // width = length of the first record
+    uint64_t width = 0;
+    {
+        const char* id0; size_t idl; bool desc;
+        walk_record(data, end, id0, idl, desc, [&](const char*, size_t n) { width += n; });
+        if (width == 0) return false;
+    }
+    int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
+    T = (int)std::min<size_t>((size_t)std::min(T, 64), std::max<size_t>(1, size / (4u << 20)));
+    // segment starts: the first '>' at a line start at or after size * t / T
+    std::vector<const char*> seg(T + 1, end);
+    seg[0] = data;
+    for (int t = 1; t < T; t++) {
+        const char* p = data + size / T * t;
+        const char* found = end;
+        while (p < end) {
+            const char* nl = static_cast<const char*>(std::memchr(p, '\n', (size_t)(end - p)));
+            if (!nl || nl + 1 >= end) break;
+            if (nl[1] == '>') { found = nl + 1; break; }
+            p = nl + 1;
+        }
+        seg[t] = found;
+    }
+    for (int t = 1; t <= T; t++) if (seg[t] < seg[t - 1]) seg[t] = seg[t - 1];
+    // pass 1: records per segment, every record exactly `width` long and with a non-empty id
+    std::vector<uint64_t> count(T, 0);
+    std::atomic<bool> clean{true};
+    auto pass1 = [&](int t) {
+        uint64_t n = 0;
+        const char* p = seg[t];
+        const char* e = seg[t + 1];
+        while (p < e && clean.load(std::memory_order_relaxed)) {
+            const char* id0; size_t idl; bool desc;
+            uint64_t len = 0;
+            p = walk_record(p, e, id0, idl, desc, [&](const char*, size_t k) { len += k; });
+            if (len != width || idl == 0) { clean.store(false); return; }
+            n++;
+        }
+        count[t] = n;
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(pass1, t);
+        pass1(0);
+        for (auto& x : th) x.join();
+    }
+    if (!clean.load()) return false;
+    std::vector<uint64_t> first(T + 1, 0);
+    for (int t = 0; t < T; t++) first[t + 1] = first[t] + count[t];
+    const uint64_t n = first[T];
+    if (n == 0) return false;
+    a.ids.assign(n, std::string());
+    a.width = width;
+    {   // uninitialised, 2 MB aligned, transparent huge pages requested: the pages are first touched by the threads below
+        void* mem = nullptr;
+        const size_t bytes = ((size_t)(n * width) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+        if (posix_memalign(&mem, 2u << 20, bytes) != 0) throw std::bad_alloc();
+        madvise(mem, bytes, MADV_HUGEPAGE);
+        a.fast_.reset(static_cast<uint8_t*>(mem));
+    }
+    uint8_t* dst = a.fast_.get();
+    // pass 2: ids, validation (encoding.rs:7-38) and the copy
+    auto pass2 = [&](int t) {
+        uint64_t r = first[t];
+        const char* p = seg[t];
+        const char* e = seg[t + 1];
+        while (p < e && clean.load(std::memory_order_relaxed)) {
+            const char* id0; size_t idl; bool desc;
+            uint8_t* out = dst + r * width;
+            unsigned bad = 0;
+            p = walk_record(p, e, id0, idl, desc, [&](const char* s, size_t k) {
+                for (size_t i = 0; i < k; i++) bad |= (unsigned)!g_valid.ok[(uint8_t)s[i]];
+                std::memcpy(out, s, k);
+                out += k;
+            });
+            if (bad) { clean.store(false); return; }
+            a.ids[r].assign(id0, idl);
+            r++;
+        }
+    };
+    {
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(pass2, t);
+        pass2(0);
+        for (auto& x : th) x.join();
+    }
+    if (!clean.load()) {
+        a = Alignment();
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+Alignment load_fasta(int fd, int threads) {
+    const bool trace = std::getenv("DG_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    InputBytes in(fd, threads);
+    const auto t1 = std::chrono::steady_clock::now();
     Alignment a;
-    FastaReader rd(fd);
+    const bool ok = parse_parallel(in.data, in.size, threads, a);
+    if (trace)
+        fprintf(stderr, "[load_fasta] %zu bytes: input %.3f s, parallel parse %.3f s (%s)\n", in.size,
+                std::chrono::duration<double>(t1 - t0).count(),
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count(), ok ? "ok" : "fell back");
+    if (ok) return a;
+    a = Alignment();
+    FastaReader rd(in.data, in.size);
     std::string id;
     bool first = true;
     for (;;) {

@@ -20,6 +20,8 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -37,15 +39,21 @@ DistanceError io_error_os(int err);                             // IOError(Os { 
 
 struct Alignment {
     std::vector<std::string> ids;
-    std::vector<uint8_t> seqs;  // n x width raw ASCII bytes (validated)
     uint64_t width = 0;
     uint64_t n() const { return ids.size(); }
+    const uint8_t* data() const { return fast_ ? fast_.get() : seqs.data(); }   // n x width raw ASCII bytes (validated)
+
+    std::vector<uint8_t> seqs;            // filled by the sequential reader ...
+    struct FreeDeleter { void operator()(uint8_t* p) const { std::free(p); } };
+    std::unique_ptr<uint8_t, FreeDeleter> fast_;   // ... or by the parallel loader (uninitialised, huge-page backed when possible)
 };
 
 class FastaReader {
 public:
     // validate = false: bytes are copied unchecked (stream mode checks the width first, fastaio.rs:246-254)
     explicit FastaReader(int fd, bool validate = true);
+    // the same over bytes already in memory
+    FastaReader(const char* data, size_t size, bool validate = true);
     // Reads the next record: id into `id`, sequence bytes APPENDED to `seq`.  Returns false at the
     // end of the input.  Throws DistanceError on malformed input or an invalid nucleotide.
     bool next(std::string& id, std::vector<uint8_t>& seq);
@@ -54,6 +62,8 @@ private:
     bool read_line();  // fills line_ (without the '\n'); false at EOF with nothing read
     bool fill();
     int fd_;
+    const char* mem_ = nullptr;   // in-memory source (fd_ < 0)
+    size_t mem_size_ = 0, mem_pos_ = 0;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
     bool eof_ = false;
@@ -62,8 +72,12 @@ private:
     bool validate_ = true;
 };
 
-// load_fasta (fastaio.rs:174-200)
-Alignment load_fasta(int fd);
+// load_fasta (fastaio.rs:174-200).  The whole input is taken into memory (mmap for regular files) and parsed by
+// `threads` workers (0 = all cores), each on a run of whole records: record boundaries are found, every record's
+// width is checked and its bytes are validated and copied straight to n x width.  Anything but a clean alignment
+// (a width mismatch, an invalid byte, a malformed or empty record ...) abandons the parallel pass and re-reads the
+// same bytes with the sequential FastaReader, which raises the reference's error for the first offence in file order.
+Alignment load_fasta(int fd, int threads = 0);
 // the cross-file width check of load_fastas (fastaio.rs:202-212)
 void check_same_width(const Alignment& a, const Alignment& b);
 

@@ -11,6 +11,8 @@
 //   DISTANCE_GPUS=<k> or DISTANCE_GPUS=0,2,3 chooses the devices (default: device 0); there is no flag
 //   for it so the CLI surface stays the reference's.
 #include <cerrno>
+#include <chrono>
+#include <cmath>
 #include <csignal>
 #include <cstdio>
 #include <cstdlib>
@@ -227,6 +229,9 @@ int run(const Args& a) {
             throw message_error("If you stream one file, you must also provide exactly one other file to be loaded");
         stream_fd = a.stream == "-" ? 0 : open_read(a.stream);  // lib.rs:200-207
     }
+    const bool trace = std::getenv("DG_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     std::vector<Alignment> loaded;
     for (size_t k = 0; k < fds.size(); k++) {
         loaded.push_back(load_fasta(fds[k]));
@@ -242,6 +247,7 @@ int run(const Args& a) {
                                       : std::max(1u, std::thread::hardware_concurrency());
 
     // ---- run (lib.rs:490-498) ----------------------------------------------------------------------
+    if (trace) fprintf(stderr, "[distance] %.3f s: inputs parsed\n", since());
     const uint64_t width = loaded[0].width;
     TsvWriter writer(out_fd, (int)std::min<uint64_t>(threads, 256));
     SinkState st{&writer, {}};
@@ -253,8 +259,9 @@ int run(const Args& a) {
     if (width <= 65535) dg_set_option(ctx, DG_OPT_RESULT_U16, 1);  // n / n_high: half the D2H bytes, same text
 
     for (size_t k = 0; k < loaded.size(); k++)
-        gpu_check(ctx, dg_load_resident(ctx, (int)k, loaded[k].seqs.data(), loaded[k].n(), DG_INPUT_ASCII, nullptr));
+        gpu_check(ctx, dg_load_resident(ctx, (int)k, loaded[k].data(), loaded[k].n(), DG_INPUT_ASCII, nullptr));
 
+    if (trace) fprintf(stderr, "[distance] %.3f s: GPU context up, alignments resident\n", since());
     writer.write_header();  // gather_write writes the header before anything arrives (lib.rs:613)
     if (stream_fd >= 0) {
         // stream() (lib.rs:269-365) + stream_fasta (fastaio.rs:215-286)
@@ -294,6 +301,7 @@ int run(const Args& a) {
     }
     writer.flush();
     if (out_fd != 1) ::close(out_fd);
+    if (trace) fprintf(stderr, "[distance] %.3f s: %llu lines written\n", since(), (unsigned long long)writer.lines());
     return 0;
 }
 
@@ -332,9 +340,143 @@ int selftest_format(uint64_t n) {
     return bad ? 1 : 0;
 }
 
+// Hidden developer check: the parallel loader against the sequential reader on the same file (ids, width and every
+// byte must agree; errors must be the same text), with the time each takes.  `distance --selftest-parse FILE [threads]`.
+int selftest_parse(const char* path, int threads) {
+    auto load = [&](bool parallel, Alignment& a, std::string& err, double& secs) {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) { err = "open failed"; return; }
+        const auto t0 = std::chrono::steady_clock::now();
+        try {
+            if (parallel) {
+                a = load_fasta(fd, threads);
+            } else {
+                FastaReader rd(fd);
+                std::string id;
+                bool first = true;
+                for (;;) {
+                    const size_t before = a.seqs.size();
+                    if (!rd.next(id, a.seqs)) break;
+                    const uint64_t len = a.seqs.size() - before;
+                    if (first) { a.width = len; first = false; }
+                    else if (len != a.width)
+                        throw message_error("Different length sequences in alignment(s): " + std::to_string(len) + " vs " + std::to_string(a.width));
+                    a.ids.push_back(id);
+                }
+                if (a.ids.empty()) throw message_error("Empty FASTA file");
+            }
+        } catch (const DistanceError& e) {
+            err = e.what();
+        }
+        secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        ::close(fd);
+    };
+    Alignment fast, slow;
+    std::string ef, es;
+    double tf = 0, ts = 0;
+    load(true, fast, ef, tf);
+    load(false, slow, es, ts);
+    bool same = ef == es;
+    if (same && ef.empty()) {
+        same = fast.ids == slow.ids && fast.width == slow.width &&
+               std::memcmp(fast.data(), slow.data(), (size_t)(fast.n() * fast.width)) == 0;
+    }
+    printf("selftest-parse: %s; records %llu width %llu; parallel loader %.3f s (%s), sequential reader %.3f s; error '%s'\n",
+           same ? "identical" : "MISMATCH", (unsigned long long)slow.n(), (unsigned long long)slow.width, tf,
+           fast.fast_ ? "parallel pass" : "fell back to the sequential reader", ts, es.c_str());
+    return same ? 0 : 1;
+}
+
+// Hidden developer check: the pooled TSV writer against a line-by-line restatement of gather_write (lib.rs:626-633)
+// for every mode and result kind, with short and long ids, several thread counts, panels larger than one chunk.
+// `distance --selftest-tsv`.
+int selftest_tsv() {
+    uint64_t x = 0x243F6A8885A308D3ull;
+    auto rnd = [&] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+    int bad = 0, cases = 0;
+    for (int threads : {1, 3, 8}) {
+        for (int mode : {DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM}) {
+            for (int kind : {DG_RESULT_U16, DG_RESULT_U32, DG_RESULT_F64}) {
+                const uint64_t n1 = 700 + rnd() % 200, n2 = mode == DG_MODE_SQUARE ? n1 : 300 + rnd() % 100;
+                std::vector<std::string> ids1, ids2;
+                auto make_id = [&](uint64_t i, const char* pre) {
+                    std::string s = pre + std::to_string(i);
+                    if (rnd() % 7 == 0) s += "|EPI_ISL_" + std::to_string(rnd() % 100000000) + "|a/very/long/identifier/2020-03-01";
+                    return s;
+                };
+                for (uint64_t i = 0; i < n1; i++) ids1.push_back(make_id(i, "s"));
+                for (uint64_t i = 0; i < n2; i++) ids2.push_back(make_id(i, "q"));
+                char path[] = "/tmp/dg_tsv_selftest_XXXXXX";
+                const int fd = mkstemp(path);
+                if (fd < 0) { perror("mkstemp"); return 1; }
+                std::string want = "sequence1\tsequence2\tdistance\n";
+                {
+                    TsvWriter w(fd, threads);
+                    w.set_ids(&ids1, mode == DG_MODE_SQUARE ? &ids1 : &ids2);
+                    w.write_header();
+                    // RECT: rows = ids1, cols = ids2.  STREAM: rows = streamed ids (ids2), cols = loaded ids (ids1).
+                    const uint64_t rows_total = mode == DG_MODE_SQUARE ? n1 - 1 : (mode == DG_MODE_RECT ? n1 : n2);
+                    const uint64_t cols = mode == DG_MODE_SQUARE ? n1 : (mode == DG_MODE_RECT ? n2 : n1);
+                    for (uint64_t r0 = 0; r0 < rows_total;) {
+                        const uint64_t r1 = std::min<uint64_t>(rows_total, r0 + 150 + rnd() % 300);
+                        uint64_t cnt = 0;
+                        for (uint64_t r = r0; r < r1; r++) cnt += mode == DG_MODE_SQUARE ? n1 - 1 - r : cols;
+                        std::vector<uint16_t> d16(cnt);
+                        std::vector<uint32_t> d32(cnt);
+                        std::vector<double> d64(cnt);
+                        for (uint64_t k = 0; k < cnt; k++) {
+                            const uint64_t v = rnd();
+                            d16[k] = (uint16_t)(v % 5 == 0 ? v >> 20 : v % 120);
+                            d32[k] = (uint32_t)(v % 11 == 0 ? v >> 33 : v % 70000);
+                            switch (v % 9) {
+                            case 0: d64[k] = 0.0; break;
+                            case 1: d64[k] = -0.0; break;
+                            case 2: d64[k] = std::nan(""); break;
+                            case 3: d64[k] = (v & 1024) ? INFINITY : -INFINITY; break;
+                            case 4: d64[k] = (double)(v >> 11) * 1e3; break;
+                            default: d64[k] = (double)(v >> 11) / 9007199254740992.0 * 2.0;
+                            }
+                        }
+                        dg_panel p{};
+                        p.mode = mode; p.result_kind = kind; p.row_begin = r0; p.row_end = r1; p.n_cols = cols; p.n_results = cnt;
+                        p.data = kind == DG_RESULT_U16 ? (const void*)d16.data() : (kind == DG_RESULT_U32 ? (const void*)d32.data() : (const void*)d64.data());
+                        w.write_panel(p);
+                        uint64_t k = 0;
+                        for (uint64_t r = r0; r < r1; r++)
+                            for (uint64_t c = mode == DG_MODE_SQUARE ? r + 1 : 0; c < cols; c++, k++) {
+                                if (mode == DG_MODE_SQUARE) want += ids1[r] + "\t" + ids1[c] + "\t";
+                                else if (mode == DG_MODE_RECT) want += ids1[r] + "\t" + ids2[c] + "\t";
+                                else want += ids1[c] + "\t" + ids2[r] + "\t";
+                                if (kind == DG_RESULT_U16) format_u32(d16[k], want);
+                                else if (kind == DG_RESULT_U32) format_u32(d32[k], want);
+                                else format_float12(d64[k], want);
+                                want += "\n";
+                            }
+                        r0 = r1;
+                    }
+                }
+                std::string got(want.size() + 16, '\0');
+                const ssize_t n = ::pread(fd, &got[0], got.size(), 0);
+                got.resize(n > 0 ? (size_t)n : 0);
+                ::close(fd);
+                ::unlink(path);
+                cases++;
+                if (got != want) {
+                    bad++;
+                    fprintf(stderr, "MISMATCH threads %d mode %d kind %d: %zu vs %zu bytes\n", threads, mode, kind, got.size(), want.size());
+                }
+            }
+        }
+    }
+    printf("selftest-tsv: %d cases, %d mismatches\n", cases, bad);
+    return bad ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
-    std::signal(SIGPIPE, SIG_IGN);  // a closed pipe shows up as EPIPE -> exit 0 (lib.rs:598-608)
+    std::signal(SIGPIPE, SIG_IGN);
+    if (argc == 2 && !strcmp(argv[1], "--selftest-tsv")) return selftest_tsv();  // a closed pipe shows up as EPIPE -> exit 0 (lib.rs:598-608)
     if (argc == 3 && !strcmp(argv[1], "--selftest-format")) return selftest_format(strtoull(argv[2], nullptr, 10));
+    if (argc >= 3 && !strcmp(argv[1], "--selftest-parse")) return selftest_parse(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     const Args a = parse_args(argc, argv);
     if (a.licenses) {  // main.rs:7-10
         printf("%s\n", kLicences);

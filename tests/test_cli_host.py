@@ -116,3 +116,67 @@ def test_not_fasta(tmp_path):  # rust-bio: "Expected > at record start."
 def test_licences_flag():
     rc, out, _ = run(["-l"])
     assert rc == 0 and "GNU LIBRARY GENERAL PUBLIC LICENSE" in out
+
+
+# ---------------------------------------------------------------------------------------------
+# the parallel FASTA loader against the sequential reader (same ids / bytes / error text)
+# ---------------------------------------------------------------------------------------------
+def _fasta(records, line=0, eol="\n", final_eol=True):
+    out = []
+    for rid, seq in records:
+        out.append(">" + rid)
+        if line:
+            out.extend(seq[i:i + line] for i in range(0, len(seq), line))
+        else:
+            out.append(seq)
+    return eol.join(out) + (eol if final_eol else "")
+
+
+def _selftest_parse(tmp_path, text, threads=4, binary=False):
+    f = tmp_path / "x.fa"
+    f.write_bytes(text if binary else text.encode())
+    rc, out, err = run(["--selftest-parse", str(f), str(threads)])
+    assert rc == 0 and "identical" in out, (out, err)
+    return out
+
+
+def test_parallel_loader_matches_sequential_reader(tmp_path):
+    import random
+    rnd = random.Random(7)
+    width = 5000
+    recs = [(f"seq{i} some description", "".join(rnd.choice("ACGTNacgtn-?RYKM") for _ in range(width))) for i in range(3000)]
+    big = _fasta(recs)                                   # 15 MB: several segments
+    assert "parallel pass" in _selftest_parse(tmp_path, big)
+    assert "parallel pass" in _selftest_parse(tmp_path, _fasta(recs, line=70))                 # multi-line
+    assert "parallel pass" in _selftest_parse(tmp_path, _fasta(recs, line=60, eol="\r\n"))     # CRLF
+    assert "parallel pass" in _selftest_parse(tmp_path, _fasta(recs, final_eol=False), threads=16)
+    assert "parallel pass" in _selftest_parse(tmp_path, _fasta(recs[:1]))
+
+
+def test_parallel_loader_falls_back_for_errors_and_odd_input(tmp_path):
+    import random
+    rnd = random.Random(9)
+    width = 4000
+    recs = [(f"r{i}", "".join(rnd.choice("ACGT") for _ in range(width))) for i in range(3000)]
+    bad = list(recs)
+    bad[2500] = ("r2500", recs[2500][1][:100] + "X" + recs[2500][1][101:])      # invalid nucleotide late in the file
+    out = _selftest_parse(tmp_path, _fasta(bad))
+    assert "fell back" in out and "Invalid nucleotide character in record 'r2500': 'X'" in out
+    short = list(recs)
+    short[1700] = ("r1700", recs[1700][1][:-1])                                   # width mismatch
+    out = _selftest_parse(tmp_path, _fasta(short))
+    assert "fell back" in out and "Different length sequences" in out
+    both = list(short)
+    both[900] = ("r900", "U" + recs[900][1][1:])                                  # the earlier offence wins
+    out = _selftest_parse(tmp_path, _fasta(both))
+    assert "Invalid nucleotide character in record 'r900': 'U'" in out
+    assert "fell back" in _selftest_parse(tmp_path, "junk\n" + _fasta(recs))        # no '>' at the start
+    assert "Empty FASTA file" in _selftest_parse(tmp_path, "")
+    _selftest_parse(tmp_path, _fasta(recs[:10]) + ">\n\n" + _fasta(recs[10:20]))    # an empty record ends the iteration
+    _selftest_parse(tmp_path, _fasta(recs[:50]) + "\n\n")                           # trailing blank lines
+    _selftest_parse(tmp_path, _fasta(recs[:5]).encode() + b"\xff\xfe", binary=True)  # non-ASCII tail
+
+
+def test_pooled_tsv_writer_matches_line_by_line_text():
+    rc, out, err = run(["--selftest-tsv"])
+    assert rc == 0 and "0 mismatches" in out, (out, err)
