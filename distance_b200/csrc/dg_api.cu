@@ -15,6 +15,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -361,6 +363,14 @@ struct TcSchedule {
     bool needs_pp;  // the n/n_high sum needs the both-partial correction
 };
 
+template <int FAM>
+bool planes_match(const TcSchedule& sch) {
+    if (sch.nplanes != tc::PackPlanes<FAM>::N) return false;
+    for (int i = 0; i < sch.nplanes; i++)
+        if (sch.plane_id[i] != tc::PackPlanes<FAM>::id(i)) return false;
+    return true;
+}
+
 const TcSchedule& tc_schedule(int fam) {
     using namespace tc;
     static const TcSchedule snp = {8, {P_UA, P_UG, P_UC, P_UT, P_VA, P_VG, P_VC, P_VT}, 1, {4},
@@ -371,6 +381,10 @@ const TcSchedule& tc_schedule(int fam) {
                                    {{0, 1}, {2, 3}, {4, 5}}, {{0, 1}, {2, 3}, {5, 4}}, false};
     static const TcSchedule tn93 = {5, {P_K, P_PURK, P_PYRK, P_W, P_Z}, 5, {1, 1, 1, 1, 1},
                                     {{0}, {1}, {2}, {3}, {4}}, {{0}, {1}, {2}, {3}, {4}}, false};
+    // pack_ops_kernel stores the planes of tc::PackPlanes<FAM> (compile-time): the schedules must list the same ones
+    static const bool ok = planes_match<FAM_SNP>(snp) && planes_match<FAM_RAW>(raw) && planes_match<FAM_K80>(k80) &&
+                           planes_match<FAM_TN93>(tn93);
+    if (!ok) fail(DG_ERR_STATE, "internal: tensor schedules and PackPlanes disagree");
     return fam == FAM_SNP ? snp : (fam == FAM_RAW ? raw : (fam == FAM_K80 ? k80 : tn93));
 }
 // first stored plane of the V operand (pp_correct_scan_kernel reads the partial codes back from it)
@@ -409,8 +423,21 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
-    if (s.tc_fp4) tc::pack_ops_kernel<true><<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
-    else tc::pack_ops_kernel<false><<<(unsigned)std::min<uint64_t>(n_pad, 148 * 8), 256, 0, st>>>(pp);
+    const unsigned grid = (unsigned)std::min<uint64_t>(n_pad, 148 * 8);
+    auto launch = [&](auto fp4, auto fam) {
+        static_assert(tc::PackPlanes<decltype(fam)::value>::N <= tc::MAX_PLANES, "plane list too long");
+        tc::pack_ops_kernel<decltype(fp4)::value, decltype(fam)::value><<<grid, 256, 0, st>>>(pp);
+    };
+    auto by_fam = [&](auto fp4) {
+        switch (c->fam) {
+        case FAM_SNP: launch(fp4, std::integral_constant<int, FAM_SNP>{}); break;
+        case FAM_RAW: launch(fp4, std::integral_constant<int, FAM_RAW>{}); break;
+        case FAM_K80: launch(fp4, std::integral_constant<int, FAM_K80>{}); break;
+        default: launch(fp4, std::integral_constant<int, FAM_TN93>{}); break;
+        }
+    };
+    if (s.tc_fp4) by_fam(std::true_type{});
+    else by_fam(std::false_type{});
     CUDA_CHECK(cudaGetLastError());
     c->tm.pack_launches++;
 }
@@ -1609,6 +1636,15 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
         uint8_t lut[256];
         uint32_t valid[8];
         host_lut(lut, valid);
+        if (n_gpus > 1) {   // primary contexts take ~1 s each to create: bring them up side by side
+            std::vector<std::thread> th;
+            for (int i = 0; i < n_gpus; i++) {
+                const int id = gpu_ids ? gpu_ids[i] : i;
+                if (id >= 0 && id < ndev) th.emplace_back([id] { if (cudaSetDevice(id) == cudaSuccess) cudaFree(nullptr); });
+            }
+            for (auto& t : th) t.join();
+            cudaGetLastError();
+        }
         for (int i = 0; i < n_gpus; i++) {
             Device d;
             d.id = gpu_ids ? gpu_ids[i] : i;

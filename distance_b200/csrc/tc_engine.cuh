@@ -194,6 +194,27 @@ __device__ __forceinline__ void tc_mma_f4_pair(uint32_t d_tmem, uint64_t a_desc,
 enum PlaneId { P_UA = 0, P_UG, P_UC, P_UT, P_VA, P_VG, P_VC, P_VT, P_KA, P_KG, P_KC, P_KT,
                P_PURK, P_PYRK, P_K, P_W, P_Z, P_PURC, P_PYRC };
 constexpr int MAX_PLANES = 12;
+// The stored planes of every measure family, in storage order (the host-side schedules in dg_api.cu index into these
+// lists).  Compile-time, so pack_ops_kernel unrolls the plane loop with every plane expression resolved.
+template <int FAM> struct PackPlanes;
+template <> struct PackPlanes<FAM_SNP> {
+    static constexpr int N = 8;
+    __host__ __device__ static constexpr uint32_t id(int i) { return i < 4 ? P_UA + i : P_VA + (i - 4); }
+};
+template <> struct PackPlanes<FAM_RAW> {
+    static constexpr int N = 12;
+    __host__ __device__ static constexpr uint32_t id(int i) { return i < 4 ? P_UA + i : (i < 8 ? P_VA + (i - 4) : P_KA + (i - 8)); }
+};
+template <> struct PackPlanes<FAM_K80> {
+    static constexpr int N = 6;
+    __host__ __device__ static constexpr uint32_t id(int i) {
+        return i == 0 ? P_PURK : (i == 1 ? P_PYRK : (i == 2 ? P_W : (i == 3 ? P_Z : (i == 4 ? P_PURC : P_PYRC))));
+    }
+};
+template <> struct PackPlanes<FAM_TN93> {
+    static constexpr int N = 5;
+    __host__ __device__ static constexpr uint32_t id(int i) { return i == 0 ? P_K : (i == 1 ? P_PURK : (i == 2 ? P_PYRK : (i == 3 ? P_W : P_Z))); }
+};
 
 struct PackI8Params {
     const uint8_t* codes;  // n x width
@@ -348,8 +369,9 @@ __device__ __forceinline__ void load_codes16(const PackI8Params& p, const uint8_
 // so they are not 16-byte aligned), translated through a 256-entry LUT in shared memory (ASCII -> Paradis,
 // encoding.rs:4-41; or Paradis -> itself if legal) and expanded to every stored plane with byte-SIMD arithmetic.
 // Per-record A,T,G,C counts (count_bases, fastaio.rs:53-66) are reduced in the CTA: no atomics.
-template <bool FP4>
-__global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
+template <bool FP4, int FAM>
+__global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
+    using PL = PackPlanes<FAM>;
     __shared__ uint8_t lut[256];
     __shared__ uint32_t red[8][4];
     {
@@ -402,7 +424,7 @@ __global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
 #pragma unroll
                 for (int k = 0; k < 4; k++) w[4 * h + k] = wh[k];
             }
-            int8_t* base = p.ops + (seq * p.nplanes) * p.wp8 + (uint64_t)g * 16;
+            int8_t* base = p.ops + (seq * PL::N) * p.wp8 + (uint64_t)g * 16;
             if (FP4) {
                 NibBits nb[4];
 #pragma unroll
@@ -414,8 +436,9 @@ __global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
                         cG += __popc(nb[k].G & nb[k].K); cC += __popc(nb[k].C & nb[k].K);
                     }
                 }
-                for (int pl = 0; pl < p.nplanes; pl++) {
-                    const uint32_t id = p.plane_id[pl];
+#pragma unroll
+                for (int pl = 0; pl < PL::N; pl++) {
+                    const uint32_t id = PL::id(pl);
                     *reinterpret_cast<uint4*>(base + pl * p.wp8) =
                         make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id));
                 }
@@ -430,8 +453,9 @@ __global__ void __launch_bounds__(256) pack_ops_kernel(PackI8Params p) {
                         cG += __popc(b[k].G & b[k].K); cC += __popc(b[k].C & b[k].K);
                     }
                 }
-                for (int pl = 0; pl < p.nplanes; pl++) {
-                    const uint32_t id = p.plane_id[pl];
+#pragma unroll
+                for (int pl = 0; pl < PL::N; pl++) {
+                    const uint32_t id = PL::id(pl);
                     *reinterpret_cast<uint4*>(base + pl * p.wp8) =
                         make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id));
                 }
