@@ -158,6 +158,9 @@ def run_reference(args):
 
 
 def run_ours(args):
+    # a hung collective or kernel must not sit on the GPUs until an outer limit fires: dump every thread's stack and exit
+    import faulthandler
+    faulthandler.dump_traceback_later(args.watchdog, exit=True)
     import distance_b200 as dg
     from distance_b200 import api, dist
 
@@ -242,9 +245,10 @@ def run_ours(args):
     # The pipelined session (dg_square_*): chunks of the alignment go up highest records first, so the PCIe upload,
     # packing + tiles and the D2H of finished panels overlap; the sink reads every panel in pinned host memory.
     #   N = 1 : dg_run_square_host on the pinned host alignment.
-    #   N > 1 : every code byte crosses PCIe ONCE: for each chunk every rank uploads 1/N of it from pinned host
-    #           memory, the ranks all-gather the chunk over NVLink (NCCL) and hand the gathered device buffer to
-    #           dg_square_push together with the CUDA event that marks it ready (no host synchronisation).
+    #   N > 1 : every code byte crosses PCIe ONCE: each rank uploads 1/N of the alignment from pinned host memory, ONE
+    #           NCCL all-gather over NVLink completes it on every GPU, and the session takes its chunks from that device
+    #           buffer (per-chunk collectives were faster at N = 2 but tie every rank's progress to every other rank's
+    #           host; one collective per step keeps the ranks independent).
     import ctypes as C
     e2e_state = {"n": 0, "acc": 0}
 
@@ -259,34 +263,28 @@ def run_ours(args):
     if world > 1:
         import torch
         import torch.distributed as td
-        host_codes = torch.from_numpy(codes).pin_memory()
-        RING = api.DG_SQUARE_LOOKAHEAD + 1
-        side = [torch.cuda.Stream(device=d.device) for _ in range(2)]
-        ring_piece, ring_gath, ring_ev = None, None, [torch.cuda.Event() for _ in range(RING)]
+        # rank r owns records [r*per, (r+1)*per): one pinned host slice, one device slice, ONE all-gather per step
+        per = (n + world - 1) // world
+        lo_r, hi_r = min(n, rank * per), min(n, (rank + 1) * per)
+        host_slice = torch.full((per, WIDTH), 240, dtype=torch.uint8).pin_memory()
+        host_slice[:hi_r - lo_r] = torch.from_numpy(np.ascontiguousarray(codes[lo_r:hi_r]))
+        dev_slice = torch.empty((per, WIDTH), dtype=torch.uint8, device=d.device)
+        gathered = torch.empty((world * per, WIDTH), dtype=torch.uint8, device=d.device)
 
         def e2e_step():
-            nonlocal ring_piece, ring_gath
             e2e_state["n"] = 0
+            dev_slice.copy_(host_slice, non_blocking=True)          # 1/N of the code bytes over this rank's PCIe link
+            td.all_gather_into_tensor(gathered, dev_slice)          # the rest over NVLink
+            torch.cuda.synchronize()
+            # the session takes the chunks from the gathered device buffer (device-to-device copies): packing, tiles and
+            # the D2H of finished panels overlap as in the single-GPU path
             eng.square_begin(n, e2e_cb, rank, world)
-            g = 0
+            base = gathered.data_ptr()
             while True:
                 lo, hi = eng.square_next()
                 if hi == lo:
                     break
-                nr = hi - lo
-                per = (nr + world - 1) // world
-                if ring_piece is None or ring_piece[0].shape[0] < per:
-                    ring_piece = [torch.empty((per, WIDTH), dtype=torch.uint8, device=d.device) for _ in range(RING)]
-                    ring_gath = [torch.empty((per * world, WIDTH), dtype=torch.uint8, device=d.device) for _ in range(RING)]
-                k = g % RING
-                r0, r1 = min(hi, lo + rank * per), min(hi, lo + (rank + 1) * per)
-                with torch.cuda.stream(side[g % 2]):
-                    if r1 > r0:
-                        ring_piece[k][:r1 - r0].copy_(host_codes[r0:r1], non_blocking=True)
-                    td.all_gather_into_tensor(ring_gath[k][:per * world], ring_piece[k][:per])
-                    ring_ev[k].record()
-                eng.square_push(ring_gath[k].data_ptr(), d.local_rank, lo, hi, ring_ev[k].cuda_event)
-                g += 1
+                eng.square_push(base + lo * WIDTH, d.local_rank, lo, hi)
             eng.square_end()
             return e2e_state["n"]
     else:
@@ -303,6 +301,12 @@ def run_ours(args):
         e2e_step()
     sync_all()
     t1 = time.time()
+    if args.trace_e2e:   # one more step with the library's device timeline of the session on stderr (rank 0)
+        if rank == 0:
+            os.environ["DG_TRACE"] = "1"
+        e2e_step()
+        os.environ.pop("DG_TRACE", None)
+        sync_all()
     e2e_step_ms = d.max(1e3 * (t1 - t0) / args.steps)
     e2e_value = total_pairs / (e2e_step_ms * 1e-3)
 
@@ -432,8 +436,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (operand planes %.0f MB vs 126 MB L2)" % (n * 8 * 14976 / 1e6)},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_step_ms,
                     "h2d_bytes_per_step": int(n * WIDTH),
-                    "input_path": ("pipelined session (dg_square_*): per chunk every rank uploads 1/N from pinned host memory, NCCL "
-                                   "all-gather over NVLink, dg_square_push(device buffer, ready event); panels in completion order")
+                    "input_path": ("every rank uploads 1/N of the code bytes from pinned host memory, one NCCL all-gather over NVLink, then the "
+                                   "pipelined session (dg_square_*) takes its chunks from the gathered device buffer; panels in completion order")
                     if world > 1 else "pipelined session (dg_run_square_host) from pinned host memory: upload, tiles and D2H overlap; "
                                       "panels reach the sink in completion order (descending rows)",
                     "in_order_ms_per_step": e2e_inorder_ms,
@@ -469,6 +473,8 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05 int8, 3 tcgen05 fp4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=420, help="seconds after which a stuck run dumps its stacks and exits")
+    ap.add_argument("--trace-e2e", action="store_true", help="after the timed steps, print rank 0's device timeline of one e2e session (DG_TRACE)")
     ap.add_argument("--no-repack-overlap", action="store_true", help="pack every operand plane before the first tile (DG_OPT_REPACK_OVERLAP=0)")
     ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
     ap.add_argument("--measure", default="n_high", choices=sorted(OPS_PER_PAIR_SITE),

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square", "dg_run_rect", "dg_run_part",
     "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
     "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
-    "dg_square_begin", "dg_square_next", "dg_square_push", "dg_square_end", "dg_run_square_host",
+    "dg_square_begin", "dg_square_next", "dg_square_plan", "dg_square_push", "dg_square_end", "dg_run_square_host",
 ]
 
 
@@ -113,6 +113,8 @@ def load_library():
     L.dg_square_begin.argtypes = [vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_square_next.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
     L.dg_square_push.argtypes = [vp, vp, i32, u64, u64, vp]
+    L.dg_square_plan.argtypes = [vp, vp, vp, u64]
+    L.dg_square_plan.restype = C.c_int64
     L.dg_square_end.argtypes = [vp]
     L.dg_run_square_host.argtypes = [vp, vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
@@ -387,6 +389,15 @@ class Engine:
         possible without pushing, so callers use square_chunks() for the plan."""
         self._check(self.L.dg_square_begin(self.h, n, input_kind, None, part, n_parts, sink, None))
         self._n[0] = n
+
+    def square_plan(self):
+        """dg_square_plan: [(lo, hi)] of every chunk of the open session, in push order."""
+        n = self.L.dg_square_plan(self.h, None, None, 0)
+        if n < 0:
+            self._check(int(n))
+        lo, hi = (np.zeros(max(n, 1), dtype=np.uint64) for _ in range(2))
+        self.L.dg_square_plan(self.h, lo.ctypes.data_as(C.c_void_p), hi.ctypes.data_as(C.c_void_p), n)
+        return [(int(lo[k]), int(hi[k])) for k in range(n)]
 
     def square_next(self):
         lo, hi = C.c_uint64(), C.c_uint64()

@@ -1910,6 +1910,20 @@ int dg_square_next(dg_ctx* ctx, uint64_t* lo, uint64_t* hi) {
     });
 }
 
+int64_t dg_square_plan(dg_ctx* ctx, uint64_t* lo, uint64_t* hi, uint64_t cap) {
+    if (!ctx) return DG_ERR_INVALID_ARG;
+    int64_t count = 0;
+    const int rc = guarded(ctx, [&] {
+        if (!ctx->sq_open) fail(DG_ERR_STATE, "no dg_square session is open");
+        for (size_t g = 0; g < ctx->sq_chunks.size() && g < cap; g++) {
+            if (lo) lo[g] = ctx->sq_chunks[g].lo;
+            if (hi) hi[g] = ctx->sq_chunks[g].hi;
+        }
+        count = (int64_t)ctx->sq_chunks.size();
+    });
+    return rc != DG_OK ? rc : count;
+}
+
 int dg_square_push(dg_ctx* ctx, const uint8_t* codes, int src_device, uint64_t lo, uint64_t hi, void* ready_event) {
     const int rc = guarded(ctx, [&] { sq_push(ctx, codes, src_device, lo, hi, ready_event); });
     if (rc != DG_OK && ctx && ctx->sq_open) sq_abort(ctx);

@@ -231,6 +231,9 @@ DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t 
 DG_API int dg_square_begin(dg_ctx *ctx, uint64_t n, int input_kind, const uint64_t *acgt_counts, uint32_t part,
                            uint32_t n_parts, dg_sink_fn sink, void *user);
 DG_API int dg_square_next(dg_ctx *ctx, uint64_t *lo, uint64_t *hi);
+/* The whole chunk sequence of the open session (push order): writes up to `cap` ranges, returns the number of chunks
+ * or a negative DG_ERR_*.  Lets a launcher enqueue every upload / collective before the first push. */
+DG_API int64_t dg_square_plan(dg_ctx *ctx, uint64_t *lo, uint64_t *hi, uint64_t cap);
 DG_API int dg_square_push(dg_ctx *ctx, const uint8_t *codes, int src_device, uint64_t lo, uint64_t hi,
                           void *ready_event);
 DG_API int dg_square_end(dg_ctx *ctx);
