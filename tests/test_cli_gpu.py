@@ -148,3 +148,15 @@ def test_stream_length_error_precedes_invalid_char(tmp_path):
     assert rc == 1 and err == 'Error: Message("Different length sequences in alignment(s): 3 vs 4")\n'  # fastaio.rs:246-248
     fs.write_text(">s1\nACGT\n>s2\nAXGT\n")
     assert run(["-i", str(fl), "-s", str(fs)])[2] == "Error: Message(\"Invalid nucleotide character in record 's2': 'X'\")\n"
+
+
+@pytest.mark.parametrize("measure", ALL)
+def test_cli_matches_committed_golden_tsv(measure):
+    """The committed fixtures of tests/golden (oracle-generated, tests/golden/make_golden.py): every code of
+    encoding.rs, -0.0 / NaN / inf pairs, in all three modes."""
+    g = os.path.join(ROOT, "tests", "golden")
+    a, b = os.path.join(g, "golden_a.fasta"), os.path.join(g, "golden_b.fasta")
+    for mode, args in (("square", [a]), ("rect", [a, b]), ("stream", ["-i", a, "-s", b])):
+        rc, out, err = run(["-m", measure] + args)
+        assert rc == 0, err
+        compare_tsv(measure, out, open(os.path.join(g, f"golden_{mode}_{measure}.tsv")).read())

@@ -198,3 +198,22 @@ def test_n_equals_n_high_random(oracle):
         got, _ = oracle.run("n", "square", a)
         want, _ = oracle.run("n_high", "square", a)
         assert got.tolist() == want.tolist()
+
+
+def test_committed_tsv_fixtures_are_what_the_oracle_writes():
+    """tests/golden/golden_*.tsv (what the GPU CLI is compared with in tests/test_cli_gpu.py) are regenerated from the
+    oracle and must be byte-identical to the committed files."""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    texts = mg.golden_texts()
+    assert len(texts) == 2 + 3 * 6
+    for name, data in texts.items():
+        with open(os.path.join(here, name), "rb") as f:
+            assert f.read() == data, name
+    sq = texts["golden_square_jc69.tsv"].decode()
+    assert "-0.000000000000" in sq and "NaN" in sq and "inf" in sq   # the special values are exercised
+    assert "\t0.000000000000\n" in texts["golden_square_tn93.tsv"].decode()
