@@ -33,6 +33,7 @@ ABI_SYMBOLS = [
     "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
     "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
     "dg_square_begin", "dg_square_next", "dg_square_plan", "dg_square_push", "dg_square_end", "dg_run_square_host",
+    "dg_rect_begin", "dg_run_rect_host",
 ]
 
 
@@ -117,6 +118,8 @@ def load_library():
     L.dg_square_plan.restype = C.c_int64
     L.dg_square_end.argtypes = [vp]
     L.dg_run_square_host.argtypes = [vp, vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
+    L.dg_rect_begin.argtypes = [vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
+    L.dg_run_rect_host.argtypes = [vp, vp, u64, i32, vp, C.c_uint32, C.c_uint32, SINK_FN, vp]
     L.dg_stream_begin.argtypes = [vp, SINK_FN, vp, u64]
     L.dg_stream_push.argtypes = [vp, vp, u64, i32, vp]
     L.dg_stream_end.argtypes = [vp]
@@ -136,7 +139,8 @@ def load_library():
     for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square",
                  "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end",
                  "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings", "dg_square_begin",
-                 "dg_square_next", "dg_square_push", "dg_square_end", "dg_run_square_host"):
+                 "dg_square_next", "dg_square_push", "dg_square_end", "dg_run_square_host", "dg_rect_begin",
+                 "dg_run_rect_host"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -365,6 +369,38 @@ class Engine:
         self._n[0] = n
         self.last_panels = panels
         return out, panels
+
+    def rect_pipelined(self, codes_a: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None, part: int = 0,
+                       n_parts: int = 1, one_call: bool = True):
+        """dg_run_rect_host (or dg_rect_begin + next / push / end): alignment 1 must be loaded.  Returns (values of this
+        part's panels concatenated in the order the sink saw them, panels)."""
+        codes_a = np.ascontiguousarray(codes_a, dtype=np.uint8)
+        n = codes_a.shape[0]
+        dtype = self._dtype()
+        chunks, panels = [], []
+
+        def sink(user, pp):
+            p = pp.contents
+            cnt = int(p.n_results)
+            src = np.frombuffer((C.c_uint8 * (cnt * np.dtype(dtype).itemsize)).from_address(p.data), dtype=dtype, count=cnt)
+            chunks.append(src.copy())
+            panels.append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), cnt))
+            return 0
+
+        cb = SINK_FN(sink)
+        cnt = None if acgt is None else np.ascontiguousarray(acgt, dtype=np.uint64)
+        cptr = None if cnt is None else cnt.ctypes.data_as(C.c_void_p)
+        if one_call:
+            self._check(self.L.dg_run_rect_host(self.h, codes_a.ctypes.data_as(C.c_void_p), n, input_kind, cptr,
+                                                part, n_parts, cb, None))
+        else:
+            self._check(self.L.dg_rect_begin(self.h, n, input_kind, cptr, part, n_parts, cb, None))
+            for lo, hi in self.square_plan():
+                self.square_push(codes_a.ctypes.data + lo * self.width, -1, lo, hi)
+            self.square_end()
+        self._n[0] = n
+        self.last_panels = panels
+        return (np.concatenate(chunks) if chunks else np.zeros(0, dtype=dtype)), panels
 
     def square_pipelined_discard(self, pinned_codes: np.ndarray, part: int = 0, n_parts: int = 1,
                                  input_kind: int = DG_INPUT_PARADIS):

@@ -221,8 +221,10 @@ struct dg_ctx {
     struct SqChunk { uint64_t lo, hi; };
     bool sq_open = false;
     bool sq_tc = false, sq_fallback = false, sq_needs_pp = false;
-    std::vector<Panel> sq_panels;      // this part's panels, ascending rows; launched from the back
-    int sq_next = -1;                  // next panel to launch
+    int sq_mode = DG_MODE_SQUARE;      // SQUARE (chunks and panels descending) or RECT (alignment 0 pushed ascending against
+                                       // the resident alignment 1: panels ascending = the reference's output order)
+    std::vector<Panel> sq_panels;      // this part's panels in LAUNCH order
+    size_t sq_next = 0;                // next panel to launch
     std::vector<SqChunk> sq_chunks;    // descending record ranges, pushed in this order
     size_t sq_pushed = 0, sq_pumped = 0;
     std::vector<uint32_t> sq_base;     // entries before chunk g (size chunks + 1), known once chunk g-1 is pumped
@@ -1050,9 +1052,11 @@ void sq_report_invalid(dg_ctx* c, Device& d, unsigned long long key) {
          (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
 }
 
-void sq_launch_panel(dg_ctx* c, int k) {
+void sq_launch_panel(dg_ctx* c, size_t k) {
     Device& d = c->devs[0];
     PlaneSet& S = d.set[0];
+    const bool rect = c->sq_mode == DG_MODE_RECT;
+    PlaneSet& B = rect ? d.set[1] : S;
     while ((int)c->sq_queue.size() >= Device::NPS) sq_sink_front(c);
     const int si = (int)(c->sq_launched % Device::NPS);
     c->sq_launched++;
@@ -1063,18 +1067,34 @@ void sq_launch_panel(dg_ctx* c, int k) {
     CUDA_CHECK(cudaEventRecord(s.k_start, st));
     const size_t li = c->sq_trace_panel.size();
     if (c->sq_trace) {
-        c->sq_trace_panel.push_back(k);
+        c->sq_trace_panel.push_back((int)k);
         for (auto* v : {&d.tr_k0, &d.tr_k1, &d.tr_d2h})
             while (v->size() <= li) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); v->push_back(e); }
         CUDA_CHECK(cudaEventRecord(d.tr_k0[li], st));
     }
     const uint32_t n_entries = c->sq_base[c->sq_pumped];   // entries of every chunk pumped so far
-    const bool repair = c->sq_needs_pp && n_entries != 0;
+    const bool repair = c->sq_needs_pp && n_entries != 0 && (!rect || B.pp.n_entries != 0);
     if (c->fam == FAM_SNP && !repair) {
-        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s, true);
+        launch_tc_gemm(c, d, S, B, c->sq_mode, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s, true);
     } else {
-        launch_tc_gemm(c, d, S, S, DG_MODE_SQUARE, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s, true);
-        if (repair) {
+        launch_tc_gemm(c, d, S, B, c->sq_mode, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s, true);
+        if (repair && rect) {
+            // rows' entries = the chunks that overlap the panel's rows (contiguous in the shared entry buffer),
+            // columns = the classic per-site index of the resident alignment 1
+            size_t ga0 = c->sq_pumped, ga1 = 0;
+            for (size_t g = 0; g < c->sq_pumped; g++)
+                if (c->sq_chunks[g].lo < p.row1 && c->sq_chunks[g].hi > p.row0) { ga0 = std::min(ga0, g); ga1 = std::max(ga1, g + 1); }
+            if (ga0 < ga1 && c->sq_base[ga1] > c->sq_base[ga0]) {
+                tc::PpCorrParams cp{};
+                cp.a_entries = d.sq_entries + c->sq_base[ga0]; cp.a_n = c->sq_base[ga1] - c->sq_base[ga0];
+                cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
+                cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1; cp.n_b = (uint32_t)B.n;
+                cp.square = 0; cp.n_total = S.n; cp.out_base = p.out_base; cp.out = s.d_scratch;
+                tc::pp_correct_kernel<<<(cp.a_n + 255) / 256, 256, 0, st>>>(cp);
+                CUDA_CHECK(cudaGetLastError());
+                c->tm.count_launches++;
+            }
+        } else if (repair) {
             // the panel's rows live in the chunks [ga0, ga1): chunks are descending, find those that overlap the rows
             size_t ga0 = c->sq_pumped, ga1 = 0;
             for (size_t g = 0; g < c->sq_pumped; g++)
@@ -1092,7 +1112,7 @@ void sq_launch_panel(dg_ctx* c, int k) {
                 c->tm.count_launches++;
             }
         }
-        launch_combine(c, d, S, S, DG_MODE_SQUARE, p, s.d_out, s.d_scratch, false, false, st);
+        launch_combine(c, d, S, B, c->sq_mode, p, s.d_out, s.d_scratch, false, false, st);
     }
     CUDA_CHECK(cudaEventRecord(s.k_stop, st));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_k1[li], st));
@@ -1102,10 +1122,10 @@ void sq_launch_panel(dg_ctx* c, int k) {
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_d2h[li], d.copy));
     InFlight f;
     f.dev = 0; f.slot = si; f.pairs = p.n_results;
-    f.desc.mode = DG_MODE_SQUARE;
+    f.desc.mode = c->sq_mode;
     f.desc.result_kind = c->result_kind();
     f.desc.row_begin = p.row0; f.desc.row_end = p.row1;
-    f.desc.n_cols = S.n; f.desc.n_results = p.n_results;
+    f.desc.n_cols = B.n; f.desc.n_results = p.n_results;
     c->sq_queue.push_back(f);
 }
 
@@ -1148,17 +1168,26 @@ void sq_pump(dg_ctx* c, size_t g) {
         }
         // auto engine: an alignment so full of partial codes that the repair would cost more than the tiles finishes
         // on the LOP3 engine (same rule as use_tc)
-        const double m = (double)(c->sq_n - ch.lo);
-        if (c->engine == 0 && d.h_sq_work[g] > 2.0 * m * m && m >= 1024) c->sq_fallback = true;
+        if (c->sq_mode == DG_MODE_RECT) {
+            const PlaneSet& Bs = d.set[1];
+            const double m = (double)ch.hi;
+            if (c->engine == 0 && std::sqrt(d.h_sq_work[g] * Bs.pp.pair_work) > 2.0 * m * (double)Bs.n && m >= 1024) c->sq_fallback = true;
+        } else {
+            const double m = (double)(c->sq_n - ch.lo);
+            if (c->engine == 0 && d.h_sq_work[g] > 2.0 * m * m && m >= 1024) c->sq_fallback = true;
+        }
     }
     c->sq_base[g + 1] = total;
     c->sq_pumped = g + 1;
     CUDA_CHECK(cudaEventRecord(d.sq_ready, d.fill));   // the host has waited for chunk g's scan: nothing else to order
     if (!c->sq_tc || c->sq_fallback) return;
-    while (c->sq_next >= 0 && c->sq_panels[c->sq_next].row0 >= ch.lo) sq_launch_panel(c, c->sq_next--);
+    // SQUARE: a panel needs every record at or above its first row; RECT: its own rows (alignment 1 is resident)
+    while (c->sq_next < c->sq_panels.size() &&
+           (c->sq_mode == DG_MODE_RECT ? c->sq_panels[c->sq_next].row1 <= ch.hi : c->sq_panels[c->sq_next].row0 >= ch.lo))
+        sq_launch_panel(c, c->sq_next++);
 }
 
-void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
+void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
               dg_sink_fn sink, void* user) {
     if (c->streaming || c->sq_open) fail(DG_ERR_STATE, "a session is already open");
     if (c->devs.size() != 1) fail(DG_ERR_STATE, "dg_square_* sessions drive one device per context (one process per GPU)");
@@ -1171,6 +1200,14 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
     c->have_invalid = false;
     PlaneSet& S = d.set[0];
     const bool want_tc = c->engine != 1;
+    const bool rect = mode == DG_MODE_RECT;
+    if (rect) {
+        if (d.set[1].n == 0) fail(DG_ERR_STATE, "alignment 1 is not loaded (dg_load_resident(ctx, 1, ...) before dg_rect_begin)");
+        if (want_tc && (!d.set[1].tc_ready || d.set[1].tc_fp4 != c->want_fp4()))
+            fail(DG_ERR_STATE, "alignment 1 was loaded for another engine (set DG_OPT_ENGINE before loading)");
+        ensure_pp_index(c, d, d.set[1]);
+    }
+    c->sq_mode = mode;
     reserve_resident(c, S, n, want_tc);
     S.input_kind = input_kind;
     S.acgt_from_host = acgt_counts != nullptr;
@@ -1193,14 +1230,16 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
     }
     // panels: the whole triangle in ~pipe_panels x n_parts pieces (small panels keep the D2H stream fed from early on)
     const TileShape ts = tile_shape(c->fam, c->tile_variant);
-    const uint64_t total_bytes = n * (n - 1) / 2 * c->elem_bytes();
+    const uint64_t n_cols = rect ? d.set[1].n : n;
+    const uint64_t total_bytes = (rect ? n * n_cols : n * (n - 1) / 2) * c->elem_bytes();
     const size_t pb = (size_t)std::min<uint64_t>(c->panel_bytes,
                           std::max<uint64_t>(8ull << 20, total_bytes / ((uint64_t)std::max(1, c->pipe_panels) * n_parts)));  // DG_OPT_PANEL_BYTES caps it
-    std::vector<Panel> all = make_panels(pb, c->elem_bytes(), DG_MODE_SQUARE, n, n, ts.tm);
+    std::vector<Panel> all = make_panels(pb, c->elem_bytes(), mode, n, n_cols, ts.tm);
     c->sq_panels.clear();
     for (size_t k = 0; k < all.size(); k++)
         if (k % n_parts == part) c->sq_panels.push_back(all[k]);
-    c->sq_next = (int)c->sq_panels.size() - 1;
+    if (!rect) std::reverse(c->sq_panels.begin(), c->sq_panels.end());   // launch order: descending rows
+    c->sq_next = 0;
     size_t max_bytes = 256;
     for (auto& p : c->sq_panels) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
     if (want_tc) ensure_pipe_ring(c, d, max_bytes, c->fam != FAM_SNP || c->sq_needs_pp);
@@ -1209,11 +1248,20 @@ void sq_begin(dg_ctx* c, uint64_t n, int input_kind, const uint64_t* acgt_counts
     const uint64_t target = c->pipe_chunk_bytes ? c->pipe_chunk_bytes : std::max<uint64_t>(24ull << 20, n * c->width / 40);
     const uint64_t rows = std::max<uint64_t>(ROW_ALIGN, target / c->width / ROW_ALIGN * ROW_ALIGN);
     c->sq_chunks.clear();
-    for (uint64_t hi = n; hi > 0;) {
-        uint64_t lo = hi > rows ? (hi - rows) / ROW_ALIGN * ROW_ALIGN : 0;
-        if (lo < ROW_ALIGN * 2) lo = 0;   // no sliver at the bottom
-        c->sq_chunks.push_back({lo, hi});
-        hi = lo;
+    if (rect) {
+        for (uint64_t lo = 0; lo < n;) {   // ascending
+            uint64_t hi = std::min<uint64_t>(n, lo + rows);
+            if (n - hi < ROW_ALIGN * 2) hi = n;   // no sliver at the top
+            c->sq_chunks.push_back({lo, hi});
+            lo = hi;
+        }
+    } else {
+        for (uint64_t hi = n; hi > 0;) {
+            uint64_t lo = hi > rows ? (hi - rows) / ROW_ALIGN * ROW_ALIGN : 0;
+            if (lo < ROW_ALIGN * 2) lo = 0;   // no sliver at the bottom
+            c->sq_chunks.push_back({lo, hi});
+            hi = lo;
+        }
     }
     const size_t G = c->sq_chunks.size();
     c->sq_pushed = c->sq_pumped = 0;
@@ -1330,21 +1378,23 @@ void sq_end(dg_ctx* c) {
         }
     }
     S.tc_ready = c->sq_tc;
-    if (c->sq_next >= 0) {
+    if (c->sq_next < c->sq_panels.size()) {
         // LOP3 engine (forced, or chosen because the alignment is full of partial ambiguity codes): the remaining
         // panels run the classic way on the now-resident alignment
         CUDA_CHECK(cudaStreamSynchronize(d.prep));
         CUDA_CHECK(cudaStreamSynchronize(d.fill));
-        std::vector<Panel> rest(c->sq_panels.begin(), c->sq_panels.begin() + c->sq_next + 1);
-        c->sq_next = -1;
+        std::vector<Panel> rest(c->sq_panels.begin() + c->sq_next, c->sq_panels.end());
+        c->sq_next = c->sq_panels.size();
+        PlaneSet& Bs = c->sq_mode == DG_MODE_RECT ? d.set[1] : S;
         if (c->sq_tc) ensure_pp_index(c, d, S);
-        const bool tc_run = use_tc(c, S, S);
+        const bool tc_run = use_tc(c, S, Bs);
         if (!tc_run) {
             ensure_lop3(c, d, S);
             check_invalid(c, d, S.codes, 0);
+            if (c->sq_mode == DG_MODE_RECT) ensure_lop3(c, d, Bs);
         }
         c->last_engine = tc_run ? (S.tc_fp4 ? 3 : 2) : 1;
-        run_panel_list(c, DG_MODE_SQUARE, rest, tc_run, c->sq_sink, c->sq_user, false);
+        run_panel_list(c, c->sq_mode, rest, tc_run, c->sq_sink, c->sq_user, false);
     }
     CUDA_CHECK(cudaStreamSynchronize(d.prep));
     CUDA_CHECK(cudaStreamSynchronize(d.fill));
@@ -1896,7 +1946,14 @@ int64_t dg_plan_ctx(dg_ctx* ctx, int mode, uint64_t* row_begin, uint64_t* row_en
 
 int dg_square_begin(dg_ctx* ctx, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
                     dg_sink_fn sink, void* user) {
-    const int rc = guarded(ctx, [&] { sq_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user); });
+    const int rc = guarded(ctx, [&] { sq_begin(ctx, DG_MODE_SQUARE, n, input_kind, acgt_counts, part, n_parts, sink, user); });
+    if (rc != DG_OK && ctx && !ctx->streaming && !ctx->sq_open && rc != DG_ERR_STATE) sq_abort(ctx);
+    return rc;
+}
+
+int dg_rect_begin(dg_ctx* ctx, uint64_t n, int input_kind, const uint64_t* acgt_counts, uint32_t part, uint32_t n_parts,
+                  dg_sink_fn sink, void* user) {
+    const int rc = guarded(ctx, [&] { sq_begin(ctx, DG_MODE_RECT, n, input_kind, acgt_counts, part, n_parts, sink, user); });
     if (rc != DG_OK && ctx && !ctx->streaming && !ctx->sq_open && rc != DG_ERR_STATE) sq_abort(ctx);
     return rc;
 }
@@ -1936,10 +1993,11 @@ int dg_square_end(dg_ctx* ctx) {
     return rc;
 }
 
-int dg_run_square_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_kind, const uint64_t* acgt_counts,
-                       uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user) {
+static int run_session_host(dg_ctx* ctx, int mode, const uint8_t* codes, uint64_t n, int input_kind, const uint64_t* acgt_counts,
+                            uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user) {
     if (ctx && !codes) { ctx->err = "codes is NULL"; return DG_ERR_INVALID_ARG; }
-    int rc = dg_square_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user);
+    int rc = mode == DG_MODE_RECT ? dg_rect_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user)
+                                  : dg_square_begin(ctx, n, input_kind, acgt_counts, part, n_parts, sink, user);
     if (rc != DG_OK) return rc;
     for (;;) {
         uint64_t lo = 0, hi = 0;
@@ -1948,6 +2006,16 @@ int dg_run_square_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_
         if ((rc = dg_square_push(ctx, codes + lo * ctx->width, -1, lo, hi, nullptr)) != DG_OK) return rc;
     }
     return dg_square_end(ctx);
+}
+
+int dg_run_square_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_kind, const uint64_t* acgt_counts,
+                       uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user) {
+    return run_session_host(ctx, DG_MODE_SQUARE, codes, n, input_kind, acgt_counts, part, n_parts, sink, user);
+}
+
+int dg_run_rect_host(dg_ctx* ctx, const uint8_t* codes, uint64_t n, int input_kind, const uint64_t* acgt_counts,
+                     uint32_t part, uint32_t n_parts, dg_sink_fn sink, void* user) {
+    return run_session_host(ctx, DG_MODE_RECT, codes, n, input_kind, acgt_counts, part, n_parts, sink, user);
 }
 
 int dg_stream_begin(dg_ctx* ctx, dg_sink_fn sink, void* user, uint64_t max_batch) {

@@ -241,6 +241,17 @@ DG_API int dg_square_end(dg_ctx *ctx);
 DG_API int dg_run_square_host(dg_ctx *ctx, const uint8_t *codes, uint64_t n, int input_kind,
                               const uint64_t *acgt_counts, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void *user);
 
+/* The two-file counterpart (replaces load() with two inputs, src/lib.rs:401-409, like dg_run_rect): alignment 1 is
+ * resident (dg_load_resident(ctx, 1, ...)), alignment 0 arrives in chunks, LOWEST records first, through the same
+ * dg_square_next / dg_square_plan / dg_square_push / dg_square_end calls.  A panel (rows of alignment 0 x all of
+ * alignment 1) runs as soon as its rows have landed, so panels complete in ASCENDING order: the sink sees the
+ * reference's output order (generate_pairs_rectangle, src/lib.rs:551-596) while the upload is still going on.
+ * When dg_square_end returns, alignment 0 is resident as after dg_load_resident(ctx, 0, ...). */
+DG_API int dg_rect_begin(dg_ctx *ctx, uint64_t n, int input_kind, const uint64_t *acgt_counts, uint32_t part,
+                         uint32_t n_parts, dg_sink_fn sink, void *user);
+DG_API int dg_run_rect_host(dg_ctx *ctx, const uint8_t *codes, uint64_t n, int input_kind,
+                            const uint64_t *acgt_counts, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void *user);
+
 /* -s streaming (replaces stream(), src/lib.rs:269-365): alignment 0 is resident, batches of the
  * streamed alignment are pushed in file order.  Batches are staged through double-buffered pinned
  * memory and copied with cudaMemcpyAsync while earlier batches compute.  The sink may run during

@@ -183,3 +183,60 @@ def test_overlapped_repack_keeps_the_operands(dg, oracle, measure):
             e.run_device_only(repack=True)
             e.run_device_only(api.DG_MODE_SQUARE, 1, 3, repack=True)
             check(measure, e.run_square(), want)
+
+
+# ---------------------------------------------------------------------------------------------
+# the two-file session: alignment 1 resident, alignment 0 pushed ascending, panels in the reference's order
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("measure", ALL)
+@pytest.mark.parametrize("na,nb,width,amb", [(3, 2, 9, 0.3), (700, 150, 300, 0.1), (1100, 900, 131, 0.4)])
+def test_pipelined_rect_matches_oracle_in_order(dg, oracle, measure, na, nb, width, amb):
+    from distance_b200 import synth
+    rng = np.random.default_rng(na * 13 + nb)
+    a, b = synth.random_codes(rng, na, width, p_ambig=amb), synth.random_codes(rng, nb, width, p_ambig=amb)
+    want = oracle_run(oracle, measure, "rect", a, b)
+    with dg.Engine(measure, width) as e:
+        small_pieces(e, width, chunk_records=128, panel_bytes=1 << 19)
+        e.load(1, b)
+        got, panels = e.rect_pipelined(a, one_call=(na % 2 == 1))
+        rows = [p[1] for p in panels]
+        assert rows == sorted(rows) and all(p[0] == 1 and p[3] == nb for p in panels)   # ascending = reference order
+        check(measure, got, want)
+        # alignment 0 is resident afterwards: the classic two-file run gives the same
+        check(measure, e.run_rect(), want)
+
+
+def test_pipelined_rect_parts_errors_and_fallback(dg, oracle, engine):
+    from distance_b200 import synth
+    na, nb, width = 1500, 700, 120
+    rng = np.random.default_rng(5)
+    a, b = synth.random_codes(rng, na, width, p_ambig=0.2), synth.random_codes(rng, nb, width, p_ambig=0.2)
+    want = oracle_run(oracle, "k80", "rect", a, b)
+    got = np.zeros_like(want)
+    for part in range(2):
+        with dg.Engine("k80", width) as e:
+            small_pieces(e, width, chunk_records=256, panel_bytes=1 << 20)
+            e.load(1, b)
+            vals, panels = e.rect_pipelined(a, part=part, n_parts=2, one_call=False)
+            pos = 0
+            for _, r0, r1, ncols, cnt in panels:
+                got[r0 * nb:r0 * nb + cnt] = vals[pos:pos + cnt]
+                pos += cnt
+    check("k80", got, want)
+    with dg.Engine("n_high", width) as e:
+        with pytest.raises(dg.DistanceGpuError) as ei:       # alignment 1 missing
+            e.rect_pipelined(a)
+        assert ei.value.code == -3
+        heavy_a, heavy_b = synth.random_codes(rng, na, width, p_ambig=0.9), synth.random_codes(rng, nb, width, p_ambig=0.9)
+        small_pieces(e, width, chunk_records=128, panel_bytes=1 << 20)
+        e.load(1, heavy_b)
+        vals, _ = e.rect_pipelined(heavy_a)                  # full of partial codes: auto finishes on the LOP3 tiles
+        check("n_high", vals, oracle_run(oracle, "n_high", "rect", heavy_a, heavy_b))
+        if engine == "auto":
+            assert e.timings()["engine"] == 1
+        bad = a.copy()
+        bad[777, 5] = 3
+        e.load(1, b)
+        with pytest.raises(dg.DistanceGpuError) as ei:
+            e.rect_pipelined(bad)
+        assert ei.value.code == -4 and e.invalid_site()[:2] == (777, 5)

@@ -1,6 +1,12 @@
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-for i in 1 2; do
-timeout 120 $TR --nproc-per-node 2 --master-port 2954$i bench.py --gpus 2 --steps 10 --warmup 3 --watchdog 90 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; echo "run $i rc=$?"; python -c "
-import json; d=json.load(open('gpurun_out/bench_2gpu.json')); print('N=2 value %.4g (%.2f ms) e2e %.4g (%.2f ms)'%(d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step']))" 2>&1 | tail -1
-done
+timeout 600 python -m pytest tests/test_gpu_pipelined.py -x -q > gpurun_out/pytest_pipe.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_pipe.log
+timeout 900 python tools/run_configs.py --only 1,2,3,5 --cpu-budget 4 > gpurun_out/configs_v2.jsonl 2> gpurun_out/configs_v2.err; echo "configs rc=$?"; tail -3 gpurun_out/configs_v2.err
+python - <<PY
+import json
+for l in open("gpurun_out/configs_v2.jsonl"):
+    d=json.loads(l)
+    if "kernel_only" in d:
+        print(d["config"][:60], "| kernel %.2f ms (fp4 frac %.2f) | e2e %.1f ms | pipelined %.1f ms | cpu %.3g" % (d["kernel_only"]["ms"], d["kernel_only"]["frac_of_measured_fp4_peak"], d["e2e"]["ms"], d["e2e_pipelined"]["ms"], d["cpu_baseline"]["value"]))
+    else:
+        print(d)
+PY
