@@ -265,13 +265,16 @@ inline const char* walk_record(const char* p, const char* end, const char*& id0,
     return p;
 }
 
-// The parallel pass.  false = "not a clean alignment": the caller re-reads sequentially for the exact error / edge case.
-bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
+// The parallel pass over whole records.  false = "not clean": the caller re-reads the same bytes sequentially for the
+// exact error / edge case.  width: in = the width every record must have (0 = take the first record's), out = the width.
+// dst_for(n) returns where the n x width bytes go (nullptr = refuse: too many records for the caller's buffer).
+// The ids are appended to `ids`; n_out = records parsed.
+template <typename DstFor>
+bool parse_clean(const char* data, size_t size, int threads, uint64_t& width, DstFor&& dst_for, std::vector<std::string>& ids,
+                 uint64_t& n_out) {
     if (size == 0 || data[0] != '>') return false;
     const char* end = data + size;
-    // width = length of the first record
-    uint64_t width = 0;
-    {
+    if (width == 0) {   // width = length of the first record
         const char* id0; size_t idl; bool desc;
         walk_record(data, end, id0, idl, desc, [&](const char*, size_t n) { width += n; });
         if (width == 0) return false;
@@ -320,16 +323,10 @@ bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
     for (int t = 0; t < T; t++) first[t + 1] = first[t] + count[t];
     const uint64_t n = first[T];
     if (n == 0) return false;
-    a.ids.assign(n, std::string());
-    a.width = width;
-    {   // uninitialised, 2 MB aligned, transparent huge pages requested: the pages are first touched by the threads below
-        void* mem = nullptr;
-        const size_t bytes = ((size_t)(n * width) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
-        if (posix_memalign(&mem, 2u << 20, bytes) != 0) throw std::bad_alloc();
-        madvise(mem, bytes, MADV_HUGEPAGE);
-        a.fast_.reset(static_cast<uint8_t*>(mem));
-    }
-    uint8_t* dst = a.fast_.get();
+    uint8_t* dst = dst_for(n);
+    if (!dst) return false;
+    const size_t id0_index = ids.size();
+    ids.resize(id0_index + n);
     // pass 2: ids, validation (encoding.rs:7-38) and the copy
     auto pass2 = [&](int t) {
         uint64_t r = first[t];
@@ -345,7 +342,7 @@ bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
                 out += k;
             });
             if (bad) { clean.store(false); return; }
-            a.ids[r].assign(id0, idl);
+            ids[id0_index + r].assign(id0, idl);
             r++;
         }
     };
@@ -356,9 +353,26 @@ bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
         for (auto& x : th) x.join();
     }
     if (!clean.load()) {
-        a = Alignment();
+        ids.resize(id0_index);
         return false;
     }
+    n_out = n;
+    return true;
+}
+
+bool parse_parallel(const char* data, size_t size, int threads, Alignment& a) {
+    uint64_t width = 0, n = 0;
+    const bool ok = parse_clean(data, size, threads, width, [&](uint64_t recs) {
+        // uninitialised, 2 MB aligned, transparent huge pages requested: the pages are first touched by the parser's threads
+        void* mem = nullptr;
+        const size_t bytes = ((size_t)(recs * width) + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+        if (posix_memalign(&mem, 2u << 20, bytes) != 0) throw std::bad_alloc();
+        madvise(mem, bytes, MADV_HUGEPAGE);
+        a.fast_.reset(static_cast<uint8_t*>(mem));
+        return a.fast_.get();
+    }, a.ids, n);
+    if (!ok) { a = Alignment(); return false; }
+    a.width = width;
     return true;
 }
 
@@ -395,6 +409,119 @@ Alignment load_fasta(int fd, int threads) {
     }
     if (a.ids.empty()) throw message_error("Empty FASTA file");  // fastaio.rs:195-197
     return a;
+}
+
+// ---- streamed file: blocks of whole records, parsed in parallel straight into the caller's (pinned) batch buffer ---------
+StreamBlockParser::StreamBlockParser(int fd, uint64_t width, int threads) : fd_(fd), width_(width), threads_(threads) {
+    struct stat st;
+    regular_ = fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+    if (regular_) {
+        const off_t cur = lseek(fd, 0, SEEK_CUR);
+        regular_ = cur >= 0;
+        offset_ = regular_ ? (uint64_t)cur : 0;
+        file_size_ = (uint64_t)st.st_size;
+    }
+}
+
+// Append up to `want` bytes of input to raw_; sets eof_ at the end.  Regular files: parallel pread().
+void StreamBlockParser::fill(size_t want) {
+    if (eof_ || want == 0) return;
+    const size_t old = raw_len_;
+    if (raw_cap_ < old + want) {
+        const size_t cap = std::max(old + want, raw_cap_ + raw_cap_ / 2);
+        std::unique_ptr<char[]> bigger(new char[cap]);   // not value-initialised
+        if (old) std::memcpy(bigger.get(), raw_.get(), old);
+        raw_ = std::move(bigger);
+        raw_cap_ = cap;
+    }
+    size_t got = 0;
+    if (regular_) {
+        const size_t avail = offset_ < file_size_ ? (size_t)std::min<uint64_t>(want, file_size_ - offset_) : 0;
+        int T = threads_ > 0 ? threads_ : (int)std::max(1u, std::thread::hardware_concurrency());
+        T = (int)std::min<size_t>((size_t)std::min(T, 32), std::max<size_t>(1, avail / (8u << 20)));
+        std::atomic<int> err{0};
+        std::atomic<size_t> done{0};
+        auto rd = [&](int t) {
+            size_t lo = avail / T * t, hi = t == T - 1 ? avail : avail / T * (t + 1);
+            while (lo < hi) {
+                ssize_t r = ::pread(fd_, raw_.get() + old + lo, hi - lo, (off_t)(offset_ + lo));
+                if (r < 0) { if (errno == EINTR) continue; err.store(errno); return; }
+                if (r == 0) break;
+                lo += (size_t)r; done += (size_t)r;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < T; t++) th.emplace_back(rd, t);
+        if (avail) rd(0);
+        for (auto& x : th) x.join();
+        if (err.load()) throw io_error_os(err.load());
+        got = done.load() == avail ? avail : 0;
+        if (done.load() != avail) regular_ = false;   // the file changed under us: continue with plain reads from here
+        else offset_ += got;
+        if (got < want && regular_) eof_ = true;
+        if (!regular_) lseek(fd_, (off_t)offset_, SEEK_SET);
+    }
+    if (!regular_) {
+        while (got < want) {
+            ssize_t r = ::read(fd_, raw_.get() + old + got, want - got);
+            if (r < 0) { if (errno == EINTR) continue; throw io_error_os(errno); }
+            if (r == 0) { eof_ = true; break; }
+            got += (size_t)r;
+        }
+    }
+    raw_len_ = old + got;
+}
+
+uint64_t StreamBlockParser::next(uint8_t* dst, uint64_t max_records, std::vector<std::string>& ids) {
+    if (done_) return 0;
+    // every record occupies at least width + 2 input bytes ('>', '\n', the sequence): a block of at most
+    // max_records * (width + 2) bytes holds at most max_records whole records
+    size_t target = (size_t)(max_records * (width_ + 2));
+    size_t cut = 0;
+    for (;;) {
+        if (raw_len_ < target) fill(target - raw_len_);
+        if (raw_len_ == 0) { done_ = true; return 0; }
+        if (eof_) { cut = raw_len_; break; }
+        // the last record start inside the block: everything before it is whole records
+        cut = 0;
+        for (size_t p = raw_len_ - 1; p > 0; p--)
+            if (raw_[p] == '>' && raw_[p - 1] == '\n') { cut = p; break; }
+        if (cut > 0) break;
+        target *= 2;   // one record longer than the block (huge header or width mismatch ahead): take more
+    }
+    uint64_t n = 0;
+    uint64_t w = width_;
+    const size_t ids_before = ids.size();
+    const bool clean = parse_clean(raw_.get(), cut, threads_, w, [&](uint64_t recs) { return recs <= max_records ? dst : nullptr; },
+                                   ids, n);
+    if (!clean) {
+        // the sequential reader over the same bytes, with stream_fasta's order of checks: width (fastaio.rs:246-248), then
+        // the nucleotides (:250-254)
+        ids.resize(ids_before);
+        FastaReader rd(raw_.get(), cut, /*validate=*/false);
+        std::vector<uint8_t> rec;
+        std::string id;
+        n = 0;
+        for (;;) {
+            rec.clear();
+            if (!rd.next(id, rec)) {
+                if (!rd.at_end()) done_ = true;   // an empty record ends the iteration (rust-bio), whatever follows
+                break;
+            }
+            if (rec.size() != width_)
+                throw message_error("Different length sequences in alignment(s): " + std::to_string(rec.size()) + " vs " +
+                                    std::to_string(width_));
+            validate_record(id, rec.data(), rec.size());
+            if (n >= max_records) throw message_error("internal: stream block holds more records than the batch");
+            std::memcpy(dst + n * width_, rec.data(), width_);
+            ids.push_back(id);
+            n++;
+        }
+    }
+    std::memmove(raw_.get(), raw_.get() + cut, raw_len_ - cut);   // carry the partial last record over
+    raw_len_ -= cut;
+    if (eof_ && raw_len_ == 0) done_ = true;
+    return n;
 }
 
 void check_same_width(const Alignment& a, const Alignment& b) {  // fastaio.rs:206-208

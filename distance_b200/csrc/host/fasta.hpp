@@ -57,6 +57,8 @@ public:
     // Reads the next record: id into `id`, sequence bytes APPENDED to `seq`.  Returns false at the
     // end of the input.  Throws DistanceError on malformed input or an invalid nucleotide.
     bool next(std::string& id, std::vector<uint8_t>& seq);
+    // every input byte has been consumed (false after next() stopped early at an empty record)
+    bool at_end() const { return eof_ && pos_ == end_ && !have_line_; }
 
 private:
     bool read_line();  // fills line_ (without the '\n'); false at EOF with nothing read
@@ -78,6 +80,28 @@ private:
 // (a width mismatch, an invalid byte, a malformed or empty record ...) abandons the parallel pass and re-reads the
 // same bytes with the sequential FastaReader, which raises the reference's error for the first offence in file order.
 Alignment load_fasta(int fd, int threads = 0);
+// stream_fasta (fastaio.rs:215-286) in blocks: reads the streamed file a batch at a time (parallel pread for regular
+// files), cuts the block at the last record start, and parses its whole records with the same parallel pass as
+// load_fasta, writing the sequence bytes straight into the caller's batch buffer (the pinned staging buffer of
+// dg_stream_buffer).  A block that is not clean (width mismatch, invalid byte, malformed record) is re-read by the
+// sequential FastaReader with the reference's order of checks, so the first offence in file order raises its error.
+class StreamBlockParser {
+public:
+    StreamBlockParser(int fd, uint64_t width, int threads = 0);
+    // Up to max_records whole records into dst (max_records x width bytes); their ids are appended.  0 = end of input.
+    uint64_t next(uint8_t* dst, uint64_t max_records, std::vector<std::string>& ids);
+
+private:
+    void fill(size_t want);
+    int fd_;
+    uint64_t width_;
+    int threads_;
+    bool regular_ = false, eof_ = false, done_ = false;
+    uint64_t offset_ = 0, file_size_ = 0;
+    std::unique_ptr<char[]> raw_;   // uninitialised storage: carry-over of the previous block + the new bytes
+    size_t raw_cap_ = 0, raw_len_ = 0;
+};
+
 // the cross-file width check of load_fastas (fastaio.rs:202-212)
 void check_same_width(const Alignment& a, const Alignment& b);
 

@@ -273,27 +273,18 @@ int run(const Args& a) {
         writer.set_ids(&loaded[0].ids, &streamed_ids);
         const uint64_t batch = std::max<uint64_t>(64, std::min<uint64_t>(8192, (64ull << 20) / std::max<uint64_t>(1, width)));
         gpu_check(ctx, dg_stream_begin(ctx, sink_cb, &st, batch), &st);
-        FastaReader rd(stream_fd, /*validate=*/false);
-        std::vector<uint8_t> buf;
-        buf.reserve(batch * width);
-        std::string id;
-        uint64_t in_batch = 0, records = 0;
+        // whole-record blocks parsed in parallel straight into the library's pinned staging buffer (no host copy)
+        StreamBlockParser parser(stream_fd, width, (int)std::min<uint64_t>(threads, 64));
+        uint64_t records = 0;
         for (;;) {
-            const size_t before = buf.size();
-            if (!rd.next(id, buf)) break;
-            records++;
-            const uint64_t len = buf.size() - before;
-            if (len != width)  // fastaio.rs:246-248
-                throw message_error("Different length sequences in alignment(s): " + std::to_string(len) + " vs " + std::to_string(width));
-            validate_record(id, buf.data() + before, len);  // fastaio.rs:250-254 -> :111-113
-            streamed_ids.push_back(id);
-            if (++in_batch == batch) {
-                gpu_check(ctx, dg_stream_push(ctx, buf.data(), in_batch, DG_INPUT_ASCII, nullptr), &st);
-                buf.clear();
-                in_batch = 0;
-            }
+            uint8_t* buf = nullptr;
+            uint64_t cap = 0;
+            gpu_check(ctx, dg_stream_buffer(ctx, &buf, &cap), &st);
+            const uint64_t got = parser.next(buf, cap, streamed_ids);
+            if (got == 0) break;
+            records += got;
+            gpu_check(ctx, dg_stream_push(ctx, buf, got, DG_INPUT_ASCII, nullptr), &st);
         }
-        if (in_batch) gpu_check(ctx, dg_stream_push(ctx, buf.data(), in_batch, DG_INPUT_ASCII, nullptr), &st);
         gpu_check(ctx, dg_stream_end(ctx), &st);
         if (records == 0) throw message_error("Empty FASTA file");  // fastaio.rs:281-283 (after the header was written)
     } else if (loaded.size() == 1) {
@@ -394,6 +385,53 @@ int selftest_parse(const char* path, int threads) {
     return same ? 0 : 1;
 }
 
+// Hidden developer check: the block parser of the streamed file against the sequential reader with stream_fasta's checks
+// (same ids, bytes, record count, error text).  `distance --selftest-stream FILE WIDTH BATCH [threads]`.
+int selftest_stream(const char* path, uint64_t width, uint64_t batch, int threads) {
+    std::vector<std::string> ids_b, ids_s;
+    std::vector<uint8_t> seq_b, seq_s;
+    std::string eb, es;
+    {
+        const int fd = ::open(path, O_RDONLY);
+        if (fd < 0) { perror("open"); return 1; }
+        try {
+            StreamBlockParser parser(fd, width, threads);
+            std::vector<uint8_t> buf(batch * width);
+            for (;;) {
+                const uint64_t got = parser.next(buf.data(), batch, ids_b);
+                if (got == 0) break;
+                seq_b.insert(seq_b.end(), buf.begin(), buf.begin() + (std::ptrdiff_t)(got * width));
+            }
+        } catch (const DistanceError& e) { eb = e.what(); }
+        ::close(fd);
+    }
+    {
+        const int fd = ::open(path, O_RDONLY);
+        try {
+            FastaReader rd(fd, false);
+            std::string id;
+            for (;;) {
+                const size_t before = seq_s.size();
+                if (!rd.next(id, seq_s)) break;
+                const uint64_t len = seq_s.size() - before;
+                if (len != width)
+                    throw message_error("Different length sequences in alignment(s): " + std::to_string(len) + " vs " + std::to_string(width));
+                validate_record(id, seq_s.data() + before, len);
+                ids_s.push_back(id);
+            }
+        } catch (const DistanceError& e) { es = e.what(); }
+        ::close(fd);
+    }
+    // on an error the records delivered before it must be a prefix of the sequential reader's
+    bool same = eb == es;
+    if (es.empty()) same = same && ids_b == ids_s && seq_b == seq_s;
+    else same = same && ids_b.size() <= ids_s.size() && std::equal(ids_b.begin(), ids_b.end(), ids_s.begin()) &&
+                std::equal(seq_b.begin(), seq_b.end(), seq_s.begin());
+    printf("selftest-stream: %s; records %zu (block parser %zu); error '%s'\n", same ? "identical" : "MISMATCH", ids_s.size(),
+           ids_b.size(), es.c_str());
+    return same ? 0 : 1;
+}
+
 // Hidden developer check: the pooled TSV writer against a line-by-line restatement of gather_write (lib.rs:626-633)
 // for every mode and result kind, with short and long ids, several thread counts, panels larger than one chunk.
 // `distance --selftest-tsv`.
@@ -481,7 +519,9 @@ int selftest_tsv() {
 
 int main(int argc, char** argv) {
     std::signal(SIGPIPE, SIG_IGN);
-    if (argc == 2 && !strcmp(argv[1], "--selftest-tsv")) return selftest_tsv();  // a closed pipe shows up as EPIPE -> exit 0 (lib.rs:598-608)
+    if (argc == 2 && !strcmp(argv[1], "--selftest-tsv")) return selftest_tsv();
+    if (argc >= 5 && !strcmp(argv[1], "--selftest-stream"))
+        return selftest_stream(argv[2], strtoull(argv[3], nullptr, 10), strtoull(argv[4], nullptr, 10), argc > 5 ? atoi(argv[5]) : 0);  // a closed pipe shows up as EPIPE -> exit 0 (lib.rs:598-608)
     if (argc == 3 && !strcmp(argv[1], "--selftest-format")) return selftest_format(strtoull(argv[2], nullptr, 10));
     if (argc >= 3 && !strcmp(argv[1], "--selftest-parse")) return selftest_parse(argv[2], argc > 3 ? atoi(argv[3]) : 0);
     const Args a = parse_args(argc, argv);

@@ -180,3 +180,36 @@ def test_parallel_loader_falls_back_for_errors_and_odd_input(tmp_path):
 def test_pooled_tsv_writer_matches_line_by_line_text():
     rc, out, err = run(["--selftest-tsv"])
     assert rc == 0 and "0 mismatches" in out, (out, err)
+
+
+def _selftest_stream(tmp_path, text, width, batch, threads=4):
+    f = tmp_path / "s.fa"
+    f.write_bytes(text.encode())
+    rc, out, err = run(["--selftest-stream", str(f), str(width), str(batch), str(threads)])
+    assert rc == 0 and "identical" in out, (out, err)
+    return out
+
+
+def test_stream_block_parser_matches_sequential_reader(tmp_path):
+    import random
+    rnd = random.Random(11)
+    width = 3000
+    recs = [(f"q{i} desc", "".join(rnd.choice("ACGTNacgt-?RY") for _ in range(width))) for i in range(2500)]
+    for batch in (1, 7, 64, 1000, 5000):
+        assert "records 2500 (block parser 2500)" in _selftest_stream(tmp_path, _fasta(recs), width, batch)
+    _selftest_stream(tmp_path, _fasta(recs, line=70, eol="\r\n"), width, 333)
+    _selftest_stream(tmp_path, _fasta(recs, final_eol=False), width, 4096, threads=16)
+    # errors: the first offence in file order, width before nucleotides (fastaio.rs:246-254)
+    bad = list(recs)
+    bad[2000] = ("q2000", recs[2000][1][:50] + "X" + recs[2000][1][51:])
+    assert "Invalid nucleotide character in record 'q2000': 'X'" in _selftest_stream(tmp_path, _fasta(bad), width, 256)
+    bad[1200] = ("q1200", recs[1200][1][:-3])
+    assert "Different length sequences in alignment(s): 2997 vs 3000" in _selftest_stream(tmp_path, _fasta(bad), width, 256)
+    assert "Different length" in _selftest_stream(tmp_path, _fasta(recs), width + 1, 256)      # every record is "wrong"
+    assert "Expected > at record start." in _selftest_stream(tmp_path, "garbage\n" + _fasta(recs[:10]), width, 4)
+    # an empty record ends the iteration; an empty id with a description does not
+    out = _selftest_stream(tmp_path, _fasta(recs[:300]) + ">\n\n" + _fasta(recs[300:400]), width, 64)
+    assert "records 300 (block parser 300)" in out
+    out = _selftest_stream(tmp_path, _fasta(recs[:300]) + "> only a description\n" + recs[0][1] + "\n" + _fasta(recs[300:400]), width, 64)
+    assert "records 401 (block parser 401)" in out
+    assert "records 0" in _selftest_stream(tmp_path, "", width, 8)
