@@ -7,7 +7,7 @@ LIBDIR := distance_b200/_lib
 LIB := $(LIBDIR)/libdistance_gpu.so
 CSRC := distance_b200/csrc
 
-all: lib cli oracle
+all: lib cli oracle tools
 
 lib: $(LIB)
 
@@ -31,7 +31,15 @@ $(CLI): $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp $(HOST)/fasta.hpp $(H
 oracle:
 	$(MAKE) -C oracle
 
+# micro-benchmarks behind the roofline denominators and the host-side figures (profiles/*.json)
+TOOLS := tools/ubench_int tools/ubench_tc tools/ubench_fp4 tools/ubench_pcie tools/ubench_init tools/tsv_bench
+tools: $(TOOLS)
+tools/ubench_%: tools/ubench_%.cu
+	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $< -lcuda -ldl
+tools/tsv_bench: tools/tsv_bench.cpp $(HOST)/tsv.cpp $(HOST)/fasta.cpp $(HOST)/tsv.hpp $(HOST)/fasta.hpp
+	$(CXX) -O2 -std=c++17 -pthread -o $@ tools/tsv_bench.cpp $(HOST)/tsv.cpp $(HOST)/fasta.cpp
+
 clean:
 	rm -rf $(LIBDIR) $(BINDIR) && $(MAKE) -C oracle clean
 
-.PHONY: all lib cli oracle clean
+.PHONY: all lib cli oracle tools clean

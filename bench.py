@@ -383,6 +383,9 @@ def run_ours(args):
             "bound": "tensor", "kernel": kname, "achieved": ach, "peak": pk8,
             "unit": unit, "frac": ach / pk8,
             "frac_of_int8_peak": ach / peaks["int8_tops_measured"] if peaks.get("int8_tops_measured") else None,
+            # context: MEASURED_PEAKS.json only carries dense bf16 (cuBLAS); nominal fp4 = 4 x bf16
+            "measured_peaks_json_bf16_tflops": measured.get("bf16_tflops"),
+            "frac_of_4x_measured_bf16": (ach / (4.0 * measured["bf16_tflops"])) if measured.get("bf16_tflops") else None,
             "traffic": peaks.get("tc_kernel_dram_bytes_per_launch"),
             "ops_per_pair_site": I8_OPS_PER_PAIR_SITE[MEASURE], "peak_source": src8,
             "frac_in_survey_units": ach / pk8 * 10.0 / I8_OPS_PER_PAIR_SITE[MEASURE],

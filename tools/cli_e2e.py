@@ -13,8 +13,40 @@ ap.add_argument("--n", type=int, default=20000)
 ap.add_argument("--measure", default="n_high")
 ap.add_argument("--dir", default="/dev/shm")
 ap.add_argument("--seed", type=int, default=20251018 + 2)
+ap.add_argument("--stream", type=int, default=0,
+                help="config 4 instead: -m k80 -i <1,000 resident records> -s <this many streamed records> (a pool of 20,000 records repeated)")
 a = ap.parse_args()
 cli = os.path.join(ROOT, "distance_b200", "_bin", "distance")
+if a.stream:
+    import numpy as np
+    root = synth.make_root(synth.SC2_WIDTH, 20251018 + 4)
+    res = synth.make_alignment(1000, seed=20251018 + 4, ambiguity=True, root=root)
+    pool = synth.make_alignment(20000, seed=20251018 + 44, ambiguity=True, root=root)
+    fr, fs = os.path.join(a.dir, "dg_cfg4_resident.fasta"), os.path.join(a.dir, "dg_cfg4_stream.fasta")
+    with open(fr, "wb") as f:
+        for i, r in enumerate(res):
+            f.write(b">r%06d\n" % i); f.write(r.tobytes()); f.write(b"\n")
+    t0 = time.time()
+    with open(fs, "wb") as f:
+        k = 0
+        while k < a.stream:
+            for r in pool[:min(len(pool), a.stream - k)]:
+                f.write(b">q%07d\n" % k); f.write(r.tobytes()); f.write(b"\n"); k += 1
+    gen_s = time.time() - t0
+    pairs = 1000 * a.stream
+    out = {"config": "cfg4 through the CLI: -m k80 -i 1,000 resident -s %d streamed" % a.stream, "pairs": pairs,
+           "stream_fasta_bytes": os.path.getsize(fs), "cores": os.cpu_count(), "fasta_write_s": gen_s, "runs": []}
+    for rep in range(2):
+        t0 = time.time()
+        with open("/dev/null", "wb") as so:
+            p = subprocess.run([cli, "-m", "k80", "-i", fr, "-s", fs], stdout=so, stderr=subprocess.PIPE, env=dict(os.environ, DG_TRACE="1"))
+        wall = time.time() - t0
+        out["runs"].append({"tsv_to": "/dev/null", "rc": p.returncode, "wall_s": wall, "pairs_per_s": pairs / wall,
+                            "stream_gb_per_s": os.path.getsize(fs) / wall / 1e9,
+                            "phases": [l for l in p.stderr.decode().splitlines() if l.startswith("[distance]")]})
+    os.unlink(fr); os.unlink(fs)
+    print(json.dumps(out))
+    sys.exit(0)
 fa = os.path.join(a.dir, f"dg_cli_e2e_{a.n}.fasta")
 t0 = time.time()
 asc = synth.make_alignment(a.n, seed=a.seed, ambiguity=True)
