@@ -232,9 +232,12 @@ int run(const Args& a) {
     const bool trace = std::getenv("DG_TRACE") != nullptr;
     const auto t_start = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
+    // -t (lib.rs:252-264): here the worker count of the host side -- FASTA parsing and TSV formatting
+    const uint64_t threads = a.have_threads ? std::max<uint64_t>(1, a.threads)
+                                            : std::max(1u, std::thread::hardware_concurrency());
     std::vector<Alignment> loaded;
     for (size_t k = 0; k < fds.size(); k++) {
-        loaded.push_back(load_fasta(fds[k]));
+        loaded.push_back(load_fasta(fds[k], (int)std::min<uint64_t>(threads, 64)));
         if (k == 1) check_same_width(loaded[0], loaded[1]);
         if (fds[k] != 0) ::close(fds[k]);
     }
@@ -243,8 +246,6 @@ int run(const Args& a) {
         out_fd = ::open(a.output.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);  // File::create, lib.rs:248-250
         if (out_fd < 0) throw io_error_os(errno);
     }
-    uint64_t threads = a.have_threads ? std::max<uint64_t>(1, a.threads)  // lib.rs:252-264
-                                      : std::max(1u, std::thread::hardware_concurrency());
 
     // ---- run (lib.rs:490-498) ----------------------------------------------------------------------
     if (trace) fprintf(stderr, "[distance] %.3f s: inputs parsed\n", since());
