@@ -280,7 +280,9 @@ bool parse_clean(const char* data, size_t size, int threads, uint64_t& width, Ds
         if (width == 0) return false;
     }
     int T = threads > 0 ? threads : (int)std::max(1u, std::thread::hardware_concurrency());
-    T = (int)std::min<size_t>((size_t)std::min(T, 64), std::max<size_t>(1, size / (4u << 20)));
+    size_t seg_bytes = 4u << 20;   // at least this much input per thread (DG_PARSE_SEG overrides it: tests cut tiny inputs)
+    if (const char* e = std::getenv("DG_PARSE_SEG")) seg_bytes = std::max<size_t>(1, (size_t)std::strtoull(e, nullptr, 10));
+    T = (int)std::min<size_t>((size_t)std::min(T, 64), std::max<size_t>(1, size / seg_bytes));
     // segment starts: the first '>' at a line start at or after size * t / T
     std::vector<const char*> seg(T + 1, end);
     seg[0] = data;
@@ -476,18 +478,39 @@ uint64_t StreamBlockParser::next(uint8_t* dst, uint64_t max_records, std::vector
     if (done_) return 0;
     // every record occupies at least width + 2 input bytes ('>', '\n', the sequence): a block of at most
     // max_records * (width + 2) bytes holds at most max_records whole records
-    size_t target = (size_t)(max_records * (width_ + 2));
+    const size_t first_target = (size_t)(max_records * (width_ + 2));
+    size_t target = first_target;
     size_t cut = 0;
     for (;;) {
         if (raw_len_ < target) fill(target - raw_len_);
         if (raw_len_ == 0) { done_ = true; return 0; }
-        if (eof_) { cut = raw_len_; break; }
-        // the last record start inside the block: everything before it is whole records
-        cut = 0;
-        for (size_t p = raw_len_ - 1; p > 0; p--)
-            if (raw_[p] == '>' && raw_[p - 1] == '\n') { cut = p; break; }
-        if (cut > 0) break;
-        target *= 2;   // one record longer than the block (huge header or width mismatch ahead): take more
+        if (raw_len_ > first_target) {
+            // the block had to grow beyond the size that bounds its record count (records longer than width + 2 bytes:
+            // long headers, wrapped lines, a width mismatch ahead): count the record starts and take at most max_records
+            uint64_t starts = 0;
+            size_t boundary = 0;   // start of record number max_records (0-based), if there is one
+            for (size_t p = 1; p < raw_len_; p++) {
+                const char* q = static_cast<const char*>(std::memchr(raw_.get() + p, '>', raw_len_ - p));
+                if (!q) break;
+                p = (size_t)(q - raw_.get());
+                if (raw_[p - 1] == '\n' && ++starts == max_records) { boundary = p; break; }
+            }
+            if (boundary) { cut = boundary; break; }           // max_records whole records (record 0 starts at byte 0)
+            if (eof_) { cut = raw_len_; break; }               // fewer: the rest of the input
+            if (starts > 0) {                                  // some whole records and a partial one: cut at the last start
+                for (size_t p = raw_len_ - 1; p > 0; p--)
+                    if (raw_[p] == '>' && raw_[p - 1] == '\n') { cut = p; break; }
+                break;
+            }
+        } else {
+            if (eof_) { cut = raw_len_; break; }
+            // the last record start inside the block: everything before it is whole records
+            cut = 0;
+            for (size_t p = raw_len_ - 1; p > 0; p--)
+                if (raw_[p] == '>' && raw_[p - 1] == '\n') { cut = p; break; }
+            if (cut > 0) break;
+        }
+        target *= 2;   // not even one whole record yet: take more
     }
     uint64_t n = 0;
     uint64_t w = width_;

@@ -213,3 +213,48 @@ def test_stream_block_parser_matches_sequential_reader(tmp_path):
     out = _selftest_stream(tmp_path, _fasta(recs[:300]) + "> only a description\n" + recs[0][1] + "\n" + _fasta(recs[300:400]), width, 64)
     assert "records 401 (block parser 401)" in out
     assert "records 0" in _selftest_stream(tmp_path, "", width, 8)
+
+
+def test_parsers_fuzz_against_sequential_reader(tmp_path):
+    """Random FASTA-like inputs (ragged line lengths, CR LF mixes, blank lines, stray whitespace, empty ids, width
+    mismatches, invalid bytes, junk) cut into many tiny segments / batches: the parallel loader and the stream block parser
+    must agree with the sequential reader on ids, bytes and error text every time."""
+    import random
+    rnd = random.Random(20251018)
+    env = dict(os.environ, DG_PARSE_SEG="97")
+    alphabet = "ACGTNacgtn-?RYKMSWBDHV"
+    for case in range(int(os.environ.get("DG_FUZZ_CASES", "60"))):
+        width = rnd.choice([1, 7, 60, 61, 250])
+        n = rnd.randint(1, 40)
+        eol = rnd.choice(["\n", "\r\n"])
+        parts = []
+        for i in range(n):
+            seq = "".join(rnd.choice(alphabet) for _ in range(width))
+            kind = rnd.random()
+            if case % 3 == 1 and kind < 0.04:
+                seq = seq[:-1]                                    # width mismatch
+            elif case % 3 == 2 and kind < 0.04:
+                k = rnd.randrange(width)
+                seq = seq[:k] + rnd.choice("XUZ*.1 ") + seq[k + 1:]   # invalid byte (or an inner blank)
+            rid = f"id{i}" if rnd.random() > 0.03 else ""
+            desc = rnd.choice(["", " d", "\tx y ", "  "])
+            parts.append(">" + rid + desc + eol)
+            line = rnd.choice([0, 0, 13, 60, 70])
+            chunks = [seq] if not line else [seq[j:j + line] for j in range(0, len(seq), line)]
+            for ch in chunks:
+                parts.append(ch + rnd.choice(["", "", " ", "\t"]) + eol)
+                if rnd.random() < 0.05:
+                    parts.append(eol)                             # blank line inside a record
+        text = "".join(parts)
+        if rnd.random() < 0.3:
+            text = text.rstrip("\r\n")                            # no final newline
+        if case % 10 == 9:
+            text = rnd.choice(["junk" + eol, eol, " "]) + text    # something before the first '>'
+        f = tmp_path / f"fuzz{case}.fa"
+        f.write_bytes(text.encode())
+        p = subprocess.run([CLI, "--selftest-parse", str(f), str(rnd.choice([1, 3, 8]))], capture_output=True, env=env, timeout=60)
+        assert p.returncode == 0 and b"identical" in p.stdout, (case, p.stdout, p.stderr)
+        batch = rnd.choice([1, 2, 5, 17])
+        p = subprocess.run([CLI, "--selftest-stream", str(f), str(width), str(batch), str(rnd.choice([1, 4]))],
+                           capture_output=True, env=env, timeout=60)
+        assert p.returncode == 0 and b"identical" in p.stdout, (case, batch, p.stdout, p.stderr)
