@@ -455,6 +455,9 @@ int selftest_tsv() {
                 char path[] = "/tmp/dg_tsv_selftest_XXXXXX";
                 const int fd = mkstemp(path);
                 if (fd < 0) { perror("mkstemp"); return 1; }
+                // every other case through an O_APPEND descriptor: the writer then keeps ordered write() calls (as for a
+                // pipe) instead of positioned parallel writes
+                if ((cases & 1) && fcntl(fd, F_SETFL, fcntl(fd, F_GETFL) | O_APPEND) < 0) { perror("fcntl"); return 1; }
                 std::string want = "sequence1\tsequence2\tdistance\n";
                 {
                     TsvWriter w(fd, threads);

@@ -8,7 +8,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
 #include <mutex>
+#include <sys/stat.h>
 #include <thread>
 #include <unistd.h>
 
@@ -156,6 +158,16 @@ struct TsvWriter::Pool {
 };
 
 TsvWriter::TsvWriter(int fd, int threads) : fd_(fd), threads_(std::max(1, threads)), pool_(new Pool) {
+    // A regular file that is not in append mode takes positioned writes: the turn only hands out the offset, and the
+    // page-cache copies of different chunks run in parallel.  Pipes, terminals, /dev/null and O_APPEND files keep the
+    // ordered write() calls.
+    struct stat st;
+    const int fl = fcntl(fd, F_GETFL);
+    const off_t cur = lseek(fd, 0, SEEK_CUR);
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && fl >= 0 && !(fl & O_APPEND) && cur >= 0) {
+        positioned_ = true;
+        file_off_ = (uint64_t)cur;
+    }
     for (int t = 1; t < threads_; t++) pool_->threads.emplace_back([this] { worker_loop(); });
 }
 
@@ -182,12 +194,32 @@ void TsvWriter::write_all(const char* p, size_t n) {
     }
 }
 
-void TsvWriter::write_header() {
-    static const char h[] = "sequence1\tsequence2\tdistance\n";  // lib.rs:613
-    write_all(h, sizeof h - 1);
+void TsvWriter::write_at(const char* p, size_t n, uint64_t off) {
+    while (n) {
+        ssize_t w = ::pwrite(fd_, p, n, (off_t)off);
+        if (w < 0) {
+            if (errno == EINTR) continue;
+            throw io_error_os(errno);
+        }
+        p += w;
+        off += (uint64_t)w;
+        n -= (size_t)w;
+    }
 }
 
-void TsvWriter::flush() {}
+void TsvWriter::write_header() {
+    static const char h[] = "sequence1\tsequence2\tdistance\n";  // lib.rs:613
+    if (positioned_) {
+        write_at(h, sizeof h - 1, file_off_);
+        file_off_ += sizeof h - 1;
+    } else {
+        write_all(h, sizeof h - 1);
+    }
+}
+
+void TsvWriter::flush() {
+    if (positioned_) lseek(fd_, (off_t)file_off_, SEEK_SET);   // leave the descriptor where sequential writes would have
+}
 
 namespace {
 constexpr uint64_t kChunk = 1 << 16;   // results per formatting chunk (a few MB of text)
@@ -296,6 +328,27 @@ void TsvWriter::run_chunks() {
         }
         std::unique_lock<std::mutex> lk(P.mu);
         P.cv_turn.wait(lk, [&] { return P.write_turn == c; });
+        if (positioned_) {
+            // my turn = my offset; the copy into the file happens outside the turn, in parallel with the other chunks'
+            const uint64_t off = file_off_;
+            const bool go = err.empty() && P.error.empty();
+            if (go) file_off_ += n;
+            P.write_turn = c + 1;
+            lk.unlock();
+            P.cv_turn.notify_all();
+            if (go) {
+                try {
+                    write_at(buf.data(), n, off);
+                } catch (const DistanceError& e) {
+                    err = e.what();
+                }
+            }
+            if (!err.empty()) {
+                std::lock_guard<std::mutex> lk2(P.mu);
+                if (P.error.empty()) P.error = err;
+            }
+            continue;
+        }
         if (err.empty() && P.error.empty()) {
             lk.unlock();
             try {

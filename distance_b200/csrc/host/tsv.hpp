@@ -7,7 +7,8 @@
 // A panel is cut into chunks of 65,536 results; a persistent pool of `threads` workers (the calling thread is one
 // of them) grabs chunks in order, formats each into a private buffer (ids copied from a packed arena with fixed-size
 // moves, counts through a 65,536-entry text table, floats through an exact 128-bit fixed-point conversion) and issues
-// its write() when its turn comes, so formatting is parallel and the output stays in order.
+// its write() when its turn comes, so formatting is parallel and the output stays in order.  When the output is a
+// regular file (not O_APPEND) the turn only hands out the file offset and the pwrite() calls themselves run in parallel.
 // A BrokenPipe on the output ends the process with status 0 (lib.rs:598-608).
 #pragma once
 #include <cstdint>
@@ -62,6 +63,7 @@ public:
 private:
     struct Pool;
     void write_all(const char* p, size_t n);
+    void write_at(const char* p, size_t n, uint64_t off);
     void worker_loop();
     void run_chunks();
     template <int KIND>
@@ -69,6 +71,8 @@ private:
     int fd_;
     int threads_;
     Pool* pool_;
+    bool positioned_ = false;   // regular, non-append output: chunks are written with pwrite at offsets handed out in order
+    uint64_t file_off_ = 0;
     IdTable ids1_tab_, ids2_tab_;
     const std::vector<std::string>* ids1_ = nullptr;
     const std::vector<std::string>* ids2_ = nullptr;
