@@ -3,9 +3,12 @@
  *
  * A plain-C restatement of the pairwise-comparison hot path of
  * benjamincjackson/distance v0.3.1 (Rust), used as the checker for the CUDA
- * path.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
- * `--impl reference` legs may load this library.  The product (libdistance_gpu)
- * never links, loads or calls anything in this directory.
+ * path.  Only tests/ (incl. the fixture generator tests/golden/make_golden.py),
+ * __graft_entry__.smoke() and the timed CPU baselines (bench.py's cpu_baseline /
+ * `--impl reference` legs; the same bounded-sample baseline in the measurement
+ * script tools/run_configs.py) may load this library.  The product
+ * (libdistance_gpu, the `distance` binary, distance_b200/) never links, loads or
+ * calls anything in this directory.
  *
  * PARITY PIN: the reference is Rust and there is no Rust toolchain in this
  * image, so the reference itself cannot be run here (oracle/_ref does not

@@ -1,8 +1,10 @@
 """ctypes loader for the CPU oracle (oracle/distance_oracle.c).
 
-TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
-cpu_baseline / `--impl reference` legs of bench.py.  Nothing under
-distance_b200/ imports this module.
+TEST INFRASTRUCTURE ONLY: imported by tests/ (incl. tests/golden/make_golden.py),
+__graft_entry__.smoke() and the timed CPU baselines (the cpu_baseline /
+`--impl reference` legs of bench.py and the same bounded-sample baseline of the
+measurement script tools/run_configs.py).  Nothing under distance_b200/ imports
+this module.
 """
 from __future__ import annotations
 
