@@ -4,20 +4,25 @@
     python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                   (the CPU reference arm, rank 0 only)
 
-Workload (BASELINE.json configs[1]): `-m n_high` all-vs-all over 20,000 synthetic SARS-CoV-2-length
-records (29,903 nt, 1% N / ambiguity codes / gaps).  A step = one pass of the hot path
-(pack_planes -> count tiles -> results) over that alignment.  For N>1 the run is WEAK-scaled: the
-alignment grows to n = round(20000 * sqrt(N)) records so every GPU keeps ~2.0e8 pairs per step;
-ranks own disjoint result panels (dg_run_part) and exchange nothing but the timing reductions.
+Headline workload (BASELINE.json configs[1]): `-m n_high` all-vs-all over 20,000 synthetic SARS-CoV-2-length
+records (29,903 nt, 1% N / ambiguity codes / gaps).  A step = one pass of the hot path (operand pack -> count
+tiles -> results) over that alignment.  For N>1 the run is WEAK-scaled: n = round(20000 * sqrt(N)) records so
+every GPU keeps ~2.0e8 pairs per step; ranks own disjoint result panels (dg_run_part) and exchange nothing but
+the timing reductions.
 
-  value : pairs/s, whole job, inputs resident in HBM, device time from CUDA events on the library's
-          compute stream (dg_timings.run_ms), MAX over ranks.
-  e2e   : same metric through the C ABI with HOST buffers: H2D of the codes from pinned memory,
-          pack, tiles, D2H of every result panel into pinned memory and the sink callback, per step.
+  value     : pairs/s, whole job, inputs resident in HBM, device time from CUDA events on the library's compute
+              streams (dg_timings.run_ms), MAX over ranks.
+  e2e       : same metric through the C ABI with HOST buffers: H2D of the codes from pinned memory, pack, tiles,
+              D2H of every result panel into pinned memory and the sink callback, per step.
+  sustained : the same step repeated for >= 3 s with the SM clock and throttle reasons beside it.
+  configs   : BASELINE configs 1, 3, 4, 5 (and 2 again) in the same line: kernel-only ms, pairs/s, roofline
+              fraction, e2e ms, engine and an in-run SAMPLED ORACLE CHECK (>= 2,000 pairs per config, NaN / inf /
+              -0.0 included; outside every timed region; a mismatch aborts the run).
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -36,11 +41,13 @@ MEASURE = "n_high"
 BASE_N = 20000
 WIDTH = 29903
 SEED = 20251018 + 2
+REL_TOL = 1e-12   # north_star: raw / jc69 / k80 / tn93 within 1e-12 relative; counts bit-exact
 # algorithmic 32-bit lane-ops per pair-site (4 LOP3 + 1 POPC + 1 IADD per 32 sites)
 OPS_PER_PAIR_SITE = {"n": 0.1875, "n_high": 0.1875, "raw": 0.28125, "jc69": 0.28125, "k80": 0.5, "tn93": 0.5}
-# tensor engine: int8 ops (2 per MAC) per pair-site of the minimal-rank schedules in tc_engine.cuh / DESIGN.md 3.1
+# tensor engine: ops (2 per MAC) per pair-site of the minimal-rank schedules in tc_engine.cuh / DESIGN.md 3.1
 # (SURVEY 8d budgeted 10 / 10 / 14 / 14; the 4-MAC DIFF and the W/Z factorisation need fewer)
 I8_OPS_PER_PAIR_SITE = {"n": 8, "n_high": 8, "raw": 16, "jc69": 16, "k80": 12, "tn93": 10}
+ENGINE_NAME = {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}
 WORKLOAD = f"config 2: -m {MEASURE} all-vs-all, 20,000 x 29,903 nt (n = round(20000*sqrt(N)) for N GPUs), 1% N/ambiguity/gaps"
 
 
@@ -75,26 +82,29 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t0=None, t1=None):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+    def window(self, t0=None, t1=None):
         rows = [r for ts, r in self.rows if (t0 is None or ts >= t0) and (t1 is None or ts <= t1 + 0.2)]
         if not rows:
             rows = [r for _, r in self.rows]
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except Exception:
                 continue
             for name, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        return self.window(t0, t1)
 
 
 def make_workload(n: int):
@@ -124,7 +134,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     n = int(round(BASE_N * math.sqrt(args.gpus))) if args.n is None else args.n
-    codes = make_workload(min(n, 4000))  # the sample only touches the first rows x all columns
+    n_sample = min(n, 4000)
+    codes = make_workload(n_sample)  # the sample only touches the first rows x all columns
     threads = os.cpu_count() or 1
     from oracle import oracle as orc
     a = orc.Alignment(codes)
@@ -148,7 +159,10 @@ def run_reference(args):
         "ms_per_step": 1e3 * tot_s / args.steps, "higher_is_better": True, "scaling": "weak" if args.n is None else "strong",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "measure": MEASURE, "n": n, "width": WIDTH,
-                   "reference_arm_sample": sample},
+                   "reference_arm_records": n_sample, "reference_arm_rows_per_step": rows,
+                   "reference_arm_sample": sample,
+                   "reference_arm_note": "the CPU arm times a bounded sample (the first rows of an alignment truncated to "
+                                         f"{n_sample} records): CPU pairs/s does not depend on n, the per-pair cost is O(width)"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (C oracle), not the Rust binary: no Rust toolchain in this image",
@@ -157,12 +171,376 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# sampled oracle check (outside every timed region)
+# ---------------------------------------------------------------------------------------------------------------
+class ParityError(RuntimeError):
+    pass
+
+
+def compare_sample(measure, got, want, where):
+    """counts bit-exact; floats: NaN / +-inf / +-0.0 in the same places, the rest within REL_TOL.  Returns the
+    number of NaN, inf and zero (incl. -0.0) values the sample hit."""
+    got, want = np.asarray(got), np.asarray(want)
+    if measure in ("n", "n_high"):
+        if not np.array_equal(got.astype(np.int64), want.astype(np.int64)):
+            bad = np.flatnonzero(got.astype(np.int64) != want.astype(np.int64))[:5]
+            raise ParityError(f"{where}: counts differ at sample positions {bad.tolist()}: got {got[bad].tolist()} want {want[bad].tolist()}")
+        return {"nan": 0, "inf": 0, "zero": int((want == 0).sum())}
+    got, want = got.astype(np.float64), want.astype(np.float64)
+    nan_w, inf_w = np.isnan(want), np.isinf(want)
+    if not np.array_equal(np.isnan(got), nan_w):
+        raise ParityError(f"{where}: NaN positions differ")
+    if not (np.array_equal(np.isinf(got), inf_w) and np.array_equal(got[inf_w], want[inf_w])):
+        raise ParityError(f"{where}: inf positions / signs differ")
+    fin = ~(nan_w | inf_w)
+    g, w = got[fin], want[fin]
+    zero = w == 0.0
+    if not (np.array_equal(g[zero], w[zero]) and np.array_equal(np.signbit(g[zero]), np.signbit(w[zero]))):
+        raise ParityError(f"{where}: zeros (sign of -0.0 included) differ")
+    rel = np.abs(g[~zero] - w[~zero]) / np.abs(w[~zero])
+    if rel.size and rel.max() > REL_TOL:
+        raise ParityError(f"{where}: max relative error {rel.max():.3e} > {REL_TOL}")
+    return {"nan": int(nan_w.sum()), "inf": int(inf_w.sum()), "zero": int(zero.sum())}
+
+
+def oracle_pairs(measure, row_codes, col_codes, swap=False):
+    """The oracle's per-pair functions (C port of measures.rs) for one row record against some column records.
+    swap: stream mode, where the streamed (row) record is the reference's `target` (lib.rs:322-325)."""
+    from oracle import oracle as orc
+    if measure in ("n", "n_high"):
+        return np.array([orc.snp(row_codes, c) for c in col_codes], dtype=np.int64)
+    if measure == "tn93":
+        rc = orc.count_bases(row_codes)
+        out = []
+        for c in col_codes:
+            cc = orc.count_bases(c)
+            out.append(orc.tn93(c, row_codes, cc, rc) if swap else orc.tn93(row_codes, c, rc, cc))
+        return np.array(out)
+    f = {"raw": orc.raw, "jc69": orc.jc69, "k80": orc.k80}[measure]
+    return np.array([f(c, row_codes) if swap else f(row_codes, c) for c in col_codes])
+
+
+def merge_hits(a, b):
+    return {k: a.get(k, 0) + b.get(k, 0) for k in set(a) | set(b)}
+
+
+def spike(asc, rng):
+    """Three planted records so that the sampled check meets the special values: an all-N record (no compared site:
+    NaN), a copy of its neighbour (identical pair: -0.0 / 0.0), a random-base record (saturated distances)."""
+    n, w = asc.shape
+    if n >= 8:
+        asc[3, :] = ord("N")
+        asc[5, :] = asc[4, :]
+        asc[7, :] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=w)]
+    return asc
+
+
+class RowGrabber:
+    """A sink that keeps the result rows of a few sampled major rows (everything else is only counted)."""
+
+    def __init__(self, api, mode, n_rows_total, n_cols, dtype, rows):
+        self.api, self.mode, self.n, self.n_cols, self.dtype = api, mode, n_rows_total, n_cols, np.dtype(dtype)
+        self.rows = {int(r): None for r in rows}
+        self.pairs = 0
+        self.cb = api.SINK_FN(self._sink)
+
+    def _sink(self, user, pp):
+        p = pp.contents
+        r0, r1 = int(p.row_begin), int(p.row_end)
+        self.pairs += int(p.n_results)
+        isz = self.dtype.itemsize
+        for r in self.rows:
+            if r0 <= r < r1:
+                if self.mode == self.api.DG_MODE_SQUARE:
+                    off = r * (2 * self.n - r - 1) // 2 - r0 * (2 * self.n - r0 - 1) // 2
+                    ln = self.n - 1 - r
+                else:
+                    off, ln = (r - r0) * self.n_cols, self.n_cols
+                if ln:
+                    buf = (C.c_uint8 * (ln * isz)).from_address(p.data + off * isz)
+                    self.rows[r] = np.frombuffer(buf, dtype=self.dtype, count=ln).copy()
+                else:
+                    self.rows[r] = np.zeros(0, self.dtype)
+        return 0
+
+
+def sample_rows_of(panels, specials, rng, per_panel=2, max_panels=4):
+    """rows to check: the planted special rows that fall into this rank's panels + a few rows of a few panels"""
+    rows = set()
+    if not panels:
+        return []
+    pick = [panels[0], panels[-1]] + [panels[i] for i in rng.integers(0, len(panels), size=max(0, max_panels - 2))]
+    for (r0, r1, _) in pick:
+        rows.update({r0, r1 - 1})
+        rows.update(int(x) for x in rng.integers(r0, r1, size=per_panel))
+    for r in specials:
+        if any(r0 <= r < r1 for (r0, r1, _) in panels):
+            rows.add(r)
+    return sorted(rows)
+
+
+def check_rows(measure, mode_name, grab, row_codes_of, col_codes_of, n_cols_total, rng, per_row, label, swap=False):
+    """Compare `per_row` columns of every grabbed row with the oracle."""
+    hits, n_checked = {}, 0
+    for r, vals in grab.rows.items():
+        if vals is None:
+            raise ParityError(f"{label}: sampled row {r} never reached the sink")
+        first = r + 1 if mode_name == "square" else 0
+        avail = n_cols_total - first
+        if avail <= 0:
+            continue
+        k = min(per_row, avail)
+        cols = np.unique(np.concatenate([rng.integers(first, n_cols_total, size=k), np.arange(first, min(n_cols_total, first + 24)),
+                                         [n_cols_total - 1]]))
+        specials = [c for c in (3, 4, 5, 7) if first <= c < n_cols_total]
+        cols = np.unique(np.concatenate([cols, np.array(specials, dtype=cols.dtype)])) if specials else cols
+        want = oracle_pairs(measure, row_codes_of(r), [col_codes_of(int(c)) for c in cols], swap=swap)
+        got = vals[cols - first]
+        hits = merge_hits(hits, compare_sample(measure, got, want, f"{label} row {r}"))
+        n_checked += int(cols.size)
+    return n_checked, hits
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE configs 1, 3, 4, 5 (+ 2): one entry each in the JSON line
+# ---------------------------------------------------------------------------------------------------------------
+def fp4_peak_tops():
+    peaks = load_json(os.path.join(ROOT, "profiles", "int_peaks.json")) or {}
+    return peaks.get("fp4_tops_measured") or 9000.0, peaks.get("int8_tops_measured") or 4500.0
+
+
+def tensor_frac(measure, pairs, ms, n_gpus, engine):
+    fp4, i8 = fp4_peak_tops()
+    peak = fp4 if engine == 3 else i8
+    if engine not in (2, 3) or ms <= 0:
+        return None
+    return pairs * WIDTH * I8_OPS_PER_PAIR_SITE[measure] / (ms * 1e-3) / 1e12 / (peak * n_gpus)
+
+
+def pinned_copy(api, a):
+    p = api.pinned_array(a.shape, np.uint8)
+    p[...] = a
+    return p
+
+
+def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api, synth, parts_of=None):
+    """All-vs-all (b_asc None) or two-file run of one config on this rank's part: kernel-only, pipelined e2e, sampled
+    oracle check.  Inputs are ASCII (the LUT of encoding.rs runs on the device: DG_INPUT_ASCII)."""
+    rank, world = d.rank, d.world
+    part, parts = parts_of if parts_of else (rank, world)
+    mode = api.DG_MODE_SQUARE if b_asc is None else api.DG_MODE_RECT
+    mode_name = "square" if b_asc is None else "rect"
+    lut = synth.ascii_lut()
+    is_int = measure in ("n", "n_high")
+    eng = dg.Engine(measure, WIDTH, gpus=[d.local_rank])
+    eng.set_option(api.DG_OPT_KEEP_CODES, 1)
+    if is_int:
+        eng.set_option(api.DG_OPT_RESULT_U16, 1)
+        eng.set_option(api.DG_OPT_PANEL_BYTES, 128 << 20)
+    pa = pinned_copy(api, a_asc)
+    pb = None if b_asc is None else pinned_copy(api, b_asc)
+    eng.load(0, pa, input_kind=api.DG_INPUT_ASCII)
+    if pb is not None:
+        eng.load(1, pb, input_kind=api.DG_INPUT_ASCII)
+    plan = eng.plan(mode)
+    mine = [p for k, p in enumerate(plan) if k % parts == part]
+    my_pairs = sum(p[2] for p in mine)
+    n_rows, n_cols = a_asc.shape[0], (a_asc.shape[0] if b_asc is None else b_asc.shape[0])
+    # kernel-only
+    for _ in range(2):
+        eng.run_device_only(mode, part, parts, repack=True)
+    d.barrier()
+    eng.reset_timings()
+    ms = 0.0
+    for _ in range(args.cfg_steps):
+        eng.run_device_only(mode, part, parts, repack=True)
+        ms += eng.timings()["run_ms"]
+    d.barrier()
+    tm = eng.timings()
+    k_ms = d.max(ms / args.cfg_steps)
+    pairs = int(d.sum(my_pairs))
+    engine = int(tm["engine"])
+    # e2e: the pipelined session from pinned host memory (alignment 1 of a two-file run is uploaded inside the step too)
+    state = {"n": 0}
+
+    def sink(user, pp):
+        state["n"] += int(pp.contents.n_results)
+        return 0
+
+    cb = api.SINK_FN(sink)
+
+    def e2e_step():
+        state["n"] = 0
+        if pb is None:
+            eng._check(eng.L.dg_run_square_host(eng.h, C.c_void_p(pa.ctypes.data), n_rows, api.DG_INPUT_ASCII, None, part, parts, cb, None))
+        else:
+            eng.load(1, pb, input_kind=api.DG_INPUT_ASCII)
+            eng._check(eng.L.dg_run_rect_host(eng.h, C.c_void_p(pa.ctypes.data), n_rows, api.DG_INPUT_ASCII, None, part, parts, cb, None))
+        return state["n"]
+
+    e2e_step()
+    d.barrier()
+    t0 = time.time()
+    for _ in range(args.cfg_e2e_steps):
+        got_n = e2e_step()
+    d.barrier()
+    e2e_ms = d.max(1e3 * (time.time() - t0) / args.cfg_e2e_steps)
+    e2e_pairs = int(d.sum(got_n))
+    # sampled oracle check through the in-order path (dg_load_resident + dg_run_part): resident again after the session
+    rng = np.random.default_rng(1000 + cfg_id * 10 + rank)
+    eng.load(0, pa, input_kind=api.DG_INPUT_ASCII)
+    rows = sample_rows_of(mine, (3, 4, 5, 7), rng)
+    dtype = (np.uint16 if is_int else np.float64)
+    grab = RowGrabber(api, mode, n_rows, n_cols, dtype, rows)
+    eng._check(eng.L.dg_run_part(eng.h, mode, part, parts, grab.cb, None, 0))
+    if grab.pairs != my_pairs:
+        raise ParityError(f"{label}: the sink saw {grab.pairs} results, the plan has {my_pairs}")
+    cols_asc = a_asc if b_asc is None else b_asc
+    n_chk, hits = check_rows(measure, mode_name, grab, lambda r: lut[a_asc[r]], lambda c: lut[cols_asc[c]], n_cols, rng,
+                             max(64, 2400 // max(1, len(rows))), label)
+    n_chk = int(d.sum(n_chk))
+    hits = {k: int(d.sum(v)) for k, v in sorted(hits.items())} if hits else {}
+    eng.close()
+    elem = 2 if is_int else 8
+    return {"id": cfg_id, "workload": label, "measure": measure, "mode": mode_name, "pairs": pairs,
+            "kernel_ms": k_ms, "pairs_per_s": pairs / (k_ms * 1e-3), "pair_sites_per_s": pairs * WIDTH / (k_ms * 1e-3),
+            "roofline_frac": tensor_frac(measure, pairs, k_ms, world, engine), "engine": ENGINE_NAME.get(engine, "?"),
+            "sm_mhz_in_kernel": tm.get("sm_mhz"),
+            "e2e_ms": e2e_ms, "e2e_pairs_per_s": e2e_pairs / (e2e_ms * 1e-3),
+            "h2d_bytes_per_step": int(a_asc.nbytes + (0 if b_asc is None else b_asc.nbytes)), "d2h_bytes_per_step": int(my_pairs * elem),
+            "parity_sampled": "ok", "parity_pairs": n_chk, "special_values_hit": hits,
+            "part": f"rank r runs part r of {parts}" if world > 1 or parts > 1 else "whole job"}
+
+
+def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
+    """BASELINE config 4: 1,000 resident records against 1,000,000 streamed ones (every rank streams 1/N of them) in
+    pinned double-buffered batches.  The two staging buffers of the ring are filled once with two different chunks of a
+    synthetic pool (a parser would write the next batch there: dg_stream_buffer) and pushed over and over, so a step
+    moves 29.9 GB / N over PCIe without a host-side copy in the way."""
+    rank, world = d.rank, d.world
+    lut = synth.ascii_lut()
+    rng = np.random.default_rng(1000 + cfg_id * 10 + rank)
+    root = synth.make_root(WIDTH, 20251018 + 4)
+    res_asc = spike(synth.make_alignment(1000, seed=20251018 + 4, ambiguity=True, root=root), rng)
+    batch = 4096
+    pool_asc = spike(synth.make_alignment(2 * batch, seed=20251018 + 44 + rank, ambiguity=True, root=root), rng)
+    total = args.stream_records // world
+    eng = dg.Engine(measure, WIDTH, gpus=[d.local_rank])
+    eng.load(0, res_asc, input_kind=api.DG_INPUT_ASCII)
+    L = eng.L
+    st = {"n": 0, "batches": 0, "keep": {}}
+
+    def sink(user, pp):
+        p = pp.contents
+        cnt = int(p.n_results)
+        st["n"] += cnt
+        b = st["batches"]
+        if b in st["keep"] and st["keep"][b] is None:
+            st["keep"][b] = np.frombuffer((C.c_uint8 * (cnt * 8)).from_address(p.data), dtype=np.float64, count=cnt).copy()
+        st["batches"] += 1
+        return 0
+
+    cb = api.SINK_FN(sink)
+    buf, cap = C.c_void_p(), C.c_uint64()
+
+    def session(n_records, fill):
+        st["n"], st["batches"] = 0, 0
+        eng._check(L.dg_stream_begin(eng.h, cb, None, batch))
+        done, k = 0, 0
+        while done < n_records:
+            nb = min(batch, n_records - done)
+            eng._check(L.dg_stream_buffer(eng.h, C.byref(buf), C.byref(cap)))
+            if fill and k < 2:   # the ring has two staging buffers per device: slot k % 2 keeps pool chunk k % 2
+                C.memmove(buf.value, pool_asc[k * batch:(k + 1) * batch].ctypes.data, batch * WIDTH)
+            eng._check(L.dg_stream_push(eng.h, buf, nb, api.DG_INPUT_ASCII, None))
+            done += nb
+            k += 1
+        eng._check(L.dg_stream_end(eng.h))
+        return st["n"]
+
+    session(4 * batch, True)     # warm-up + fills both staging buffers
+    d.barrier()
+    eng.reset_timings()
+    t0 = time.time()
+    for _ in range(args.cfg_e2e_steps):
+        got = session(total, False)
+    d.barrier()
+    wall_ms = d.max(1e3 * (time.time() - t0) / args.cfg_e2e_steps)
+    tm = eng.timings()
+    dev_ms = d.max((tm["count_ms"] + tm["pack_ms"]) / args.cfg_e2e_steps)
+    pairs = int(d.sum(got))
+    engine = int(tm["engine"])
+    # sampled check: batches 0, 1 and a late one; batch k holds pool chunk k % 2
+    n_b = (total + batch - 1) // batch
+    st["keep"] = {k: None for k in sorted({0, 1, max(0, n_b - 2)})}
+    session(total, False)
+    hits, n_chk = {}, 0
+    for k, vals in st["keep"].items():
+        if vals is None:
+            raise ParityError(f"{label}: batch {k} never reached the sink")
+        rows_in = vals.size // 1000
+        chunk = pool_asc[(k % 2) * batch:(k % 2) * batch + rows_in]
+        for r in sorted(set([0, 3, 4, 5, 7, rows_in - 1] + [int(x) for x in rng.integers(0, rows_in, size=2)])):
+            if r >= rows_in:
+                continue
+            cols = np.unique(np.concatenate([rng.integers(0, 1000, size=100), [0, 3, 4, 5, 7, 999]]))
+            want = oracle_pairs(measure, lut[chunk[r]], [lut[res_asc[int(c)]] for c in cols], swap=True)
+            hits = merge_hits(hits, compare_sample(measure, vals.reshape(rows_in, 1000)[r, cols], want, f"{label} batch {k} row {r}"))
+            n_chk += int(cols.size)
+    n_chk = int(d.sum(n_chk))
+    hits = {k: int(d.sum(v)) for k, v in sorted(hits.items())}
+    eng.close()
+    return {"id": cfg_id, "workload": label, "measure": measure, "mode": "stream", "pairs": pairs,
+            "kernel_ms": dev_ms, "pairs_per_s": pairs / (dev_ms * 1e-3), "pair_sites_per_s": pairs * WIDTH / (dev_ms * 1e-3),
+            "kernel_note": "sum of the per-batch device spans (operand pack + tiles + combine, CUDA events)",
+            "roofline_frac": tensor_frac(measure, pairs, dev_ms, world, engine), "engine": ENGINE_NAME.get(engine, "?"),
+            "sm_mhz_in_kernel": tm.get("sm_mhz"),
+            "e2e_ms": wall_ms, "e2e_pairs_per_s": pairs / (wall_ms * 1e-3),
+            "h2d_bytes_per_step": int(total * WIDTH), "d2h_bytes_per_step": int(total * 1000 * 8),
+            "h2d_gbs": total * WIDTH / (wall_ms * 1e-3) / 1e9,
+            "streamed_records": total * world, "batch": batch,
+            "parity_sampled": "ok", "parity_pairs": n_chk, "special_values_hit": hits,
+            "part": f"every rank streams {total} records" if world > 1 else "whole job"}
+
+
+def run_configs(d, args, dg, api, synth):
+    out = []
+    want = [int(x) for x in args.configs.split(",") if x]
+    rng = np.random.default_rng(77)
+    if 1 in want:
+        asc = spike(synth.make_alignment(1000, seed=20251018 + 1, ambiguity=True), rng)
+        out.append(config_square_or_rect(1, "config 1: -m raw all-vs-all, 1,000 x 29,903", "raw", asc, None, d, args, dg, api, synth))
+    if 2 in want:
+        n2 = BASE_N if args.n is None else args.n
+        asc = spike(synth.make_alignment(n2, seed=SEED, ambiguity=True), rng)
+        out.append(config_square_or_rect(2, f"config 2: -m n all-vs-all, {n2:,} x 29,903, 1% N/ambiguity/gaps (strong-scaled over the ranks)",
+                                         "n", asc, None, d, args, dg, api, synth))
+    if 3 in want:
+        root = synth.make_root(WIDTH, 20251018 + 3)
+        a = spike(synth.make_alignment(10000, seed=20251018 + 3, ambiguity=True, root=root), rng)
+        b = spike(synth.make_alignment(10000, seed=20251018 + 33, ambiguity=True, root=root), rng)
+        out.append(config_square_or_rect(3, "config 3: -m tn93 between two alignments, 10,000 x 10,000 x 29,903", "tn93", a, b, d, args, dg, api, synth))
+    if 4 in want:
+        out.append(config_stream(4, f"config 4: -m k80, -i 1,000 resident vs -s {args.stream_records:,} streamed records (pinned double-buffered batches)",
+                                 "k80", d, args, dg, api, synth))
+    if 5 in want:
+        n5 = args.n5
+        asc = spike(synth.make_alignment(n5, seed=20251018 + 5, ambiguity=True), rng)
+        parts = max(8, d.world)
+        share = "the whole job" if d.world >= 8 else f"{d.world}/8 of the job: rank r computes part r of 8 (what GPU r of 8 B200s does)"
+        out.append(config_square_or_rect(5, f"config 5: -m jc69 all-vs-all, {n5:,} x 29,903 -- {share}", "jc69", asc, None, d, args, dg, api, synth,
+                                         parts_of=(d.rank, parts)))
+        del asc
+    return out
+
+
 def run_ours(args):
     # a hung collective or kernel must not sit on the GPUs until an outer limit fires: dump every thread's stack and exit
     import faulthandler
     faulthandler.dump_traceback_later(args.watchdog, exit=True)
     import distance_b200 as dg
-    from distance_b200 import api, dist
+    from distance_b200 import api, dist, synth
 
     d = dist.Dist()
     rank, world = d.rank, d.world
@@ -240,6 +618,34 @@ def run_ours(args):
     value = total_pairs / (step_ms * 1e-3)
     launches = int(d.sum(tm["pack_launches"] + tm["count_launches"]))
     count_launch_ms = tm["count_ms"] / max(tm["count_launches"], 1)
+    sm_mhz_burst = tm.get("sm_mhz")
+
+    # ---- sustained: the same step back to back for >= args.sustained_s seconds -----------------------------------------
+    sustained = None
+    if args.sustained_s > 0:
+        sync_all()
+        eng.reset_timings()
+        ts0 = time.time()
+        s_dev, s_steps = 0.0, 0
+        while True:
+            for _ in range(16):
+                eng.run_device_only(api.DG_MODE_SQUARE, rank, world, repack=True)
+                s_dev += eng.timings()["run_ms"]
+            s_steps += 16
+            # every rank runs the same number of steps: decide together
+            if d.max(time.time() - ts0) >= args.sustained_s:
+                break
+        sync_all()
+        ts1 = time.time()
+        s_ms = d.max(s_dev / s_steps)
+        s_wall_ms = d.max(1e3 * (ts1 - ts0) / s_steps)
+        clk = sampler.window(ts0 + 0.2, ts1)
+        sustained = {"seconds": ts1 - ts0, "steps": s_steps, "ms_per_step": s_ms, "value": total_pairs / (s_ms * 1e-3), "unit": "pairs/s",
+                     "wall_ms_per_step": s_wall_ms, "value_by_wall_clock": total_pairs / (s_wall_ms * 1e-3),
+                     "sm_mhz_in_kernel": eng.timings().get("sm_mhz"), "clocks": clk,
+                     "burst_value": value, "sustained_over_burst": (total_pairs / (s_ms * 1e-3)) / value,
+                     "note": "device time per step from CUDA events, steps back to back; sm_mhz_in_kernel = clock64 / globaltimer inside "
+                             "the GEMM launches (nvidia-smi's 200 ms samples are in `clocks`)"}
 
     # ---- e2e: host buffers through the C ABI ----------------------------------------------------
     # The pipelined session (dg_square_*): chunks of the alignment go up highest records first, so the PCIe upload,
@@ -249,7 +655,6 @@ def run_ours(args):
     #           NCCL all-gather over NVLink completes it on every GPU, and the session takes its chunks from that device
     #           buffer (per-chunk collectives were faster at N = 2 but tie every rank's progress to every other rank's
     #           host; one collective per step keeps the ranks independent).
-    import ctypes as C
     e2e_state = {"n": 0, "acc": 0}
 
     def e2e_sink(user, pp):
@@ -321,10 +726,24 @@ def run_ours(args):
             assert eng.run_discard(api.DG_MODE_SQUARE, rank, world) == my_pairs
         e2e_inorder_ms = 1e3 * (time.time() - t0i) / max(3, args.steps // 3)
         t1 = time.time()
-    clocks = sampler.stop(t_wall0, t1)
+    clocks = sampler.window(t_wall0, t_wall1)
+    clocks["sm_mhz_in_kernel"] = sm_mhz_burst
+    clocks["note"] = ("sm_mhz = median of nvidia-smi's 200 ms samples over the timed region; sm_mhz_in_kernel = clock64 / globaltimer "
+                      "around the GEMM launches of the timed steps (CTA 0), which sees the dips the 200 ms samples miss")
 
-    # ---- roofline of the dominant kernel (count_tile_kernel) ------------------------------------
-    # achieved = algorithmic lane-ops of this rank's launches / device time of those launches.
+    # ---- headline parity: sampled rows of this rank's panels against the oracle (outside the timed regions) ---------------
+    rng = np.random.default_rng(2000 + rank)
+    eng.load(0, pinned)
+    mine = dist.my_panels(plan, rank, world)
+    rows = sample_rows_of(mine, (), rng)
+    grab = RowGrabber(api, api.DG_MODE_SQUARE, n, n, np.uint16 if (args.is_int and not args.u32_results) else (np.uint32 if args.is_int else np.float64), rows)
+    eng._check(eng.L.dg_run_part(eng.h, api.DG_MODE_SQUARE, rank, world, grab.cb, None, 0))
+    assert grab.pairs == my_pairs
+    head_chk, head_hits = check_rows(MEASURE, "square", grab, lambda r: codes[r], lambda c: codes[c], n, rng,
+                                     max(64, 2400 // max(1, len(rows))), "headline")
+    head_chk = int(d.sum(head_chk))
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------------------------
     ops = my_pairs * WIDTH * OPS_PER_PAIR_SITE[MEASURE]
     count_ms_step = tm["count_ms"] / args.steps
     run_ms_step = dev_ms / args.steps
@@ -396,7 +815,8 @@ def run_ours(args):
                     "scores the same time against SURVEY 8d's 5-MAC budget.  padded_frac counts the 49 zero-padded "
                     "sites per K block as work done.  Engine chosen automatically (DG_OPT_ENGINE=0): E2M1 operands "
                     "with unit block scales and fp32 accumulation are exact for these integer sums (tools/ubench_fp4, "
-                    "parity suite), so the fp4 tensor rate applies; frac_of_int8_peak scores the same ops against kind::i8.",
+                    "parity suite; widths above 2^22 - 256 sites route to kind::i8), so the fp4 tensor rate applies; "
+                    "frac_of_int8_peak scores the same ops against kind::i8.",
         }
     else:
         roofline = roofline_lop3
@@ -415,6 +835,14 @@ def run_ours(args):
                      "ms": pack_ms_step,
                      "note": "timed alone (DG_OPT_REPACK_OVERLAP=0: %.3f ms per step with the packing serialised in front of the tiles); in the "
                              "timed steps the packing of the next panel's records overlaps the tiles of the current one" % serial_step_ms}
+    eng.close()
+    del pinned
+
+    # ---- the other BASELINE configs ------------------------------------------------------------------------------------------
+    configs = []
+    if args.configs:
+        configs = run_configs(d, args, dg, api, synth)
+    sampler.stop()
 
     line = None
     if rank == 0:
@@ -447,11 +875,12 @@ def run_ours(args):
                     "in_order_note": "dg_load_resident + dg_run_square: same bytes, panels in the reference's output order (no overlap of upload and tiles)",
                     "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
                     "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
-            "gpu_launches": launches, "engine": {1: "lop3_popc", 2: "tcgen05_i8", 3: "tcgen05_mxf4"}.get(engine_id, "?"),
+            "gpu_launches": launches, "engine": ENGINE_NAME.get(engine_id, "?"),
+            "parity_sampled": "ok", "parity_pairs": head_chk,
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
+            "sustained": sustained, "configs": configs,
         }
         print(json.dumps(line), file=OUT, flush=True)
-    eng.close()
     d.close()
     return 0
 
@@ -476,12 +905,19 @@ def main():
     ap.add_argument("--engine", type=int, default=0, help="DG_OPT_ENGINE: 0 auto, 1 LOP3+POPC, 2 tcgen05 int8, 3 tcgen05 fp4")
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--watchdog", type=int, default=420, help="seconds after which a stuck run dumps its stacks and exits")
+    ap.add_argument("--watchdog", type=int, default=900, help="seconds after which a stuck run dumps its stacks and exits")
     ap.add_argument("--trace-e2e", action="store_true", help="after the timed steps, print rank 0's device timeline of one e2e session (DG_TRACE)")
     ap.add_argument("--no-repack-overlap", action="store_true", help="pack every operand plane before the first tile (DG_OPT_REPACK_OVERLAP=0)")
     ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
     ap.add_argument("--measure", default="n_high", choices=sorted(OPS_PER_PAIR_SITE),
                     help="default n_high = BASELINE config 2 (the driver's workload); jc69 + --n 100000 = config 5")
+    ap.add_argument("--configs", default="1,2,3,4,5", help="BASELINE configs measured next to the headline (\"\" = none)")
+    ap.add_argument("--no-configs", dest="configs", action="store_const", const="")
+    ap.add_argument("--cfg-steps", type=int, default=3, help="kernel-only steps per extra config")
+    ap.add_argument("--cfg-e2e-steps", type=int, default=2, help="e2e steps per extra config")
+    ap.add_argument("--stream-records", type=int, default=1000000, help="config 4: streamed records per step (whole job)")
+    ap.add_argument("--n5", type=int, default=100000, help="config 5: records of the all-vs-all")
+    ap.add_argument("--sustained-s", type=float, default=3.0, help="seconds of back-to-back steps for the `sustained` record (0 = skip)")
     args = ap.parse_args()
     global MEASURE, WORKLOAD
     if args.measure != MEASURE or args.n is not None:
@@ -495,7 +931,11 @@ def main():
         args.panel_bytes = (256 << 20) if args.u32_results else (128 << 20)
     if args.impl == "reference":
         return run_reference(args)
-    return run_ours(args)
+    try:
+        return run_ours(args)
+    except ParityError as e:
+        print(f"bench.py: PARITY MISMATCH against the oracle: {e}", file=sys.stderr, flush=True)
+        return 3
 
 
 if __name__ == "__main__":

@@ -61,7 +61,7 @@ class Timings(C.Structure):
         ("pack_ms", C.c_double), ("count_ms", C.c_double), ("h2d_ms", C.c_double),
         ("total_ms", C.c_double), ("run_ms", C.c_double), ("pack_launches", C.c_uint64), ("count_launches", C.c_uint64),
         ("pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("engine", C.c_uint64),
+        ("engine", C.c_uint64), ("sm_mhz", C.c_double),
     ]
 
     def as_dict(self):

@@ -138,6 +138,7 @@ struct Device {
     size_t out_cap = 0;   // bytes of d_out / h_out
     size_t in_cap = 0;    // records of stream staging
     cudaEvent_t run_start = nullptr, run_stop = nullptr;
+    unsigned long long* clk_probe = nullptr;   // DG_CLOCK_PROBE: SM clocks / ns accumulated by the GEMM launches (debug)
     // load-path scratch, allocated once (no cudaMalloc / cudaFree on the per-load path)
     uint32_t* pp_cnt = nullptr;     // [width] partial codes per site
     uint32_t* pp_cursor = nullptr;  // [width]
@@ -202,12 +203,21 @@ struct dg_ctx {
     int tile_variant = 0;
     int engine = 0;       // DG_OPT_ENGINE
     int last_engine = 0;  // engine the last run used (1 LOP3, 2 tcgen05 int8, 3 tcgen05 fp4)
-    bool want_fp4() const { return engine == 0 || engine == 3; }   // operand format of the tensor engine
+    // Exactness limits of the tensor engines (per site a raw sum moves by at most 4: tc_engine.cuh header):
+    //   kind::mxf4 accumulates in fp32: integer sums are exact while 4 * (padded width) < 2^24;
+    //   kind::i8 accumulates in int32 (4 * width < 2^31); the partial-code index packs the site in 28 bits and the TMA
+    //   x coordinate (plane * bytes per plane) is an int, so the int8 engine takes widths below 2^27.
+    // auto falls through fp4 -> int8 -> LOP3+POPC tiles (uint32 counts, any width below 2^31).
+    bool fp4_exact() const { return width <= (1ull << 22) - 256; }
+    bool i8_ok() const { return width < (1ull << 27); }
+    bool tc_wanted() const { return engine >= 2 || (engine == 0 && i8_ok()); }
+    bool want_fp4() const { return engine == 3 || (engine == 0 && fp4_exact()); }   // operand format of the tensor engine
     // invalid-site report
     bool have_invalid = false;
     uint64_t inv_record = 0, inv_site = 0;
     uint8_t inv_byte = 0;
     dg_timings tm{};
+    double clk_cycles = 0, clk_ns = 0;   // harvest_clock
     // stream session
     bool streaming = false;
     bool s_tc = false;  // this stream session runs its batches on the tcgen05 engine
@@ -240,6 +250,12 @@ struct dg_ctx {
     bool sq_trace = false;
     std::vector<int> sq_trace_panel;   // panel index of the n-th launch
 
+    // auto engine: both-partial repairs (one atomic each) the tensor engine may spend per pair before the LOP3 tiles (no
+    // repair, but ~6x the time per pair-site) are the better choice; the tiles' time grows with the width, so does the budget
+    double pp_budget() const { return 2.0 * std::max(1.0, (double)width / 29903.0); }
+    // panel planner inputs: tile width of the tensor engine this context would run and work items (accumulators) per tile
+    uint64_t plan_tn() const { return want_fp4() ? 240 : 256; }
+    uint64_t plan_items() const { static const uint64_t it[4] = {1, 2, 3, 5}; return it[fam]; }
     bool result_u16 = false;  // DG_OPT_RESULT_U16: n / n_high panels hold uint16 counts (needs width <= 65535)
     bool u16() const { return measure <= 1 && result_u16; }
     size_t elem_bytes() const { return measure <= 1 ? (u16() ? 2 : 4) : 8; }
@@ -487,6 +503,32 @@ void finish_pp_index(dg_ctx* c, Device& d, PlaneSet& s, cudaStream_t st, bool fr
     c->tm.pack_launches += 2;
 }
 
+// Two kernels share an SM only when they want the same shared-memory / L1 split.  The persistent GEMM needs the
+// maximum carve-out; kernels with (almost) no shared memory get a small one by default, so the combine / packing /
+// repair launches of the other stream would wait for the GEMM's CTAs to drain instead of running beside them (f64 and
+// LSU work next to the tensor pipe).  Ask for the same carve-out for every side kernel of this device.
+template <typename K>
+void prefer_max_carveout(K kernel) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+}
+void set_side_kernel_carveouts() {
+    if (std::getenv("DG_NO_CARVEOUT")) return;   // A/B switch for the overlap measurements
+    prefer_max_carveout(tc::tc_combine_kernel);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_SNP>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_SNP>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_RAW>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_RAW>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_K80>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_K80>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_TN93>); prefer_max_carveout(tc::pack_ops_kernel<false, FAM_TN93>);
+    prefer_max_carveout(tc::pp_correct_kernel);
+    prefer_max_carveout(tc::pp_correct_chunks_kernel);
+    prefer_max_carveout(tc::pp_correct_scan_kernel<true>);
+    prefer_max_carveout(tc::pp_correct_scan_kernel<false>);
+    prefer_max_carveout(tc::pp_scan_chunk_kernel);
+    prefer_max_carveout(tc::pp_scatter_kernel);
+    prefer_max_carveout(tc::pp_fill_kernel);
+    prefer_max_carveout(tc::build_tile_list_kernel);
+    prefer_max_carveout(tc::publish_invalid_kernel);
+}
+
 int g_num_sms(int dev) {
     int v = 148;
     cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
@@ -497,7 +539,7 @@ int g_num_sms(int dev) {
 // auto -> tensor cores when the operands exist and the both-partial correction is cheap relative to the
 // GEMM (adversarially ambiguous alignments stay on the LOP3 tiles, which need no correction).
 bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
-    if (c->engine == 1) return false;
+    if (!c->tc_wanted()) return false;
     if (!A.tc_ready || !B.tc_ready || A.tc_fp4 != B.tc_fp4 || A.tc_fp4 != c->want_fp4()) {
         if (c->engine >= 2) fail(DG_ERR_STATE, "tensor-engine operands were not built for this engine (set DG_OPT_ENGINE before loading)");
         return false;
@@ -505,12 +547,67 @@ bool use_tc(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B) {
     if (c->engine >= 2) return true;
     if (!tc_schedule(c->fam).needs_pp) return true;
     const double work = std::sqrt(A.pp.pair_work * B.pp.pair_work);
-    return work <= 2.0 * (double)A.n * (double)B.n;
+    return work <= c->pp_budget() * (double)A.n * (double)B.n;
 }
 
-// One launch computes every accumulator of the family's schedule: work items = accumulators x tiles.
+// Where and how the GEMM epilogue stores each accumulator of a launch (tc::AccOp).
+struct AccPlan {
+    uint32_t nacc = 0;
+    uint8_t op[5] = {};
+    uint64_t off[5] = {};   // byte offsets from the launch's output pointer
+    uint32_t s_pitch = 0, s_colbase = 0;   // scratch rectangle (tc::TcParams); 0 = final counts in the reference's order
+};
+// n / n_high with no repair pending: the GEMM writes the final counts
+AccPlan direct_plan(const dg_ctx* c) {
+    AccPlan a;
+    a.nacc = 1;
+    a.op[0] = c->u16() ? tc::ACC_DIV3_U16 : tc::ACC_DIV3_U32;
+    return a;
+}
+// The scratch rectangle of a panel: rows [row0, row1) x the columns of the launch's tiles.
+struct ScratchGeom { uint64_t rows; uint32_t pitch, colbase; };
+ScratchGeom scratch_geom(bool fp4, int mode, uint64_t row0, uint64_t row1, uint64_t n_b) {
+    const uint32_t tn = fp4 ? tc::TN_FP4 : tc::TN;
+    const uint32_t cb0 = mode == DG_MODE_SQUARE ? (uint32_t)((row0 + 1) / tn) : 0;
+    const uint32_t blocks = (uint32_t)((n_b + tn - 1) / tn);
+    ScratchGeom g;
+    g.rows = row1 - row0;
+    g.colbase = cb0 * tn;
+    g.pitch = (blocks > cb0 ? blocks - cb0 : 0) * tn;
+    return g;
+}
+// bytes that hold any scratch plan of that panel
+size_t scratch_upper_bound(const dg_ctx* c, bool fp4, int mode, uint64_t row0, uint64_t row1, uint64_t n_b) {
+    const ScratchGeom g = scratch_geom(fp4, mode, row0, row1, n_b);
+    return (size_t)tc_schedule(c->fam).nacc * ((size_t)g.rows * g.pitch * 4 + 256) + 256;
+}
+// every accumulator of the family into the scratch buffer of a panel.  Accumulator 0 of n / n_high / raw / jc69 is
+// 3 * DIFF (up to 3 * width): while the both-partial repair is pending it is kept modulo 2^16 (or as int32 for wide
+// alignments) and pp_correct adds to it; else DIFF itself is stored.  Every other sum lies in [-width, width] and is
+// stored as int16 when that fits.
+AccPlan scratch_plan(const dg_ctx* c, bool fp4, int mode, const Panel& p, uint64_t n_b, bool pp_pending) {
+    static const bool force32 = std::getenv("DG_SCRATCH_I32") != nullptr;
+    const TcSchedule& sch = tc_schedule(c->fam);
+    const ScratchGeom g = scratch_geom(fp4, mode, p.row0, p.row1, n_b);
+    AccPlan a;
+    a.nacc = (uint32_t)sch.nacc;
+    a.s_pitch = g.pitch; a.s_colbase = g.colbase;
+    const bool narrow = c->width <= 32767 && !force32;
+    uint64_t off = 0;
+    for (int k = 0; k < sch.nacc; k++) {
+        int op;
+        if (k == 0 && sch.needs_pp) op = pp_pending ? (narrow ? tc::ACC_MOD16 : tc::ACC_RAW_I32) : (narrow ? tc::ACC_DIV3_U16 : tc::ACC_DIV3_U32);
+        else op = narrow ? tc::ACC_RAW_I16 : tc::ACC_RAW_I32;
+        a.op[k] = (uint8_t)op;
+        a.off[k] = off;
+        off += ((uint64_t)g.rows * g.pitch * (tc::acc_op_16(op) ? 2 : 4) + 255) / 256 * 256;
+    }
+    return a;
+}
+
+// One launch computes every accumulator of the plan: work items = accumulators x tiles.
 void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                    int out_mode, void* out, uint64_t acc_stride, cudaStream_t st, Slot* ws = nullptr,
+                    const AccPlan& plan, void* out, cudaStream_t st, Slot* ws = nullptr,
                     bool tiles_on_device = false) {
     const TcSchedule& sch = tc_schedule(c->fam);
     tc::TcParams tp{};
@@ -525,7 +622,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     //                1 = 128 x 256 per CTA,  2 = 128 x 256 per CTA in 2-CTA clusters with TMA multicast of B,
     //                3 = 256 x 256 block per CTA (two A sub-tiles, no cluster)
     int variant = fp4 ? 0 : c->tile_variant;   // the FP4 operands run on the cta_group::2 kernel only
-    const uint32_t nacc_launch = out_mode == tc::OUT_RAW_I32 ? (uint32_t)sch.nacc : 1u;
+    const uint32_t nacc_launch = plan.nacc;
     if (variant == 0 && !fp4) {
         // Small launches cannot fill 74 CTA pairs with 512 x 256 blocks: fall back to 128 x 256 blocks on 148 CTAs
         // when that finishes sooner (cost ~ rounds x rows per SM; the small tile needs ~1.6x the time per MAC).
@@ -548,8 +645,11 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         tp.npairs[a] = (uint32_t)sch.npairs[a];
         for (int i = 0; i < sch.npairs[a]; i++) { tp.pa[a][i] = sch.pa[a][i]; tp.pb[a][i] = sch.pb[a][i]; }
     }
-    tp.acc_stride = acc_stride;
-    tp.out_mode = out_mode;
+    for (uint32_t a = 0; a < tp.nacc; a++) { tp.acc_off[a] = plan.off[a]; tp.acc_op[a] = plan.op[a]; }
+    tp.s_pitch = plan.s_pitch; tp.s_colbase = plan.s_colbase;
+    if (plan.s_pitch && (plan.s_pitch != tp.gx * tp.tn || plan.s_colbase != tp.col_block0 * tp.tn))
+        fail(DG_ERR_STATE, "internal: scratch geometry does not match the launch's tiles");
+    tp.probe = d.clk_probe;
     tp.stages = pair ? tc::StageCfg<2, true>::N : (mt == 2 ? tc::StageCfg<2>::N : tc::StageCfg<1>::N);
     if (const char* e = std::getenv("DG_TC_STAGES")) tp.stages = (uint32_t)std::min<int>((int)tp.stages, std::max(1, std::atoi(e)));
     if (tp.gx == 0 || tp.gy == 0) return;
@@ -622,9 +722,12 @@ bool tc_pp_pending(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B, bool a
 // Raw int32 sums of every accumulator (scratch[accumulator][panel pair]) -> the reference's counts -> the result
 // (uint16 / uint32 count, f64 distance through the epi_* epilogues, or the debug counts).
 void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p, void* d_out,
-                    int* scratch, bool swap_roles, bool counts, cudaStream_t st) {
+                    int* scratch, const AccPlan& plan, bool swap_roles, bool counts, cudaStream_t st) {
     tc::CombineParams cp{};
-    cp.acc = scratch; cp.acc_stride = p.n_results;
+    cp.acc = reinterpret_cast<const uint8_t*>(scratch);
+    for (uint32_t a = 0; a < plan.nacc; a++) { cp.acc_off[a] = plan.off[a]; cp.acc_op[a] = plan.op[a]; }
+    cp.s_pitch = plan.s_pitch; cp.s_colbase = plan.s_colbase;
+    cp.literal = std::getenv("DG_EPI_LITERAL") != nullptr;
     cp.a_acgt = A.acgt; cp.b_acgt = B.acgt;
     cp.n_b = (uint32_t)B.n; cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
     cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
@@ -632,11 +735,13 @@ void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
     cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
     cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
-    // ~16 CTAs per SM, each walking many rows of its 256-column strip (one element per thread and row: coalesced)
+    // virtual blocks: 256-column strips x row phases (~16 per SM); a fixed grid of 2 CTAs per SM walks them
     const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
-    dim3 grid(gx, (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx))));
-    if (grid.x == 0 || grid.y == 0) return;
-    tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp);
+    const unsigned gy = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx)));
+    if (gx == 0) return;
+    static const int per_sm = std::getenv("DG_COMBINE_PER_SM") ? std::max(1, std::atoi(std::getenv("DG_COMBINE_PER_SM"))) : 2;
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)gx * gy, (uint64_t)g_num_sms(d.id) * per_sm);
+    tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp, gx, gy);
     CUDA_CHECK(cudaGetLastError());
     c->tm.count_launches++;
 }
@@ -650,18 +755,19 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
     const TcSchedule& sch = tc_schedule(c->fam);
     const bool pp_pending = tc_pp_pending(c, A, B, a_is_batch);
     if (c->fam == FAM_SNP && !counts && !pp_pending) {
-        launch_tc_gemm(c, d, A, B, mode, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, d_out, 0, st, ws);
+        launch_tc_gemm(c, d, A, B, mode, p, direct_plan(c), d_out, st, ws);
         return;
     }
     if (!scratch) fail(DG_ERR_STATE, "tensor engine: no scratch buffer");
-    const uint64_t stride = p.n_results;
-    launch_tc_gemm(c, d, A, B, mode, p, tc::OUT_RAW_I32, scratch, stride, st, ws);
+    const AccPlan plan = scratch_plan(c, A.tc_fp4, mode, p, B.n, pp_pending);
+    static const bool skip_gemm = std::getenv("DG_SKIP_GEMM") != nullptr, skip_combine = std::getenv("DG_SKIP_COMBINE") != nullptr;  // timing experiments only
+    if (!skip_gemm) launch_tc_gemm(c, d, A, B, mode, p, plan, scratch, st, ws);
     if (pp_pending) {
         tc::PpCorrParams cp{};
         cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
         cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1; cp.n_b = (uint32_t)B.n;
         cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
-        cp.n_total = A.n; cp.out_base = p.out_base; cp.out = scratch;
+        cp.s_pitch = plan.s_pitch; cp.s_colbase = plan.s_colbase; cp.op = plan.op[0]; cp.out = scratch;
         if (a_is_batch) {
             cp.a_ops = A.tc_ops; cp.a_nplanes = (uint32_t)sch.nplanes; cp.a_wp8 = (uint32_t)A.tc_wp8; cp.a_vplane0 = TC_VPLANE0;
             const uint64_t units = (p.row1 - p.row0) * (A.tc_wp8 / 16);
@@ -675,11 +781,10 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
         CUDA_CHECK(cudaGetLastError());
         c->tm.count_launches++;
     }
-    launch_combine(c, d, A, B, mode, p, d_out, scratch, swap_roles, counts, st);
+    if (!skip_combine) launch_combine(c, d, A, B, mode, p, d_out, scratch, plan, swap_roles, counts, st);
 }
 
-void ensure_scratch(dg_ctx* c, Slot& s, size_t pairs) {
-    const size_t bytes = pairs * 4 * (size_t)tc_schedule(c->fam).nacc;
+void ensure_scratch(Slot& s, size_t bytes) {
     if (s.scratch_cap >= bytes) return;
     if (s.d_scratch) cudaFree(s.d_scratch);
     s.d_scratch = nullptr; s.scratch_cap = 0;
@@ -690,19 +795,21 @@ void ensure_scratch(dg_ctx* c, Slot& s, size_t pairs) {
 uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
 
 // Live 512 x 256 tiles (the tensor engine's CTA-pair block) of rows [r0, r1) against n_cols columns.
-uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols) {
-    const uint64_t col_blocks = (n_cols + 255) / 256;
+uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols, uint64_t tn = 256) {
+    const uint64_t col_blocks = (n_cols + tn - 1) / tn;
     if (mode != DG_MODE_SQUARE) return (r1 - r0 + 511) / 512 * col_blocks;
     uint64_t live = 0;
     for (uint64_t rs = r0; rs < r1; rs += 512) {
-        const uint64_t first = (rs + 1) / 256;   // first column block with a column > rs
+        const uint64_t first = (rs + 1) / tn;   // first column block with a column > rs
         live += col_blocks > first ? col_blocks - first : 0;
     }
     return live;
 }
 
+// tn / items: tile width of the tensor engine in use (240 fp4, 256 int8) and work items per tile (= accumulators of the
+// family's schedule): one persistent launch deals live tiles x items to the 74 CTA pairs.
 std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, uint64_t n_rows_total,
-                               uint64_t n_cols, int tm) {
+                               uint64_t n_cols, int tm, uint64_t tn = 256, uint64_t items = 1) {
     // rows per panel: a multiple of the tile height sized so one panel's results ~ panel_bytes.  Among the
     // candidates between half and all of that budget, take the one whose tile count fills whole rounds of the
     // 74 CTA pairs best (a panel is one persistent launch: a ragged last round idles SMs).
@@ -721,7 +828,7 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
         if (r + per < rows_major) {
             double best_fill = -1;
             for (uint64_t cand = per; cand >= quantum && cand * 2 >= per; cand -= quantum) {
-                const uint64_t live = live_pair_tiles(mode, r, r + cand, n_cols);
+                const uint64_t live = live_pair_tiles(mode, r, r + cand, n_cols, tn) * items;
                 const double fill = (double)live / (double)((live + SLOTS - 1) / SLOTS * SLOTS);
                 if (fill > best_fill + 1e-9) { best_fill = fill; best_rows = cand; }
                 if (cand == quantum) break;
@@ -770,6 +877,19 @@ void enqueue_panel_kernel(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSe
     if (grid.y > 65535) fail(DG_ERR_INVALID_ARG, "panel too tall for one launch (%u row blocks)", grid.y);
     launch_count<COUNTS>(c->fam, c->tile_variant, cp, grid, st);
     c->tm.count_launches++;
+}
+
+// The SM clock the tensor-engine launches actually saw: CTA 0 of every launch adds its clock64 and globaltimer spans
+// to the device's probe; called when the streams are idle.
+void harvest_clock(dg_ctx* c) {
+    Device& d = c->devs[0];
+    if (!d.clk_probe) return;
+    unsigned long long h[8];
+    if (cudaSetDevice(d.id) != cudaSuccess || cudaMemcpy(h, d.clk_probe, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    cudaMemset(d.clk_probe, 0, sizeof h);
+    c->clk_cycles += (double)h[4]; c->clk_ns += (double)h[5];
+    static const bool verbose = std::getenv("DG_CLOCK_PROBE") != nullptr;
+    if (verbose && h[5]) fprintf(stderr, "[dg clock probe] GEMM launches %.3f ms, SM clock %.0f MHz\n", h[5] * 1e-6, (double)h[4] / (double)h[5] * 1e3);
 }
 
 void harvest_kernel_time(dg_ctx* c, Slot& s) {
@@ -873,7 +993,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
     const PlaneSet& A0 = c->devs[0].set[0];
     const PlaneSet& B0 = c->devs[0].set[wb];
     const TileShape ts = tile_shape(c->fam, c->tile_variant);
-    std::vector<Panel> all = make_panels(c->panel_bytes, c->elem_bytes(), mode, A0.n, B0.n, ts.tm);
+    std::vector<Panel> all = make_panels(c->panel_bytes, c->elem_bytes(), mode, A0.n, B0.n, ts.tm, c->plan_tn(), c->plan_items());
     std::vector<Panel> mine;
     for (size_t k = 0; k < all.size(); k++)
         if (k % n_parts == part) mine.push_back(all[k]);
@@ -890,6 +1010,7 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         CUDA_CHECK(cudaEventElapsedTime(&ms, d.run_start, d.run_stop));
         c->tm.run_ms = std::max<double>(c->tm.run_ms, ms);
     }
+    harvest_clock(c);
     c->tm.total_ms = wall_ms() - t0;
 }
 
@@ -911,8 +1032,11 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
-        if (tc_run && (c->fam != FAM_SNP || tc_pp_pending(c, d.set[0], d.set[wb], false)))
-            for (auto& sl : d.slot) ensure_scratch(c, sl, std::max<size_t>(max_bytes / c->elem_bytes(), 64));
+        if (tc_run && (c->fam != FAM_SNP || tc_pp_pending(c, d.set[0], d.set[wb], false))) {
+            size_t sb = 0;
+            for (auto& p : mine) sb = std::max(sb, scratch_upper_bound(c, d.set[0].tc_fp4, mode, p.row0, p.row1, B0.n));
+            for (auto& sl : d.slot) ensure_scratch(sl, sb);
+        }
     }
 
     const int K = (int)mine.size();
@@ -995,7 +1119,7 @@ void ensure_pp_index(dg_ctx* c, Device& d, PlaneSet& s) {
 // run: upload (PCIe H2D), packing + tiles, and the D2H of finished panels all overlap, and panels reach the sink
 // in completion order (descending rows).  The both-partial repair of n / n_high / raw / jc69 uses a chunked
 // index (one per-site offset table per chunk over one shared entry buffer) that grows with the chunks.
-void ensure_pipe_ring(dg_ctx* c, Device& d, size_t bytes, bool scratch) {
+void ensure_pipe_ring(dg_ctx* c, Device& d, size_t bytes, size_t scratch_bytes) {
     if (d.pout_cap < bytes) {
         for (auto& s : d.pslot) {
             if (s.d_out) cudaFree(s.d_out);
@@ -1009,8 +1133,9 @@ void ensure_pipe_ring(dg_ctx* c, Device& d, size_t bytes, bool scratch) {
         }
         d.pout_cap = bytes;
     }
-    if (scratch)
-        for (auto& s : d.pslot) ensure_scratch(c, s, std::max<size_t>(bytes / c->elem_bytes(), 64));
+    (void)c;
+    if (scratch_bytes)
+        for (auto& s : d.pslot) ensure_scratch(s, scratch_bytes);
 }
 
 void sq_abort(dg_ctx* c) {
@@ -1075,9 +1200,10 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
     const uint32_t n_entries = c->sq_base[c->sq_pumped];   // entries of every chunk pumped so far
     const bool repair = c->sq_needs_pp && n_entries != 0 && (!rect || B.pp.n_entries != 0);
     if (c->fam == FAM_SNP && !repair) {
-        launch_tc_gemm(c, d, S, B, c->sq_mode, p, c->u16() ? tc::OUT_DIV3_U16 : tc::OUT_DIV3_U32, s.d_out, 0, st, &s, true);
+        launch_tc_gemm(c, d, S, B, c->sq_mode, p, direct_plan(c), s.d_out, st, &s, true);
     } else {
-        launch_tc_gemm(c, d, S, B, c->sq_mode, p, tc::OUT_RAW_I32, s.d_scratch, p.n_results, st, &s, true);
+        const AccPlan plan = scratch_plan(c, S.tc_fp4, c->sq_mode, p, B.n, repair);
+        launch_tc_gemm(c, d, S, B, c->sq_mode, p, plan, s.d_scratch, st, &s, true);
         if (repair && rect) {
             // rows' entries = the chunks that overlap the panel's rows (contiguous in the shared entry buffer),
             // columns = the classic per-site index of the resident alignment 1
@@ -1089,7 +1215,7 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
                 cp.a_entries = d.sq_entries + c->sq_base[ga0]; cp.a_n = c->sq_base[ga1] - c->sq_base[ga0];
                 cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
                 cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1; cp.n_b = (uint32_t)B.n;
-                cp.square = 0; cp.n_total = S.n; cp.out_base = p.out_base; cp.out = s.d_scratch;
+                cp.square = 0; cp.s_pitch = plan.s_pitch; cp.s_colbase = plan.s_colbase; cp.op = plan.op[0]; cp.out = s.d_scratch;
                 tc::pp_correct_kernel<<<(cp.a_n + 255) / 256, 256, 0, st>>>(cp);
                 CUDA_CHECK(cudaGetLastError());
                 c->tm.count_launches++;
@@ -1104,7 +1230,7 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
             cp.n_chunks = (uint32_t)c->sq_pumped;
             cp.a_begin = ga0 < ga1 ? c->sq_base[ga0] : 0; cp.a_end = ga0 < ga1 ? c->sq_base[ga1] : 0;
             cp.row0 = (uint32_t)p.row0; cp.row_end = (uint32_t)p.row1;
-            cp.n_total = S.n; cp.out_base = p.out_base; cp.out = s.d_scratch;
+            cp.s_pitch = plan.s_pitch; cp.s_colbase = plan.s_colbase; cp.op = plan.op[0]; cp.out = s.d_scratch;
             if (cp.a_end > cp.a_begin) {
                 const unsigned gb = (unsigned)std::min<uint32_t>((cp.a_end - cp.a_begin + 127) / 128, 148 * 8);
                 tc::pp_correct_chunks_kernel<<<gb, 128, 0, st>>>(cp);
@@ -1112,7 +1238,7 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
                 c->tm.count_launches++;
             }
         }
-        launch_combine(c, d, S, B, c->sq_mode, p, s.d_out, s.d_scratch, false, false, st);
+        launch_combine(c, d, S, B, c->sq_mode, p, s.d_out, s.d_scratch, plan, false, false, st);
     }
     CUDA_CHECK(cudaEventRecord(s.k_stop, st));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_k1[li], st));
@@ -1171,10 +1297,10 @@ void sq_pump(dg_ctx* c, size_t g) {
         if (c->sq_mode == DG_MODE_RECT) {
             const PlaneSet& Bs = d.set[1];
             const double m = (double)ch.hi;
-            if (c->engine == 0 && std::sqrt(d.h_sq_work[g] * Bs.pp.pair_work) > 2.0 * m * (double)Bs.n && m >= 1024) c->sq_fallback = true;
+            if (c->engine == 0 && std::sqrt(d.h_sq_work[g] * Bs.pp.pair_work) > c->pp_budget() * m * (double)Bs.n && m >= 1024) c->sq_fallback = true;
         } else {
             const double m = (double)(c->sq_n - ch.lo);
-            if (c->engine == 0 && d.h_sq_work[g] > 2.0 * m * m && m >= 1024) c->sq_fallback = true;
+            if (c->engine == 0 && d.h_sq_work[g] > c->pp_budget() * m * m && m >= 1024) c->sq_fallback = true;
         }
     }
     c->sq_base[g + 1] = total;
@@ -1199,7 +1325,7 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     CUDA_CHECK(cudaSetDevice(d.id));
     c->have_invalid = false;
     PlaneSet& S = d.set[0];
-    const bool want_tc = c->engine != 1;
+    const bool want_tc = c->tc_wanted();
     const bool rect = mode == DG_MODE_RECT;
     if (rect) {
         if (d.set[1].n == 0) fail(DG_ERR_STATE, "alignment 1 is not loaded (dg_load_resident(ctx, 1, ...) before dg_rect_begin)");
@@ -1234,7 +1360,7 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     const uint64_t total_bytes = (rect ? n * n_cols : n * (n - 1) / 2) * c->elem_bytes();
     const size_t pb = (size_t)std::min<uint64_t>(c->panel_bytes,
                           std::max<uint64_t>(8ull << 20, total_bytes / ((uint64_t)std::max(1, c->pipe_panels) * n_parts)));  // DG_OPT_PANEL_BYTES caps it
-    std::vector<Panel> all = make_panels(pb, c->elem_bytes(), mode, n, n_cols, ts.tm);
+    std::vector<Panel> all = make_panels(pb, c->elem_bytes(), mode, n, n_cols, ts.tm, c->plan_tn(), c->plan_items());
     c->sq_panels.clear();
     for (size_t k = 0; k < all.size(); k++)
         if (k % n_parts == part) c->sq_panels.push_back(all[k]);
@@ -1242,7 +1368,12 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     c->sq_next = 0;
     size_t max_bytes = 256;
     for (auto& p : c->sq_panels) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
-    if (want_tc) ensure_pipe_ring(c, d, max_bytes, c->fam != FAM_SNP || c->sq_needs_pp);
+    if (want_tc) {
+        size_t sb = 0;
+        if (c->fam != FAM_SNP || c->sq_needs_pp)
+            for (auto& p : c->sq_panels) sb = std::max(sb, scratch_upper_bound(c, c->want_fp4(), mode, p.row0, p.row1, n_cols));
+        ensure_pipe_ring(c, d, max_bytes, sb);
+    }
     // chunks: the same for every part (a multi-rank launcher broadcasts them): <= ~40 pieces of >= 24 MB, descending,
     // every boundary but n itself a multiple of ROW_ALIGN (the pack kernel zero-fills whole 128-row groups)
     const uint64_t target = c->pipe_chunk_bytes ? c->pipe_chunk_bytes : std::max<uint64_t>(24ull << 20, n * c->width / 40);
@@ -1400,6 +1531,7 @@ void sq_end(dg_ctx* c) {
     CUDA_CHECK(cudaStreamSynchronize(d.fill));
     for (void* q : d.sq_retired) cudaFree(q);
     d.sq_retired.clear();
+    harvest_clock(c);
     c->tm.total_ms = wall_ms() - c->sq_t0;
     c->sq_open = false;
 }
@@ -1448,15 +1580,15 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
     // raw / jc69 scans the batch's own V planes against the resident index) unless the resident alignment is
     // so full of partial ambiguity codes that the repair would dominate; then the LOP3 tiles run.
     const PlaneSet& R0 = c->devs[0].set[0];
-    const bool cheap_pp = !tc_schedule(c->fam).needs_pp || R0.pp.pair_work <= 2.0 * (double)R0.n * (double)R0.n;
-    const bool s_tc = c->engine != 1 && R0.tc_ready && R0.tc_fp4 == c->want_fp4() && (c->engine >= 2 || cheap_pp);
+    const bool cheap_pp = !tc_schedule(c->fam).needs_pp || R0.pp.pair_work <= c->pp_budget() * (double)R0.n * (double)R0.n;
+    const bool s_tc = c->tc_wanted() && R0.tc_ready && R0.tc_fp4 == c->want_fp4() && (c->engine >= 2 || cheap_pp);
     if (!s_tc)
         for (auto& d : c->devs) ensure_lop3(c, d, d.set[0]);
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
         if (s_tc)
-            for (auto& sl : d.slot) ensure_scratch(c, sl, (size_t)mb * n_res);
+            for (auto& sl : d.slot) ensure_scratch(sl, scratch_upper_bound(c, c->want_fp4(), DG_MODE_RECT, 0, mb, n_res));
         if (d.in_cap < mb || (s_tc && (!d.slot[0].batch.tc_ops || d.slot[0].batch.tc_fp4 != c->want_fp4())) ||
             (!s_tc && !d.slot[0].batch.core)) {
             for (auto& s : d.slot) {
@@ -1620,6 +1752,7 @@ void destroy_device(Device& d) {
     if (d.run_start) cudaEventDestroy(d.run_start);
     if (d.run_stop) cudaEventDestroy(d.run_stop);
     if (d.d_invalid) cudaFree(d.d_invalid);
+    if (d.clk_probe) cudaFree(d.clk_probe);
     if (d.h_invalid) cudaFreeHost(d.h_invalid);
     if (d.compute) cudaStreamDestroy(d.compute);
     if (d.compute2) cudaStreamDestroy(d.compute2);
@@ -1729,12 +1862,15 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
             CUDA_CHECK(cudaHostAlloc(&d.h_pp_total, 4, cudaHostAllocDefault));
             CUDA_CHECK(cudaHostAlloc(&d.h_pp_work, 8, cudaHostAllocDefault));
             for (auto& e : d.chunk_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            set_side_kernel_carveouts();
             CUDA_CHECK(cudaMemcpyToSymbol(c_ascii_lut, lut, 256));
             CUDA_CHECK(cudaMemcpyToSymbol(c_valid_code, valid, 32));
             CUDA_CHECK(cudaMalloc(&d.d_invalid, 3 * sizeof(unsigned long long)));
             CUDA_CHECK(cudaHostAlloc(&d.h_invalid, 3 * sizeof(unsigned long long), cudaHostAllocDefault));
             for (int k = 0; k < 3; k++) d.h_invalid[k] = ~0ull;
             CUDA_CHECK(cudaMemset(d.d_invalid, 0xff, 3 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMalloc(&d.clk_probe, 8 * sizeof(unsigned long long)));
+            CUDA_CHECK(cudaMemset(d.clk_probe, 0, 8 * sizeof(unsigned long long)));
             c->devs.push_back(d);
         }
     } catch (const DgError& e) {
@@ -1746,9 +1882,9 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
         delete c;
         return rc;
     }
-    if (const char* e = std::getenv("DG_ENGINE")) {  // developer override: 1 = LOP3+POPC tiles, 2 = tcgen05 int8 GEMM
+    if (const char* e = std::getenv("DG_ENGINE")) {  // developer override: 1 = LOP3+POPC tiles, 2 = tcgen05 int8 GEMM, 3 = fp4
         const int v = std::atoi(e);
-        if (v >= 0 && v <= 3) c->engine = v;
+        if (v >= 0 && v <= 3 && !(v == 3 && !c->fp4_exact()) && !(v == 2 && !c->i8_ok())) c->engine = v;
     }
     *out = c;
     return DG_OK;
@@ -1784,6 +1920,11 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             break;
         case DG_OPT_ENGINE:
             if (value < 0 || value > 3) fail(DG_ERR_INVALID_ARG, "unknown engine %lld", (long long)value);
+            if (value == 3 && !ctx->fp4_exact())
+                fail(DG_ERR_INVALID_ARG, "engine 3 (tcgen05 kind::mxf4, fp32 accumulation) is exact only for widths up to %llu sites; "
+                     "use 0 (auto), 2 (int8, int32 accumulation) or 1 (LOP3+POPC)", (unsigned long long)((1ull << 22) - 256));
+            if (value == 2 && !ctx->i8_ok())
+                fail(DG_ERR_INVALID_ARG, "engine 2 (tcgen05 kind::i8) takes widths below 2^27 sites; use 0 (auto) or 1 (LOP3+POPC)");
             ctx->engine = (int)value;
             break;
         default: fail(DG_ERR_INVALID_ARG, "unknown option %d", key);
@@ -1807,7 +1948,7 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
             c32.resize(n * 4);
             for (uint64_t i = 0; i < n * 4; i++) c32[i] = (uint32_t)acgt_counts[i];
         }
-        const bool want_tc = ctx->engine != 1;
+        const bool want_tc = ctx->tc_wanted();
         const bool needs_pp = tc_schedule(ctx->fam).needs_pp;
         const bool trace = std::getenv("DG_TRACE") != nullptr;
         const double t_begin = wall_ms();
@@ -1914,8 +2055,9 @@ int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n_cols, 
     if (measure < 0 || measure > 5 || (mode != DG_MODE_SQUARE && mode != DG_MODE_RECT) || panel_bytes < 4096)
         return DG_ERR_INVALID_ARG;
     const TileShape ts = tile_shape(family_of(measure), tile_variant);
+    static const uint64_t fam_items[4] = {1, 2, 3, 5};   // accumulators of the tensor schedules (default engine: fp4, 240-column tiles)
     const std::vector<Panel> v = make_panels(panel_bytes, measure <= 1 ? 4 : 8, mode, n_rows,
-                                             mode == DG_MODE_SQUARE ? n_rows : n_cols, ts.tm);
+                                             mode == DG_MODE_SQUARE ? n_rows : n_cols, ts.tm, tc::TN_FP4, fam_items[family_of(measure)]);
     for (size_t k = 0; k < v.size() && k < cap; k++) {
         if (row_begin) row_begin[k] = v[k].row0;
         if (row_end) row_end[k] = v[k].row1;
@@ -1933,7 +2075,7 @@ int64_t dg_plan_ctx(dg_ctx* ctx, int mode, uint64_t* row_begin, uint64_t* row_en
         const PlaneSet& B = ctx->devs[0].set[mode == DG_MODE_SQUARE ? 0 : 1];
         if (A.n == 0 || B.n == 0) fail(DG_ERR_STATE, "alignment not loaded");
         const TileShape ts = tile_shape(ctx->fam, ctx->tile_variant);
-        const std::vector<Panel> v = make_panels(ctx->panel_bytes, ctx->elem_bytes(), mode, A.n, B.n, ts.tm);
+        const std::vector<Panel> v = make_panels(ctx->panel_bytes, ctx->elem_bytes(), mode, A.n, B.n, ts.tm, ctx->plan_tn(), ctx->plan_items());
         for (size_t k = 0; k < v.size() && k < cap; k++) {
             if (row_begin) row_begin[k] = v[k].row0;
             if (row_end) row_end[k] = v[k].row1;
@@ -2057,6 +2199,7 @@ int dg_stream_end(dg_ctx* ctx) {
     int rc = guarded(ctx, [&] {
         if (!ctx->streaming) fail(DG_ERR_STATE, "no stream session is open");
         while (!ctx->s_queue.empty()) stream_sink_front(ctx);
+        harvest_clock(ctx);
         ctx->streaming = false;
         ctx->tm.total_ms = wall_ms() - ctx->s_t0;
     });
@@ -2088,7 +2231,7 @@ int dg_debug_counts(dg_ctx* ctx, int which_a, int which_b, uint32_t* out) {
                 // tensor engine: raw sums of every accumulator -> the same canonical counts
                 int* scratch = nullptr;
                 const uint64_t rows_step = std::min<uint64_t>(A.n, 32768);
-                CUDA_CHECK(cudaMalloc(&scratch, (size_t)rows_step * B.n * 4 * tc_schedule(ctx->fam).nacc));
+                CUDA_CHECK(cudaMalloc(&scratch, scratch_upper_bound(ctx, A.tc_fp4, DG_MODE_RECT, 0, rows_step, B.n)));
                 try {
                     for (uint64_t r = 0; r < A.n; r += rows_step) {
                         Panel q = p;
@@ -2145,12 +2288,14 @@ int dg_get_timings(const dg_ctx* ctx, dg_timings* out) {
     if (!ctx || !out) return DG_ERR_INVALID_ARG;
     *out = ctx->tm;
     out->engine = (uint64_t)ctx->last_engine;
+    out->sm_mhz = ctx->clk_ns > 0 ? ctx->clk_cycles / ctx->clk_ns * 1e3 : 0.0;
     return DG_OK;
 }
 
 int dg_reset_timings(dg_ctx* ctx) {
     if (!ctx) return DG_ERR_INVALID_ARG;
     ctx->tm = dg_timings{};
+    ctx->clk_cycles = ctx->clk_ns = 0;
     return DG_OK;
 }
 

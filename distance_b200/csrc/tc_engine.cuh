@@ -36,6 +36,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
 
 namespace dg {
 namespace tc {
@@ -56,6 +57,18 @@ template <int MT, bool PAIR = false> struct StageCfg {
 };
 constexpr int THREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel traps instead of hanging
+
+// What the epilogue stores for one accumulator (per accumulator: TcParams::acc_op / CombineParams::acc_op):
+//   ACC_RAW_I32 / ACC_RAW_I16 : the raw sum into a scratch array (int16 when every sum fits: width <= 32767 and no
+//                               repair pending on that accumulator -- halves the scratch traffic)
+//   ACC_DIV3_U32 / _U16       : sum / 3 = DIFF (accumulator 0 of n / n_high / raw / jc69 with no both-partial repair
+//                               pending): the final count of n / n_high, or a 16-bit scratch value for the combine pass
+//   ACC_MOD16                 : the raw sum modulo 2^16 (accumulator 0 = 3 * DIFF with the repair pending, width <= 32767):
+//                               pp_correct adds its deltas modulo 2^16 and the combine pass recovers DIFF, because of the
+//                               two candidates x and x + 65536 (3 * DIFF < 2^17) exactly one is a multiple of 3
+enum AccOp { ACC_RAW_I32 = 0, ACC_RAW_I16 = 1, ACC_DIV3_U32 = 2, ACC_DIV3_U16 = 3, ACC_MOD16 = 4 };
+__host__ __device__ constexpr bool acc_op_16(int op) { return op == ACC_RAW_I16 || op == ACC_DIV3_U16 || op == ACC_MOD16; }
+__host__ __device__ constexpr bool acc_op_div3(int op) { return op == ACC_DIV3_U32 || op == ACC_DIV3_U16; }
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -596,24 +609,41 @@ __device__ __forceinline__ int pp_corr(uint32_t ma, uint32_t mb) {
     return ((ma & mb) ? 0 : 3) - got;
 }
 
+// Add a repair delta to accumulator 0 of the pair at scratch index idx: int32 sums take an atomicAdd; 16-bit sums
+// (ACC_MOD16: the value modulo 2^16) a wrap-around add through a CAS on the containing word.
+__device__ __forceinline__ void pp_add(void* out, int op, uint64_t idx, int c) {
+    if (op == ACC_RAW_I32) {
+        atomicAdd(reinterpret_cast<int*>(out) + idx, c);
+    } else {
+        uint32_t* w = reinterpret_cast<uint32_t*>(out) + (idx >> 1);
+        const uint32_t sh = (uint32_t)(idx & 1) * 16;
+        uint32_t old = *w, assumed;
+        do {
+            assumed = old;
+            const uint32_t nv = (assumed & ~(0xFFFFu << sh)) | ((((assumed >> sh) + (uint32_t)c) & 0xFFFFu) << sh);
+            old = atomicCAS(w, assumed, nv);
+        } while (old != assumed);
+    }
+}
+
 struct PpCorrParams {
     const uint64_t* a_entries; uint32_t a_n;          // row alignment's entries (resident rows)
     const int8_t* a_ops; uint32_t a_nplanes, a_wp8, a_vplane0;  // or: scan the V planes of the row records (stream batches)
     const uint64_t* b_entries; const uint32_t* b_off; // column alignment's index
     uint32_t row0, row_end, n_b;
     int square;
-    uint64_t n_total, out_base;
-    int* out;                                         // raw sums of accumulator 0 (3 * DIFF) of the panel
+    uint32_t s_pitch, s_colbase;                      // scratch rectangle of the panel (TcParams)
+    int op;                                           // ACC_RAW_I32 or ACC_MOD16
+    void* out;                                        // raw sums of accumulator 0 (3 * DIFF) of the panel
 };
 __device__ __forceinline__ void pp_fix_row(const PpCorrParams& p, uint32_t row, uint32_t site, uint32_t ma) {
-    const uint64_t row_base = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base
-                                       : (uint64_t)(row - p.row0) * p.n_b;
+    const uint64_t row_base = (uint64_t)(row - p.row0) * p.s_pitch;
     for (uint32_t k = p.b_off[site]; k < p.b_off[site + 1]; k++) {
         const uint64_t eb = p.b_entries[k];
         const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
         if (p.square && col <= row) continue;
         const int c = pp_corr(ma, (uint32_t)(eb & 15));
-        if (c) atomicAdd(p.out + (p.square ? row_base + (col - row - 1) : row_base + col), c);
+        if (c) pp_add(p.out, p.op, row_base + (col - p.s_colbase), c);
     }
 }
 // rows given as index entries (resident alignments)
@@ -632,8 +662,9 @@ struct PpChunkParams {
     const uint32_t* off; uint32_t off_stride, n_chunks;
     uint32_t a_begin, a_end;
     uint32_t row0, row_end;
-    uint64_t n_total, out_base;
-    int* out;
+    uint32_t s_pitch, s_colbase;
+    int op;
+    void* out;
 };
 __global__ void pp_correct_chunks_kernel(PpChunkParams p) {
     for (uint32_t e = p.a_begin + blockIdx.x * blockDim.x + threadIdx.x; e < p.a_end; e += gridDim.x * blockDim.x) {
@@ -641,7 +672,7 @@ __global__ void pp_correct_chunks_kernel(PpChunkParams p) {
         const uint32_t row = (uint32_t)((ea >> 4) & 0xFFFFFFFFull);
         if (row < p.row0 || row >= p.row_end) continue;
         const uint32_t site = (uint32_t)(ea >> 36), ma = (uint32_t)(ea & 15);
-        const uint64_t row_base = (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base;
+        const uint64_t row_base = (uint64_t)(row - p.row0) * p.s_pitch;
         for (uint32_t g = 0; g < p.n_chunks; g++) {
             const uint32_t* off = p.off + (uint64_t)g * p.off_stride;
             for (uint32_t k = off[site]; k < off[site + 1]; k++) {
@@ -649,7 +680,7 @@ __global__ void pp_correct_chunks_kernel(PpChunkParams p) {
                 const uint32_t col = (uint32_t)((eb >> 4) & 0xFFFFFFFFull);
                 if (col <= row) continue;
                 const int c = pp_corr(ma, (uint32_t)(eb & 15));
-                if (c) atomicAdd(p.out + row_base + (col - row - 1), c);
+                if (c) pp_add(p.out, p.op, row_base + (col - p.s_colbase), c);
             }
         }
     }
@@ -723,7 +754,6 @@ __global__ void build_tile_list_kernel(uint32_t gx, uint32_t gy, uint32_t raster
 }
 
 // ---- the GEMM kernel ----------------------------------------------------------------------------------
-enum OutMode { OUT_RAW_I32 = 0, OUT_DIV3_U32 = 1, OUT_DIV3_U16 = 2 };
 struct TcParams {
     uint32_t n_b, row0, row_end, col_block0;   // col_block0 in units of tn
     uint32_t tn;                               // tile columns: 256 (kind::i8) or 240 (kind::mxf4: 16 TMEM columns per
@@ -739,10 +769,15 @@ struct TcParams {
     uint32_t nacc;         // accumulators (integer counts) computed by this launch: work items = nacc x tiles
     uint32_t npairs[5];    // plane pairs summed into each accumulator
     uint8_t pa[5][4], pb[5][4];  // stored-plane index of the A / B operand of each pair
-    uint64_t acc_stride;   // OUT_RAW_I32: results of accumulator a start at out + a * acc_stride
+    uint64_t acc_off[5];   // byte offset (from out) of the array accumulator a is stored to
+    uint8_t acc_op[5];     // AccOp of accumulator a
+    // s_pitch != 0: `out` is a SCRATCH buffer: every accumulator array is the rectangle [panel rows][s_pitch] of the
+    // launch's tiles (element (row, col) at (row - row0) * s_pitch + col - s_colbase; s_pitch = gx * tn, so every
+    // 32-column chunk of every tile row starts 32-byte aligned and an epilogue lane stores its row's chunk straight from
+    // registers with 128-bit stores).  s_pitch == 0: `out` holds the final n / n_high counts in the reference's order.
+    uint32_t s_pitch, s_colbase;
     uint32_t stages;       // pipeline depth in use (<= STAGES; tuning knob)
-    int out_mode;          // OUT_RAW_I32: out = acc (int32 scratch);  OUT_DIV3_*: out = acc / 3 = DIFF (n / n_high, no
-                           // both-partial correction pending), as uint32 or uint16
+    unsigned long long* probe;  // DG_CLOCK_PROBE (debug): [4] += SM clocks, [5] += ns of this launch (CTA 0); or NULL
 };
 
 // Tile order: bands of RASTER_G row blocks, column-major inside a band, so the tiles in flight cover a
@@ -788,6 +823,128 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
 // written once), accumulation is fp32 and exact for these integer sums (|sum| <= 3 x 4 x 29,952 << 2^24; checked on
 // the device by tools/ubench_fp4 and by the parity suite).  Twice the MACs per instruction (K = 64) at the same issue
 // rate; a tile is 512 x 240 because the scale factors need TMEM columns next to the two accumulators.
+// Epilogue of one work item for one epilogue warp: the warp owns TMEM lane quadrant `quad` (32 rows of each 128-row
+// sub-tile); tcgen05.ld hands each lane one ROW of a 32-column chunk.
+//
+// epi_drain_scratch: the output is the tile-aligned scratch rectangle (TcParams::s_pitch), so each lane stores the 32
+// values of its row straight from registers: 4 (16-bit) or 8 (32-bit) 128-bit stores, no transpose, no per-row index.
+template <int OP, bool FP4, int TNX, int MT>
+__device__ __forceinline__ void epi_drain_scratch(const TcParams& p, uint8_t* outb, uint32_t tacc, uint32_t lane, uint32_t rowQ0,
+                                                  uint32_t rowB0) {
+    using T = typename std::conditional<acc_op_16(OP), uint16_t, uint32_t>::type;
+    constexpr uint32_t NCH = (TNX + 31) / 32;
+#pragma unroll 1
+    for (int m = 0; m < MT; m++) {
+        const uint32_t rq0 = rowQ0 + m * TM;   // first row of this warp's quadrant
+        if (rq0 >= p.row_end) continue;         // warp-uniform
+        const bool rv = rq0 + lane < p.row_end;
+        T* const rowp = reinterpret_cast<T*>(outb) + (uint64_t)(rq0 + lane - p.row0) * p.s_pitch + (rowB0 - p.s_colbase);
+#pragma unroll 1
+        for (uint32_t c = 0; c < NCH; c++) {
+            const uint32_t col0 = rowB0 + c * 32;
+            if (col0 >= p.n_b) break;                                   // warp-uniform
+            if (p.square && col0 + 32 <= rq0 + 1) continue;             // chunk entirely on / below the diagonal
+            uint32_t v[32];
+            tc_ld32(tacc + m * TN + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                int x = FP4 ? __float2int_rn(__uint_as_float(v[j])) : (int)v[j];   // fp32 sums are integers
+                if (acc_op_div3(OP)) x = (int)((uint32_t)x / 3u);
+                v[j] = (uint32_t)x;
+            }
+            const bool whole = TNX % 32 == 0 || c + 1 < NCH;   // the last chunk of a 240-column tile holds 16 columns
+            if (rv) {
+                uint4* d = reinterpret_cast<uint4*>(rowp + c * 32);
+                if (sizeof(T) == 2) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int k = 0; k < 16; k++) w[k] = (v[2 * k] & 0xFFFFu) | (v[2 * k + 1] << 16);
+                    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+                    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    if (whole) {
+                        d[2] = make_uint4(w[8], w[9], w[10], w[11]);
+                        d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) d[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    if (whole) {
+#pragma unroll
+                        for (int k = 4; k < 8; k++) d[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// epi_drain_final: the output holds the final counts in the reference's order (rows of a packed triangle are not
+// aligned), so the chunk is transposed through a private conflict-free shared buffer and every store instruction writes
+// 32 consecutive results of one row.  Interior chunks (32 whole rows, right of the diagonal) take a fully unrolled
+// path: 32 independent LDS + STG with incremental 64-bit offsets.
+template <int OP, bool FP4, int TNX, int MT>
+__device__ __forceinline__ void epi_drain_final(const TcParams& p, uint8_t* outb, uint32_t* ebuf, uint32_t tacc, uint32_t lane,
+                                                uint32_t rowQ0, uint32_t rowB0) {
+    using T = typename std::conditional<acc_op_16(OP), uint16_t, uint32_t>::type;
+    T* const out = reinterpret_cast<T*>(outb);
+#pragma unroll 1
+    for (int m = 0; m < MT; m++) {
+        const uint32_t rq0 = rowQ0 + m * TM;   // first row of this warp's quadrant
+        if (rq0 >= p.row_end) continue;         // warp-uniform
+        const uint32_t nrows = min(32u, p.row_end - rq0);
+        // index of (rq0, column 0) [rect] / of the virtual element (rq0, rq0 + 1) [square] in the panel
+        const uint64_t base0 = p.square ? (uint64_t)rq0 * (2 * p.n_total - rq0 - 1) / 2 - p.out_base
+                                        : (uint64_t)(rq0 - p.row0) * p.n_b;
+#pragma unroll 1
+        for (uint32_t c = 0; c < (TNX + 31) / 32; c++) {
+            const uint32_t col0 = rowB0 + c * 32;
+            if (col0 >= p.n_b) break;                                   // warp-uniform
+            if (p.square && col0 + 32 <= rq0 + 1) continue;             // chunk entirely on / below the diagonal
+            uint32_t v[32];
+            tc_ld32(tacc + m * TN + c * 32, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                uint32_t x = FP4 ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];   // fp32 sums are integers
+                if (acc_op_div3(OP)) x /= 3u;
+                ebuf[lane * EPI_PITCH + j] = x;
+            }
+            __syncwarp();
+            const uint32_t col = col0 + lane;
+            const bool lv = col < p.n_b && (TNX % 32 == 0 || c * 32 + lane < TNX);
+            if (nrows == 32 && (!p.square || col0 > rq0 + 31)) {
+                // interior chunk: every row is whole and right of the diagonal
+                uint64_t off = base0 + (p.square ? (uint64_t)(col - rq0 - 1) : (uint64_t)col);
+                const uint32_t step0 = p.square ? (uint32_t)(p.n_total - rq0 - 2) : p.n_b;   // off(r + 1) - off(r) = step0 - r | n_b
+                if (p.square) {
+#pragma unroll
+                    for (uint32_t r = 0; r < 32; r++) {
+                        const uint32_t val = ebuf[r * EPI_PITCH + lane];
+                        if (lv) out[off] = (T)val;
+                        off += (uint64_t)(step0 - r);
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t r = 0; r < 32; r++) {
+                        const uint32_t val = ebuf[r * EPI_PITCH + lane];
+                        if (lv) out[off] = (T)val;
+                        off += (uint64_t)step0;
+                    }
+                }
+            } else {
+                uint64_t rb = base0;
+#pragma unroll 4
+                for (uint32_t r = 0; r < nrows; r++) {
+                    const uint32_t row = rq0 + r;
+                    const uint32_t val = ebuf[r * EPI_PITCH + lane];
+                    if (lv && (!p.square || col > row)) out[p.square ? rb + (col - row - 1) : rb + col] = (T)val;
+                    rb += p.square ? (uint64_t)(p.n_total - row - 1) : (uint64_t)p.n_b;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 template <int CL, int MT, bool PAIR = false, bool FP4 = false>
 __global__ void __launch_bounds__(THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
@@ -847,6 +1004,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (CL > 1) cluster_sync_all();   // the peer's barriers (and scale factors) exist before anything is sent to them
     tc_fence_after();
+    unsigned long long probe_clk = 0, probe_ns = 0;
+    if (p.probe && blockIdx.x == 0 && threadIdx.x == 0) {
+        probe_clk = clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(probe_ns));
+    }
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -928,9 +1090,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===== epilogue: TMEM -> registers -> shared-memory transpose -> coalesced stores, reference order =====
-        // tcgen05.ld hands each lane one ROW of the accumulator; storing from there would scatter every
-        // warp store over 32 rows (32 partial sectors).  Each warp transposes its 32 x 32 chunk through a
-        // private conflict-free buffer so that one store instruction writes 32 consecutive results of one row.
         const uint32_t quad = warp & 3;  // warps 2,3,4,5 -> TMEM lane quadrants 2,3,0,1
         uint32_t* ebuf = reinterpret_cast<uint32_t*>(smem + 192 * 1024 + 256) + quad * (32 * EPI_PITCH);
         uint32_t it = 0;
@@ -938,45 +1097,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t a = w / ntiles, t = w - a * ntiles;
             uint32_t rowA0, rowB0;
             if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
-            uint32_t* const outw = reinterpret_cast<uint32_t*>(p.out) + (uint64_t)a * p.acc_stride;
+            uint8_t* const outb = reinterpret_cast<uint8_t*>(p.out) + p.acc_off[a];
             const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(tfull + ab, aphase);
             tc_fence_after();
-#pragma unroll 1
-            for (int m = 0; m < MT; m++) {
-                const uint32_t rq0 = rowA0 + m * TM + quad * 32;   // first row of this warp's quadrant
-                if (rq0 >= p.row_end) continue;                     // warp-uniform
-                const uint32_t nrows = min(32u, p.row_end - rq0);
-                // index of (rq0, column 0) [rect] / of the virtual element (rq0, rq0 + 1) [square] in the panel
-                const uint64_t base0 = p.square ? (uint64_t)rq0 * (2 * p.n_total - rq0 - 1) / 2 - p.out_base
-                                                : (uint64_t)(rq0 - p.row0) * p.n_b;
-#pragma unroll 1
-                for (uint32_t c = 0; c < (TNX + 31) / 32; c++) {
-                    const uint32_t col0 = rowB0 + c * 32;
-                    if (col0 >= p.n_b) break;                                   // warp-uniform
-                    if (p.square && col0 + 32 <= rq0 + 1) continue;             // chunk entirely on / below the diagonal
-                    uint32_t v[32];
-                    tc_ld32(tmem_base + ((quad * 32u) << 16) + (ab + m) * TN + c * 32, v);
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const uint32_t x = FP4 ? (uint32_t)__float2int_rn(__uint_as_float(v[j])) : v[j];   // fp32 sums are integers
-                        ebuf[lane * EPI_PITCH + j] = p.out_mode == OUT_RAW_I32 ? x : x / 3u;
-                    }
-                    __syncwarp();
-                    const uint32_t col = col0 + lane;
-                    uint64_t rb = base0;
-                    for (uint32_t r = 0; r < nrows; r++) {
-                        const uint32_t row = rq0 + r;
-                        const uint32_t val = ebuf[r * EPI_PITCH + lane];
-                        if (col < p.n_b && (!p.square || col > row) && (TNX % 32 == 0 || c * 32 + lane < TNX)) {
-                            const uint64_t idx = p.square ? rb + (col - row - 1) : rb + col;
-                            if (p.out_mode == OUT_DIV3_U16) reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)val;
-                            else outw[idx] = val;
-                        }
-                        rb += p.square ? (uint64_t)(p.n_total - row - 1) : (uint64_t)p.n_b;
-                    }
-                    __syncwarp();
+            const uint32_t tacc = tmem_base + ((quad * 32u) << 16) + ab * TN;
+            const uint32_t rowQ0 = rowA0 + quad * 32;
+            if (p.s_pitch) {
+                switch (p.acc_op[a]) {   // warp-uniform
+                case ACC_RAW_I32: epi_drain_scratch<ACC_RAW_I32, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
+                case ACC_RAW_I16: epi_drain_scratch<ACC_RAW_I16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
+                case ACC_MOD16: epi_drain_scratch<ACC_MOD16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
+                case ACC_DIV3_U32: epi_drain_scratch<ACC_DIV3_U32, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
+                default: epi_drain_scratch<ACC_DIV3_U16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 }
+            } else if (p.acc_op[a] == ACC_DIV3_U16) {
+                epi_drain_final<ACC_DIV3_U16, FP4, TNX, MT>(p, outb, ebuf, tacc, lane, rowQ0, rowB0);
+            } else {
+                epi_drain_final<ACC_DIV3_U32, FP4, TNX, MT>(p, outb, ebuf, tacc, lane, rowQ0, rowB0);
             }
             tc_fence_before();
             __syncwarp();
@@ -989,6 +1127,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+    if (p.probe && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        atomicAdd(p.probe + 4, (unsigned long long)clock64() - probe_clk);
+        atomicAdd(p.probe + 5, ns - probe_ns);
+    }
     if (CL > 1) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
     if (warp == 1) {
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -1004,34 +1148,59 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   tn93      : acc0 = L, acc1 = PP = SP + P1, acc2 = YY = SY + P2, acc3 = SP - P1, acc4 = SY - P2
 enum ResultKind { RES_U32 = 0, RES_F64 = 1, RES_U16 = 2, RES_COUNTS = 3 };
 struct CombineParams {
-    const int* acc;         // [nacc][panel pairs]
-    uint64_t acc_stride;    // pairs per accumulator
+    const uint8_t* acc;     // scratch: accumulator a's array starts at acc + acc_off[a] and holds acc_op[a] values,
+    uint64_t acc_off[5];    // element (row, col) at (row - row0) * s_pitch + col - s_colbase (TcParams)
+    uint8_t acc_op[5];
+    uint32_t s_pitch, s_colbase;
     const uint32_t* a_acgt; const uint32_t* b_acgt;
     uint32_t n_b, row0, row_end, col0;
     int square, swap_roles, measure, fam, result;
+    int literal;            // DG_EPI_LITERAL (tests): evaluate the f64 epilogues with plain divisions (epi_*_ref)
     uint64_t n_total, out_base;
     void* out;              // uint32 / uint16 / double [pairs], or uint4[pairs] canonical counts (dg_debug_counts)
 };
+__device__ __forceinline__ int load_acc(const CombineParams& p, int a, uint64_t idx) {
+    const uint8_t* b = p.acc + p.acc_off[a];
+    switch (p.acc_op[a]) {
+    case ACC_RAW_I32: return reinterpret_cast<const int*>(b)[idx];
+    case ACC_RAW_I16: return (int)reinterpret_cast<const int16_t*>(b)[idx];
+    case ACC_DIV3_U32: return (int)reinterpret_cast<const uint32_t*>(b)[idx];
+    default: return (int)reinterpret_cast<const uint16_t*>(b)[idx];   // ACC_DIV3_U16, ACC_MOD16
+    }
+}
+// accumulator 0 of n / n_high / raw / jc69 -> DIFF
+__device__ __forceinline__ uint32_t diff_of(int op, int a0) {
+    if (acc_op_div3(op)) return (uint32_t)a0;
+    if (op == ACC_MOD16) return ((uint32_t)a0 % 3u == 0u) ? (uint32_t)a0 / 3u : ((uint32_t)a0 + 65536u) / 3u;
+    return (uint32_t)a0 / 3u;
+}
 
-__global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
-    const uint32_t col = p.col0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= p.n_b) return;
-    for (uint32_t row = p.row0 + blockIdx.y; row < p.row_end; row += gridDim.y) {
+// Grid: a FIXED number of CTAs (2 per SM), each walking virtual blocks (256-column strip x row phase).  A grid sized by the
+// work (thousands of small CTAs) would take every register of every SM the moment the previous GEMM drains, and the next
+// panel's persistent GEMM CTA (1 per SM, ~24 K registers + 211 KB of shared memory) would find no room until the whole
+// combine pass is over: the f64 pass and the tensor pass would run back to back instead of side by side (measured: no
+// overlap at all).  Two resident CTAs per SM leave the GEMM its place.
+__global__ void __launch_bounds__(256, 2) tc_combine_kernel(CombineParams p, uint32_t gx, uint32_t gy) {
+    for (uint32_t vb = blockIdx.x; vb < gx * gy; vb += gridDim.x) {
+    const uint32_t bx = vb % gx, by = vb / gx;
+    const uint32_t col = p.col0 + bx * blockDim.x + threadIdx.x;
+    if (col >= p.n_b) continue;
+    for (uint32_t row = p.row0 + by; row < p.row_end; row += gy) {
         if (p.square && col <= row) continue;
         const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
                                       : (uint64_t)(row - p.row0) * p.n_b + col;
-        const int a0 = p.acc[idx];
-        const int a1 = p.fam != FAM_SNP ? p.acc[p.acc_stride + idx] : 0;
+        const uint64_t sidx = (uint64_t)(row - p.row0) * p.s_pitch + (col - p.s_colbase);
+        const int a0 = load_acc(p, 0, sidx);
+        const int a1 = p.fam != FAM_SNP ? load_acc(p, 1, sidx) : 0;
         uint4 cnt = make_uint4(0, 0, 0, 0);
         if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
-            cnt = make_uint4((uint32_t)a0 / 3u, (uint32_t)a1, 0, 0);  // {n, same}
+            cnt = make_uint4(diff_of(p.acc_op[0], a0), (uint32_t)a1, 0, 0);  // {n, same}
         } else if (p.fam == FAM_K80) {
-            const int tv = p.acc[2 * p.acc_stride + idx];
+            const int tv = load_acc(p, 2, sidx);
             const int same = (a0 + a1) >> 1, ts = (a0 - a1) >> 1;
             cnt = make_uint4((uint32_t)same, (uint32_t)(ts + tv), (uint32_t)tv, 0);  // {same, ts + tv, tv}
         } else {
-            const int yy = p.acc[2 * p.acc_stride + idx], ww = p.acc[3 * p.acc_stride + idx],
-                      zz = p.acc[4 * p.acc_stride + idx];
+            const int yy = load_acc(p, 2, sidx), ww = load_acc(p, 3, sidx), zz = load_acc(p, 4, sidx);
             const int sp = (a1 + ww) >> 1, p1 = (a1 - ww) >> 1, sy = (yy + zz) >> 1, p2 = (yy - zz) >> 1;
             cnt = make_uint4((uint32_t)a0, (uint32_t)(a0 - sp - sy), (uint32_t)p1, (uint32_t)p2);  // {L, d, P1, P2}
         }
@@ -1040,13 +1209,14 @@ __global__ void __launch_bounds__(256) tc_combine_kernel(CombineParams p) {
         if (p.result == RES_U16) { reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)cnt.x; continue; }
         double r;
         if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
-        else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z);
+        else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z, p.literal != 0);
         else {
             const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
             const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
-            r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc);
+            r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc, p.literal != 0);
         }
         reinterpret_cast<double*>(p.out)[idx] = r;
+    }
     }
 }
 

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define DG_ABI_VERSION 1
+#define DG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define DG_API __attribute__((visibility("default")))
@@ -147,6 +147,9 @@ typedef struct {
     uint64_t h2d_bytes;
     uint64_t d2h_bytes;
     uint64_t engine;      /* engine of the last run: 1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 int8 GEMM, 3 = tcgen05 fp4 GEMM */
+    double sm_mhz;        /* ABI 2: SM clock the tensor-engine launches since the last reset actually ran at (clock64 /
+                             globaltimer around each launch, first device); 0 when no such launch ran.  nvidia-smi's
+                             200 ms samples miss the few-ms dips of a power-capped burst; this does not. */
 } dg_timings;
 
 DG_API int dg_abi_version(void);

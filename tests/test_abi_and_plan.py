@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(api):
     lib = api.load_library()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.dg_abi_version() == 1
+    assert lib.dg_abi_version() == 2
 
 
 def test_no_cpu_fallback(api):
