@@ -8,6 +8,7 @@ back to the CPU: if the library is missing it raises.
 """
 from .api import (  # noqa: F401
     DG_INPUT_ASCII,
+    DG_INPUT_NIBBLE,
     DG_INPUT_PARADIS,
     MEASURES,
     DistanceGpuError,
@@ -16,9 +17,10 @@ from .api import (  # noqa: F401
     device_count,
     library_path,
     load_library,
+    pack_nibbles,
 )
 
 __all__ = [
-    "Engine", "DistanceGpuError", "MEASURES", "DG_INPUT_ASCII", "DG_INPUT_PARADIS",
+    "Engine", "DistanceGpuError", "MEASURES", "DG_INPUT_ASCII", "DG_INPUT_PARADIS", "DG_INPUT_NIBBLE", "pack_nibbles",
     "build_library", "load_library", "library_path", "device_count",
 ]

@@ -15,7 +15,7 @@ _ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _LIB_PATH = os.path.join(_ROOT, "distance_b200", "_lib", "libdistance_gpu.so")
 
 MEASURES = {"n": 0, "n_high": 1, "raw": 2, "jc69": 3, "k80": 4, "tn93": 5}
-DG_INPUT_PARADIS, DG_INPUT_ASCII = 0, 1
+DG_INPUT_PARADIS, DG_INPUT_ASCII, DG_INPUT_NIBBLE = 0, 1, 2
 DG_MODE_SQUARE, DG_MODE_RECT, DG_MODE_STREAM = 0, 1, 2
 DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
 DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16, DG_OPT_PIPE_PANELS = 1, 2, 3, 4, 5, 6
@@ -168,6 +168,22 @@ def plan_panels(measure: str, mode: int, n_rows: int, n_cols: int, panel_bytes: 
     return [(int(rb[k]), int(re_[k]), int(nr[k])) for k in range(n)]
 
 
+def pack_nibbles(codes: np.ndarray) -> np.ndarray:
+    """Paradis bytes (n x width) -> DG_INPUT_NIBBLE rows (n x (width + 1) // 2): site 2k in the low nibble of byte k, site
+    2k + 1 in the high one; a nibble is the possibility half of the code (N, '-' and '?' all become 15).  This is what a
+    host parser would emit directly; tests and bench.py derive it from the byte codes."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    n, w = codes.shape
+    hi = codes >> 4
+    if w % 2:
+        hi = np.concatenate([hi, np.full((n, 1), 15, np.uint8)], axis=1)
+    return np.ascontiguousarray(hi[:, 0::2] | (hi[:, 1::2] << 4))
+
+
+def input_stride(width: int, input_kind: int) -> int:
+    return (width + 1) // 2 if input_kind == DG_INPUT_NIBBLE else width
+
+
 def pinned_array(shape, dtype) -> np.ndarray:
     """A numpy array over page-locked memory from dg_alloc_pinned (freed with the process)."""
     L = load_library()
@@ -231,7 +247,7 @@ class Engine:
     # -- inputs ----------------------------------------------------------------------------------
     def load(self, which: int, codes: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
-        assert codes.ndim == 2 and codes.shape[1] == self.width
+        assert codes.ndim == 2 and codes.shape[1] == input_stride(self.width, input_kind)
         cnt = None if acgt is None else np.ascontiguousarray(acgt, dtype=np.uint64)
         self._check(self.L.dg_load_resident(
             self.h, which, codes.ctypes.data_as(C.c_void_p), codes.shape[0], input_kind,
@@ -332,7 +348,8 @@ class Engine:
         order the sink saw them.  `push(lo, hi)` may replace the default host-pointer push (multi-rank tests)."""
         codes = np.ascontiguousarray(codes, dtype=np.uint8)
         n = codes.shape[0]
-        assert codes.ndim == 2 and codes.shape[1] == self.width
+        stride = input_stride(self.width, input_kind)
+        assert codes.ndim == 2 and codes.shape[1] == stride
         dtype = self._dtype()
         out = np.zeros(n * (n - 1) // 2, dtype=dtype)
         panels = []
@@ -363,7 +380,7 @@ class Engine:
                 if push is not None:
                     push(int(lo.value), int(hi.value))
                 else:
-                    self._check(self.L.dg_square_push(self.h, C.c_void_p(codes.ctypes.data + lo.value * self.width), -1,
+                    self._check(self.L.dg_square_push(self.h, C.c_void_p(codes.ctypes.data + lo.value * stride), -1,
                                                       lo.value, hi.value, None))
             self._check(self.L.dg_square_end(self.h))
         self._n[0] = n
@@ -396,7 +413,7 @@ class Engine:
         else:
             self._check(self.L.dg_rect_begin(self.h, n, input_kind, cptr, part, n_parts, cb, None))
             for lo, hi in self.square_plan():
-                self.square_push(codes_a.ctypes.data + lo * self.width, -1, lo, hi)
+                self.square_push(codes_a.ctypes.data + lo * input_stride(self.width, input_kind), -1, lo, hi)
             self.square_end()
         self._n[0] = n
         self.last_panels = panels
@@ -415,6 +432,7 @@ class Engine:
             return 0
 
         n = pinned_codes.shape[0]
+        assert pinned_codes.shape[1] == input_stride(self.width, input_kind)
         self._check(self.L.dg_run_square_host(self.h, C.c_void_p(pinned_codes.ctypes.data), n, input_kind, None,
                                               part, n_parts, SINK_FN(sink), None))
         self._n[0] = n

@@ -96,6 +96,8 @@ struct PlaneSet {  // one alignment packed on one device
     uint4* aux = nullptr;
     uint32_t* acgt = nullptr;
     uint8_t* codes = nullptr;  // kept only with DG_OPT_KEEP_CODES
+    uint8_t* nib = nullptr;    // DG_INPUT_NIBBLE: the uploaded nibble rows (unpacked into `codes` on the device)
+    uint64_t nib_cap = 0;      // bytes
     int input_kind = 0;
     bool acgt_from_host = false;
     uint64_t cap_pad = 0;     // resident sets: record capacity of codes / acgt / tc_ops (buffers are reused across loads)
@@ -118,10 +120,11 @@ struct Slot {  // one stage of the result ring (and of the stream-input ring)
     uint32_t* d_tiles = nullptr;    // tcgen05 engine, square panels: live-tile list of this slot's launch
     uint32_t* h_tiles = nullptr;    // pinned staging of the same
     size_t tiles_cap = 0;
-    cudaEvent_t k_start = nullptr, k_stop = nullptr, copied = nullptr, in_ready = nullptr;
+    cudaEvent_t k_start = nullptr, k_stop = nullptr, copied = nullptr, in_ready = nullptr, gemm_done = nullptr;
     // stream mode staging
     uint8_t* h_in = nullptr;
     uint8_t* d_in = nullptr;
+    uint8_t* d_nib = nullptr;       // DG_INPUT_NIBBLE batches land here and are unpacked into d_in
     uint32_t* h_acgt = nullptr;
     PlaneSet batch;
     cudaEvent_t p_start = nullptr, p_stop = nullptr;
@@ -132,9 +135,12 @@ struct Device {
     // compute = stream of ring slot 0 (also packs / resident loads), compute2 = stream of ring slot 1:
     // consecutive panels alternate streams so the tail wave of one launch overlaps the next launch.
     cudaStream_t compute = nullptr, compute2 = nullptr, copy = nullptr, copy_in = nullptr;
-    cudaStream_t cs(int slot) const { return slot ? compute2 : compute; }
+    cudaStream_t cs(int slot) const { return (slot & 1) ? compute2 : compute; }
+    cudaStream_t post = nullptr;   // repair + combine passes of resident panels: behind their GEMM through an event, so the next
+                                   // panel's GEMM (the other compute stream) never queues behind an f64 pass
     PlaneSet set[2];
-    Slot slot[2];
+    static constexpr int NSLOT = 3;   // result ring of resident panels (stream sessions use the first two slots)
+    Slot slot[NSLOT];
     size_t out_cap = 0;   // bytes of d_out / h_out
     size_t in_cap = 0;    // records of stream staging
     cudaEvent_t run_start = nullptr, run_stop = nullptr;
@@ -239,7 +245,8 @@ struct dg_ctx {
     size_t sq_pushed = 0, sq_pumped = 0;
     std::vector<uint32_t> sq_base;     // entries before chunk g (size chunks + 1), known once chunk g-1 is pumped
     uint64_t sq_n = 0, sq_launched = 0;
-    int sq_input_kind = 0;
+    int sq_input_kind = 0;             // what the pack kernels see (nibble input is unpacked to Paradis bytes first)
+    bool sq_nibble = false;            // the session's chunks arrive as DG_INPUT_NIBBLE rows
     dg_sink_fn sq_sink = nullptr;
     void* sq_user = nullptr;
     std::vector<InFlight> sq_queue;
@@ -272,6 +279,7 @@ void free_set(PlaneSet& s) {
     if (s.aux) cudaFree(s.aux);
     if (s.acgt) cudaFree(s.acgt);
     if (s.codes) cudaFree(s.codes);
+    if (s.nib) cudaFree(s.nib);
     s = PlaneSet{};
 }
 
@@ -556,6 +564,8 @@ struct AccPlan {
     uint8_t op[5] = {};
     uint64_t off[5] = {};   // byte offsets from the launch's output pointer
     uint32_t s_pitch = 0, s_colbase = 0;   // scratch rectangle (tc::TcParams); 0 = final counts in the reference's order
+    uint32_t ksplit = 1;                   // > 1: split-K launch, every op is ACC_ADD_I32 and `bytes` of scratch are zeroed first
+    size_t bytes = 0;
 };
 // n / n_high with no repair pending: the GEMM writes the final counts
 AccPlan direct_plan(const dg_ctx* c) {
@@ -585,7 +595,7 @@ size_t scratch_upper_bound(const dg_ctx* c, bool fp4, int mode, uint64_t row0, u
 // 3 * DIFF (up to 3 * width): while the both-partial repair is pending it is kept modulo 2^16 (or as int32 for wide
 // alignments) and pp_correct adds to it; else DIFF itself is stored.  Every other sum lies in [-width, width] and is
 // stored as int16 when that fits.
-AccPlan scratch_plan(const dg_ctx* c, bool fp4, int mode, const Panel& p, uint64_t n_b, bool pp_pending) {
+AccPlan scratch_plan(const dg_ctx* c, bool fp4, int mode, const Panel& p, uint64_t n_b, bool pp_pending, uint32_t ksplit = 1) {
     static const bool force32 = std::getenv("DG_SCRATCH_I32") != nullptr;
     const TcSchedule& sch = tc_schedule(c->fam);
     const ScratchGeom g = scratch_geom(fp4, mode, p.row0, p.row1, n_b);
@@ -598,10 +608,13 @@ AccPlan scratch_plan(const dg_ctx* c, bool fp4, int mode, const Panel& p, uint64
         int op;
         if (k == 0 && sch.needs_pp) op = pp_pending ? (narrow ? tc::ACC_MOD16 : tc::ACC_RAW_I32) : (narrow ? tc::ACC_DIV3_U16 : tc::ACC_DIV3_U32);
         else op = narrow ? tc::ACC_RAW_I16 : tc::ACC_RAW_I32;
+        if (ksplit > 1) op = tc::ACC_ADD_I32;
         a.op[k] = (uint8_t)op;
         a.off[k] = off;
         off += ((uint64_t)g.rows * g.pitch * (tc::acc_op_16(op) ? 2 : 4) + 255) / 256 * 256;
     }
+    a.ksplit = ksplit;
+    a.bytes = (size_t)off;
     return a;
 }
 
@@ -647,6 +660,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     }
     for (uint32_t a = 0; a < tp.nacc; a++) { tp.acc_off[a] = plan.off[a]; tp.acc_op[a] = plan.op[a]; }
     tp.s_pitch = plan.s_pitch; tp.s_colbase = plan.s_colbase;
+    tp.ksplit = std::max<uint32_t>(1, plan.ksplit);
     if (plan.s_pitch && (plan.s_pitch != tp.gx * tp.tn || plan.s_colbase != tp.col_block0 * tp.tn))
         fail(DG_ERR_STATE, "internal: scratch geometry does not match the launch's tiles");
     tp.probe = d.clk_probe;
@@ -688,7 +702,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         tp.tile_list = ws->d_tiles; tp.n_live = n_live;
         live = n_live;
     }
-    const uint64_t tiles = live * tp.nacc;
+    const uint64_t tiles = live * tp.nacc * tp.ksplit;
     if (cl == 1) {
         auto kern = mt == 2 ? tc::tc_gemm_kernel<1, 2> : tc::tc_gemm_kernel<1, 1>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
@@ -735,12 +749,12 @@ void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
     cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
     cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
-    // virtual blocks: 256-column strips x row phases (~16 per SM); a fixed grid of 2 CTAs per SM walks them
+    // virtual blocks: 256-column strips x row phases (~16 per SM)
     const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
     const unsigned gy = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(p.row1 - p.row0, (uint64_t)g_num_sms(d.id) * 16 / std::max(1u, gx)));
     if (gx == 0) return;
-    static const int per_sm = std::getenv("DG_COMBINE_PER_SM") ? std::max(1, std::atoi(std::getenv("DG_COMBINE_PER_SM"))) : 2;
-    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)gx * gy, (uint64_t)g_num_sms(d.id) * per_sm);
+    static const int per_sm = std::getenv("DG_COMBINE_PER_SM") ? std::max(0, std::atoi(std::getenv("DG_COMBINE_PER_SM"))) : 0;
+    const unsigned grid = per_sm ? (unsigned)std::min<uint64_t>((uint64_t)gx * gy, (uint64_t)g_num_sms(d.id) * per_sm) : gx * gy;
     tc::tc_combine_kernel<<<grid, 256, 0, st>>>(cp, gx, gy);
     CUDA_CHECK(cudaGetLastError());
     c->tm.count_launches++;
@@ -749,19 +763,52 @@ void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
 // tcgen05 variant of enqueue_panel_kernel.  n / n_high with no correction pending: one GEMM writes the result
 // directly.  Otherwise (and for the debug counts): one GEMM per accumulator into `scratch`, the both-partial
 // repair of accumulator 0, then tc_combine_kernel.
-void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
-                      void* d_out, int* scratch, bool swap_roles, bool counts, cudaStream_t st, bool a_is_batch = false,
-                      Slot* ws = nullptr) {
+uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols, uint64_t tn = 256);
+
+// Split-K for small launches: a panel with fewer work items than CTA pairs leaves most of the chip idle while a few
+// pairs walk the whole K range (1,000 x 1,000 records: 16 items of 468 K blocks on 74 pairs).  Dealing each tile's K
+// range to `ks` pairs (partial sums added into a zeroed int32 scratch) fills the chip.  Cost model in K blocks: rounds x
+// (blocks per item + a fixed ~30 for the launch ramp, the epilogue and its atomics); split only for a clear win.
+uint32_t choose_ksplit(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p) {
+    const char* fe = std::getenv("DG_KSPLIT");   // tests: 1 = never split, k = always k ways
+    const int forced = fe ? std::atoi(fe) : 0;
+    const TcSchedule& sch = tc_schedule(c->fam);
+    const uint64_t KT = (uint64_t)sch.npairs[0] * (A.tc_wp8 / tc::KB);
+    if (forced > 0) return (uint32_t)std::min<uint64_t>(forced, std::max<uint64_t>(1, KT));
+    const uint64_t items = live_pair_tiles(mode, p.row0, p.row1, B.n, A.tc_fp4 ? tc::TN_FP4 : tc::TN) * sch.nacc;
+    const uint64_t slots = 74, ovh = 30;
+    if (items == 0 || items >= 2 * slots) return 1;
+    auto cost = [&](uint64_t ks) { return (items * ks + slots - 1) / slots * (KT / ks + ovh); };
+    uint64_t best = 1, best_cost = cost(1);
+    for (uint64_t ks = 2; ks <= 16 && KT / ks >= 16; ks++)
+        if (cost(ks) < best_cost) { best_cost = cost(ks); best = ks; }
+    return best_cost * 4 <= cost(1) * 3 ? (uint32_t)best : 1u;
+}
+
+// Returns the stream that carries the panel's last kernel: `st`, or `post` when the repair + combine passes were put
+// there (behind `ws->gemm_done`).
+cudaStream_t enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p,
+                              void* d_out, int* scratch, bool swap_roles, bool counts, cudaStream_t st, bool a_is_batch = false,
+                              Slot* ws = nullptr, cudaEvent_t after_gemm = nullptr, cudaStream_t post = nullptr) {
     const TcSchedule& sch = tc_schedule(c->fam);
     const bool pp_pending = tc_pp_pending(c, A, B, a_is_batch);
-    if (c->fam == FAM_SNP && !counts && !pp_pending) {
+    const uint32_t ks = scratch ? choose_ksplit(c, A, B, mode, p) : 1u;
+    if (c->fam == FAM_SNP && !counts && !pp_pending && ks == 1) {
         launch_tc_gemm(c, d, A, B, mode, p, direct_plan(c), d_out, st, ws);
-        return;
+        if (after_gemm) CUDA_CHECK(cudaEventRecord(after_gemm, st));
+        return st;
     }
     if (!scratch) fail(DG_ERR_STATE, "tensor engine: no scratch buffer");
-    const AccPlan plan = scratch_plan(c, A.tc_fp4, mode, p, B.n, pp_pending);
+    const AccPlan plan = scratch_plan(c, A.tc_fp4, mode, p, B.n, pp_pending, ks);
+    if (ks > 1) CUDA_CHECK(cudaMemsetAsync(scratch, 0, plan.bytes, st));
     static const bool skip_gemm = std::getenv("DG_SKIP_GEMM") != nullptr, skip_combine = std::getenv("DG_SKIP_COMBINE") != nullptr;  // timing experiments only
     if (!skip_gemm) launch_tc_gemm(c, d, A, B, mode, p, plan, scratch, st, ws);
+    if (after_gemm) CUDA_CHECK(cudaEventRecord(after_gemm, st));
+    if (post && ws && ws->gemm_done) {   // the rest of the panel runs on the post stream
+        CUDA_CHECK(cudaEventRecord(ws->gemm_done, st));
+        CUDA_CHECK(cudaStreamWaitEvent(post, ws->gemm_done, 0));
+        st = post;
+    }
     if (pp_pending) {
         tc::PpCorrParams cp{};
         cp.b_entries = B.pp.entries; cp.b_off = B.pp.site_off;
@@ -782,6 +829,7 @@ void enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B
         c->tm.count_launches++;
     }
     if (!skip_combine) launch_combine(c, d, A, B, mode, p, d_out, scratch, plan, swap_roles, counts, st);
+    return st;
 }
 
 void ensure_scratch(Slot& s, size_t bytes) {
@@ -795,7 +843,7 @@ void ensure_scratch(Slot& s, size_t bytes) {
 uint64_t sq_off(uint64_t n, uint64_t i) { return i * (2 * n - i - 1) / 2; }
 
 // Live 512 x 256 tiles (the tensor engine's CTA-pair block) of rows [r0, r1) against n_cols columns.
-uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols, uint64_t tn = 256) {
+uint64_t live_pair_tiles(int mode, uint64_t r0, uint64_t r1, uint64_t n_cols, uint64_t tn) {
     const uint64_t col_blocks = (n_cols + tn - 1) / tn;
     if (mode != DG_MODE_SQUARE) return (r1 - r0 + 511) / 512 * col_blocks;
     uint64_t live = 0;
@@ -897,6 +945,28 @@ void harvest_kernel_time(dg_ctx* c, Slot& s) {
     if (cudaEventElapsedTime(&ms, s.k_start, s.k_stop) == cudaSuccess) c->tm.count_ms += ms;
 }
 
+
+// ---- DG_INPUT_NIBBLE -------------------------------------------------------------------------------------------------
+bool valid_input_kind(int k) { return k == DG_INPUT_PARADIS || k == DG_INPUT_ASCII || k == DG_INPUT_NIBBLE; }
+uint64_t input_stride(const dg_ctx* c, int kind) { return kind == DG_INPUT_NIBBLE ? (c->width + 1) / 2 : c->width; }
+// what the pack kernels see: nibble rows are unpacked to Paradis bytes on the device first
+int device_kind(int kind) { return kind == DG_INPUT_NIBBLE ? DG_INPUT_PARADIS : kind; }
+void ensure_nib(dg_ctx* c, PlaneSet& s, uint64_t n) {
+    const uint64_t bytes = n * input_stride(c, DG_INPUT_NIBBLE);
+    if (s.nib_cap >= bytes) return;
+    if (s.nib) cudaFree(s.nib);
+    s.nib = nullptr; s.nib_cap = 0;
+    CUDA_CHECK(cudaMalloc(&s.nib, std::max<uint64_t>(bytes, 16)));
+    s.nib_cap = bytes;
+}
+void enqueue_nibble_unpack(dg_ctx* c, const uint8_t* d_nib, uint8_t* d_codes, uint64_t n, cudaStream_t st) {
+    const uint64_t wb = input_stride(c, DG_INPUT_NIBBLE);
+    const uint64_t units = n * ((wb + 3) / 4);
+    const unsigned grid = (unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 32);
+    tc::nibble_unpack_kernel<<<std::max(1u, grid), 256, 0, st>>>(d_nib, d_codes, n, c->width, wb);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.pack_launches++;
+}
 
 // ---- resident alignments: buffer reuse, pipelined upload, lazy LOP3 planes ---------------------------
 // (Re)size the buffers of a resident alignment; buffers are kept when the new alignment fits.
@@ -1004,6 +1074,8 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
         CUDA_CHECK(cudaSetDevice(d.id));
         CUDA_CHECK(cudaEventRecord(d.slot[1].in_ready, d.compute2));
         CUDA_CHECK(cudaStreamWaitEvent(d.compute, d.slot[1].in_ready, 0));
+        CUDA_CHECK(cudaEventRecord(d.slot[2].in_ready, d.post));
+        CUDA_CHECK(cudaStreamWaitEvent(d.compute, d.slot[2].in_ready, 0));
         CUDA_CHECK(cudaEventRecord(d.run_stop, d.compute));
         CUDA_CHECK(cudaEventSynchronize(d.run_stop));
         float ms = 0;
@@ -1022,6 +1094,21 @@ void run_mode(dg_ctx* c, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn s
 // tensor-bound tiles of this one (a panel needs the records at or above its first row only).
 void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc_run, dg_sink_fn sink, void* user,
                     bool device_only, bool repack_descending) {
+    std::vector<cudaEvent_t> tr0, tr1, tr2;   // DG_TRACE (declared before `dump`, which reads them when the function leaves)
+    struct TraceDump {   // prints and frees the DG_TRACE events when the function leaves
+        std::vector<cudaEvent_t>*a = nullptr, *b = nullptr, *c = nullptr; cudaEvent_t base = nullptr; const std::vector<Panel>* panels = nullptr;
+        ~TraceDump() {
+            if (!a || a->empty()) return;
+            cudaDeviceSynchronize();
+            for (size_t k = 0; k < a->size(); k++) {
+                float t0 = 0, t1 = 0, t2 = 0;
+                cudaEventElapsedTime(&t0, base, (*a)[k]); cudaEventElapsedTime(&t1, base, (*b)[k]); cudaEventElapsedTime(&t2, base, (*c)[k]);
+                fprintf(stderr, "  [dg trace] panel %2zu rows [%6llu,%6llu): start %7.3f  gemm end %7.3f  panel end %7.3f ms\n", k,
+                        (unsigned long long)(*panels)[k].row0, (unsigned long long)(*panels)[k].row1, t0, t1, t2);
+                cudaEventDestroy((*a)[k]); cudaEventDestroy((*b)[k]); cudaEventDestroy((*c)[k]);
+            }
+        }
+    } dump;
     const int wb = mode == DG_MODE_SQUARE ? 0 : 1;
     std::vector<uint64_t> packed_lo(c->devs.size(), c->devs[0].set[0].n);
     const int ndev = (int)c->devs.size();
@@ -1032,7 +1119,10 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
-        if (tc_run && (c->fam != FAM_SNP || tc_pp_pending(c, d.set[0], d.set[wb], false))) {
+        bool any_split = false;
+        if (tc_run)
+            for (auto& p : mine) any_split = any_split || choose_ksplit(c, d.set[0], d.set[wb], mode, p) > 1;
+        if (tc_run && (c->fam != FAM_SNP || any_split || tc_pp_pending(c, d.set[0], d.set[wb], false))) {
             size_t sb = 0;
             for (auto& p : mine) sb = std::max(sb, scratch_upper_bound(c, d.set[0].tc_fp4, mode, p.row0, p.row1, B0.n));
             for (auto& sl : d.slot) ensure_scratch(sl, sb);
@@ -1040,12 +1130,23 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
     }
 
     const int K = (int)mine.size();
-    const int lookahead = 2 * ndev;
+    constexpr int NS = Device::NSLOT;
+    const int lookahead = NS * ndev;
+    // DG_POST_STREAM=1 (experiment): repair + combine passes on a third stream, so that the GEMMs run back to back.  Measured
+    // on configs 2 and 3: no gain (7.03 vs 6.86 ms, 6.57 vs 6.43 ms): the tensor pass and the f64 / repair passes slow each
+    // other down by what the overlap wins (the step runs at the power cap either way), so the simpler order is the default.
+    static const bool use_post = std::getenv("DG_POST_STREAM") != nullptr;
+    // DG_TRACE: device timeline of the panels of device 0 (start, end of the GEMM, end of the panel) on stderr
+    const bool trace = std::getenv("DG_TRACE") != nullptr && ndev == 1;
+    if (trace)
+        for (int k = 0; k < K; k++)
+            for (auto* v : {&tr0, &tr1, &tr2}) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); v->push_back(e); }
+    if (trace) { dump.a = &tr0; dump.b = &tr1; dump.c = &tr2; dump.base = c->devs[0].run_start; dump.panels = &mine; }
     for (int k = 0; k < K + lookahead; k++) {
         const int h = k - lookahead;  // panel to hand to the sink
         if (h >= 0) {
             Device& d = c->devs[h % ndev];
-            Slot& s = d.slot[(h / ndev) & 1];
+            Slot& s = d.slot[(h / ndev) % NS];
             CUDA_CHECK(cudaSetDevice(d.id));
             CUDA_CHECK(cudaEventSynchronize(device_only ? s.k_stop : s.copied));
             harvest_kernel_time(c, s);
@@ -1069,7 +1170,7 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
         }
         if (k < K) {
             Device& d = c->devs[k % ndev];
-            const int si = (k / ndev) & 1;
+            const int si = (k / ndev) % NS;
             Slot& s = d.slot[si];
             CUDA_CHECK(cudaSetDevice(d.id));
             const Panel& p = mine[k];
@@ -1085,9 +1186,13 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
                 CUDA_CHECK(cudaStreamWaitEvent(d.cs(si), d.sq_ready, 0));
             }
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
-            if (tc_run) enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si), false, &s);
+            if (trace) CUDA_CHECK(cudaEventRecord(tr0[k], d.cs(si)));
+            cudaStream_t last = d.cs(si);
+            if (tc_run) last = enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si), false, &s,
+                                                trace ? tr1[k] : nullptr, use_post ? d.post : nullptr);
             else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
-            CUDA_CHECK(cudaEventRecord(s.k_stop, d.cs(si)));
+            CUDA_CHECK(cudaEventRecord(s.k_stop, last));
+            if (trace) CUDA_CHECK(cudaEventRecord(tr2[k], last));
             if (!device_only) {
                 CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
                 CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(),
@@ -1204,6 +1309,12 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
     } else {
         const AccPlan plan = scratch_plan(c, S.tc_fp4, c->sq_mode, p, B.n, repair);
         launch_tc_gemm(c, d, S, B, c->sq_mode, p, plan, s.d_scratch, st, &s, true);
+        static const bool use_post = std::getenv("DG_POST_STREAM") != nullptr;
+        if (use_post) {   // experiment (see run_panel_list): repair + combine on the post stream: the next panel's GEMM does not queue behind them
+            CUDA_CHECK(cudaEventRecord(s.gemm_done, st));
+            CUDA_CHECK(cudaStreamWaitEvent(d.post, s.gemm_done, 0));
+            st = d.post;
+        }
         if (repair && rect) {
             // rows' entries = the chunks that overlap the panel's rows (contiguous in the shared entry buffer),
             // columns = the classic per-site index of the resident alignment 1
@@ -1320,7 +1431,7 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     if (!sink) fail(DG_ERR_INVALID_ARG, "sink is NULL");
     if (n == 0 || n >= (1ull << 31)) fail(DG_ERR_INVALID_ARG, "bad record count");
     if (n_parts == 0 || part >= n_parts) fail(DG_ERR_INVALID_ARG, "bad part %u of %u", part, n_parts);
-    if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+    if (!valid_input_kind(input_kind)) fail(DG_ERR_INVALID_ARG, "bad input_kind");
     Device& d = c->devs[0];
     CUDA_CHECK(cudaSetDevice(d.id));
     c->have_invalid = false;
@@ -1335,14 +1446,16 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     }
     c->sq_mode = mode;
     reserve_resident(c, S, n, want_tc);
-    S.input_kind = input_kind;
+    if (input_kind == DG_INPUT_NIBBLE) ensure_nib(c, S, n);
+    S.input_kind = device_kind(input_kind);
     S.acgt_from_host = acgt_counts != nullptr;
     S.pp_stale = true;
     c->sq_tc = want_tc;
     c->sq_fallback = false;
     c->sq_needs_pp = tc_schedule(c->fam).needs_pp;
     c->sq_n = n;
-    c->sq_input_kind = input_kind;
+    c->sq_input_kind = device_kind(input_kind);
+    c->sq_nibble = input_kind == DG_INPUT_NIBBLE;
     c->sq_sink = sink; c->sq_user = user;
     c->sq_queue.clear();
     c->sq_launched = 0;
@@ -1447,19 +1560,21 @@ void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t
     CUDA_CHECK(cudaSetDevice(d.id));
     const size_t g = c->sq_pushed;
     const uint64_t nr = hi - lo;
-    uint8_t* dst = S.codes + lo * c->width;
+    const uint64_t stride = input_stride(c, c->sq_nibble ? DG_INPUT_NIBBLE : DG_INPUT_PARADIS);
+    uint8_t* dst = c->sq_nibble ? S.nib + lo * stride : S.codes + lo * stride;
     if (ready_event) CUDA_CHECK(cudaStreamWaitEvent(d.copy_in, (cudaEvent_t)ready_event, 0));
     if (src_dev < 0) {
-        CUDA_CHECK(cudaMemcpyAsync(dst, codes, (size_t)nr * c->width, cudaMemcpyHostToDevice, d.copy_in));
-        c->tm.h2d_bytes += nr * c->width;
+        CUDA_CHECK(cudaMemcpyAsync(dst, codes, (size_t)nr * stride, cudaMemcpyHostToDevice, d.copy_in));
+        c->tm.h2d_bytes += nr * stride;
     } else {
-        CUDA_CHECK(cudaMemcpyPeerAsync(dst, d.id, codes, src_dev, (size_t)nr * c->width, d.copy_in));
+        CUDA_CHECK(cudaMemcpyPeerAsync(dst, d.id, codes, src_dev, (size_t)nr * stride, d.copy_in));
     }
     cudaEvent_t ev = d.chunk_ev[g & 31];
     CUDA_CHECK(cudaEventRecord(ev, d.copy_in));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_copy[g], d.copy_in));
     // packing + index scan of this chunk: enqueued now, runs as soon as the copy has landed
     CUDA_CHECK(cudaStreamWaitEvent(d.prep, ev, 0));
+    if (c->sq_nibble) enqueue_nibble_unpack(c, dst, S.codes + lo * c->width, nr, d.prep);
     if (c->sq_tc) {
         if (c->sq_needs_pp) CUDA_CHECK(cudaMemsetAsync(d.pp_cnt, 0, (size_t)c->width * 4, d.prep));
         enqueue_tc_pack(c, S, S.codes, nr, c->sq_input_kind, !S.acgt_from_host && c->fam == FAM_TN93, d.prep, lo,
@@ -1549,7 +1664,7 @@ void stream_sink_front(dg_ctx* c) {
         c->have_invalid = true;
         c->inv_record = (key >> 32) + f.desc.row_begin;
         c->inv_site = key & 0xffffffffull;
-        c->inv_byte = s.h_in[(key >> 32) * c->width + c->inv_site];
+        c->inv_byte = s.batch.input_kind == DG_INPUT_NIBBLE ? 0 : s.h_in[(key >> 32) * c->width + c->inv_site];
         fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in streamed record %llu at site %llu",
              c->inv_byte, (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
     }
@@ -1588,17 +1703,20 @@ void stream_begin(dg_ctx* c, dg_sink_fn sink, void* user, uint64_t max_batch) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, (size_t)mb * n_res * c->elem_bytes());
         if (s_tc)
-            for (auto& sl : d.slot) ensure_scratch(sl, scratch_upper_bound(c, c->want_fp4(), DG_MODE_RECT, 0, mb, n_res));
+            for (int q = 0; q < 2; q++) ensure_scratch(d.slot[q], scratch_upper_bound(c, c->want_fp4(), DG_MODE_RECT, 0, mb, n_res));
         if (d.in_cap < mb || (s_tc && (!d.slot[0].batch.tc_ops || d.slot[0].batch.tc_fp4 != c->want_fp4())) ||
             (!s_tc && !d.slot[0].batch.core)) {
-            for (auto& s : d.slot) {
+            for (int q = 0; q < 2; q++) {
+                Slot& s = d.slot[q];
                 if (s.h_in) cudaFreeHost(s.h_in);
                 if (s.d_in) cudaFree(s.d_in);
+                if (s.d_nib) cudaFree(s.d_nib);
                 if (s.h_acgt) cudaFreeHost(s.h_acgt);
                 free_set(s.batch);
-                s.h_in = s.d_in = nullptr; s.h_acgt = nullptr;
+                s.h_in = s.d_in = s.d_nib = nullptr; s.h_acgt = nullptr;
                 CUDA_CHECK(cudaHostAlloc(&s.h_in, (size_t)mb * c->width, cudaHostAllocDefault));
                 CUDA_CHECK(cudaMalloc(&s.d_in, (size_t)mb * c->width));
+                CUDA_CHECK(cudaMalloc(&s.d_nib, (size_t)mb * input_stride(c, DG_INPUT_NIBBLE)));
                 CUDA_CHECK(cudaHostAlloc(&s.h_acgt, (size_t)mb * 4 * sizeof(uint32_t), cudaHostAllocDefault));
                 alloc_set(c, s.batch, mb, false, !s_tc);
                 if (s_tc) alloc_tc_operands(c, s.batch);
@@ -1627,21 +1745,26 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     Slot& s = d.slot[si];
     CUDA_CHECK(cudaSetDevice(d.id));
     const double th = wall_ms();
-    if (codes != s.h_in) std::memcpy(s.h_in, codes, (size_t)nb * c->width);   // dg_stream_buffer: filled in place
+    const bool nibble = input_kind == DG_INPUT_NIBBLE;
+    const uint64_t stride = input_stride(c, input_kind);
+    input_kind = device_kind(input_kind);
+    if (codes != s.h_in) std::memcpy(s.h_in, codes, (size_t)nb * stride);   // dg_stream_buffer: filled in place
     const bool host_counts = acgt != nullptr && c->fam == FAM_TN93;
     if (host_counts)
         for (uint64_t i = 0; i < nb * 4; i++) s.h_acgt[i] = (uint32_t)acgt[i];
-    CUDA_CHECK(cudaMemcpyAsync(s.d_in, s.h_in, (size_t)nb * c->width, cudaMemcpyHostToDevice, d.copy_in));
+    CUDA_CHECK(cudaMemcpyAsync(nibble ? s.d_nib : s.d_in, s.h_in, (size_t)nb * stride, cudaMemcpyHostToDevice, d.copy_in));
     if (host_counts)
         CUDA_CHECK(cudaMemcpyAsync(s.batch.acgt, s.h_acgt, (size_t)nb * 4 * sizeof(uint32_t),
                                    cudaMemcpyHostToDevice, d.copy_in));
     CUDA_CHECK(cudaEventRecord(s.in_ready, d.copy_in));
     c->tm.h2d_ms += wall_ms() - th;
-    c->tm.h2d_bytes += nb * c->width;
+    c->tm.h2d_bytes += nb * stride;
     cudaStream_t cst = d.cs(si);
     CUDA_CHECK(cudaStreamWaitEvent(cst, s.in_ready, 0));
     s.batch.n = nb;
     CUDA_CHECK(cudaEventRecord(s.p_start, cst));
+    if (nibble) enqueue_nibble_unpack(c, s.d_nib, s.d_in, nb, cst);
+    s.batch.input_kind = nibble ? DG_INPUT_NIBBLE : input_kind;
     // fastaio.rs:250-254: the streamed tn93 records count raw upper-case chars only (:139-142)
     if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, !host_counts && c->fam == FAM_TN93, cst, 0,
                                  d.d_invalid + si, true);
@@ -1712,9 +1835,10 @@ void destroy_device(Device& d) {
         if (s.h_out) cudaFreeHost(s.h_out);
         if (s.h_in) cudaFreeHost(s.h_in);
         if (s.d_in) cudaFree(s.d_in);
+        if (s.d_nib) cudaFree(s.d_nib);
         if (s.h_acgt) cudaFreeHost(s.h_acgt);
         free_set(s.batch);
-        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop})
+        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop, s.gemm_done})
             if (e) cudaEventDestroy(e);
     }
     for (auto& s : d.pslot) {
@@ -1723,7 +1847,7 @@ void destroy_device(Device& d) {
         if (s.d_tiles) cudaFree(s.d_tiles);
         if (s.h_tiles) cudaFreeHost(s.h_tiles);
         if (s.h_out) cudaFreeHost(s.h_out);
-        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied})
+        for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.gemm_done})
             if (e) cudaEventDestroy(e);
     }
     if (d.sq_off) cudaFree(d.sq_off);
@@ -1758,6 +1882,7 @@ void destroy_device(Device& d) {
     if (d.compute2) cudaStreamDestroy(d.compute2);
     if (d.copy) cudaStreamDestroy(d.copy);
     if (d.copy_in) cudaStreamDestroy(d.copy_in);
+    if (d.post) cudaStreamDestroy(d.post);
 }
 
 void host_lut(uint8_t lut[256], uint32_t valid[8]) {
@@ -1841,6 +1966,7 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.compute2, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
             CUDA_CHECK(cudaStreamCreateWithFlags(&d.copy_in, cudaStreamNonBlocking));
+            CUDA_CHECK(cudaStreamCreateWithFlags(&d.post, cudaStreamNonBlocking));
             {
                 int lo_pri = 0, hi_pri = 0;
                 CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
@@ -1849,10 +1975,10 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
                 CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ready, cudaEventDisableTiming));
             }
             for (auto& s : d.slot)
-                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.in_ready, &s.p_start, &s.p_stop})
+                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.in_ready, &s.p_start, &s.p_stop, &s.gemm_done})
                     CUDA_CHECK(cudaEventCreate(e));
             for (auto& s : d.pslot)
-                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied})
+                for (cudaEvent_t* e : {&s.k_start, &s.k_stop, &s.copied, &s.gemm_done})
                     CUDA_CHECK(cudaEventCreate(e));
             CUDA_CHECK(cudaEventCreate(&d.run_start));
             CUDA_CHECK(cudaEventCreate(&d.run_stop));
@@ -1940,9 +2066,12 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
         if (which < 0 || which > 1) fail(DG_ERR_INVALID_ARG, "which must be 0 or 1");
         if (!codes || n == 0) fail(DG_ERR_INVALID_ARG, "empty alignment");
         if (n >= (1ull << 31)) fail(DG_ERR_INVALID_ARG, "too many records");
-        if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+        if (!valid_input_kind(input_kind)) fail(DG_ERR_INVALID_ARG, "bad input_kind");
         if (ctx->streaming || ctx->sq_open) fail(DG_ERR_STATE, "a session is open");
         ctx->have_invalid = false;
+        const bool nibble = input_kind == DG_INPUT_NIBBLE;
+        const uint64_t stride = input_stride(ctx, input_kind);   // bytes per record of the caller's buffer
+        const int dkind = device_kind(input_kind);
         std::vector<uint32_t> c32;
         if (acgt_counts) {
             c32.resize(n * 4);
@@ -1956,7 +2085,8 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
             CUDA_CHECK(cudaSetDevice(d.id));
             PlaneSet& s = d.set[which];
             reserve_resident(ctx, s, n, want_tc);
-            s.input_kind = input_kind;
+            if (nibble) ensure_nib(ctx, s, n);
+            s.input_kind = dkind;
             s.acgt_from_host = acgt_counts != nullptr;
             // Upload in chunks on the copy stream; each chunk is packed on the compute stream as soon as
             // it has landed, so packing hides behind the PCIe transfer of the next chunk.
@@ -1975,17 +2105,17 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
                 CUDA_CHECK(cudaEventRecord(d.slot[0].p_start, d.compute));
                 for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
                     const uint64_t nr = std::min(chunk, n - r0);
+                    uint8_t* land = nibble ? s.nib + r0 * stride : s.codes + r0 * stride;   // where the chunk lands
                     if (src_dev < 0)
-                        CUDA_CHECK(cudaMemcpyAsync(s.codes + r0 * ctx->width, codes + r0 * ctx->width, (size_t)nr * ctx->width,
-                                                   cudaMemcpyHostToDevice, d.copy_in));
+                        CUDA_CHECK(cudaMemcpyAsync(land, codes + r0 * stride, (size_t)nr * stride, cudaMemcpyHostToDevice, d.copy_in));
                     else
-                        CUDA_CHECK(cudaMemcpyPeerAsync(s.codes + r0 * ctx->width, d.id, codes + r0 * ctx->width, src_dev,
-                                                       (size_t)nr * ctx->width, d.copy_in));
+                        CUDA_CHECK(cudaMemcpyPeerAsync(land, d.id, codes + r0 * stride, src_dev, (size_t)nr * stride, d.copy_in));
                     cudaEvent_t ev = d.chunk_ev[n_ev++ & 31];
                     CUDA_CHECK(cudaEventRecord(ev, d.copy_in));
                     CUDA_CHECK(cudaStreamWaitEvent(d.compute, ev, 0));
+                    if (nibble) enqueue_nibble_unpack(ctx, land, s.codes + r0 * ctx->width, nr, d.compute);
                     if (want_tc) {
-                        enqueue_tc_pack(ctx, s, s.codes, nr, input_kind, !acgt_counts && ctx->fam == FAM_TN93, d.compute, r0,
+                        enqueue_tc_pack(ctx, s, s.codes, nr, dkind, !acgt_counts && ctx->fam == FAM_TN93, d.compute, r0,
                                         d.d_invalid + 2, false, needs_pp ? &d : nullptr);   // also collects the partial codes
                     }
                 }
@@ -1998,7 +2128,7 @@ static int load_resident_impl(dg_ctx* ctx, int which, const uint8_t* codes, int 
                 CUDA_CHECK(cudaStreamSynchronize(d.copy_in));
                 CUDA_CHECK(cudaStreamSynchronize(d.compute));
                 ctx->tm.h2d_ms += wall_ms() - th;
-                if (src_dev < 0) ctx->tm.h2d_bytes += n * ctx->width;
+                if (src_dev < 0) ctx->tm.h2d_bytes += n * stride;
                 float ms = 0;
                 CUDA_CHECK(cudaEventElapsedTime(&ms, d.slot[0].p_start, d.slot[0].p_stop));
                 ctx->tm.pack_ms += ms;  // device span of the pipelined upload + packing
@@ -2145,7 +2275,7 @@ static int run_session_host(dg_ctx* ctx, int mode, const uint8_t* codes, uint64_
         uint64_t lo = 0, hi = 0;
         if ((rc = dg_square_next(ctx, &lo, &hi)) != DG_OK) return rc;
         if (hi == lo) break;
-        if ((rc = dg_square_push(ctx, codes + lo * ctx->width, -1, lo, hi, nullptr)) != DG_OK) return rc;
+        if ((rc = dg_square_push(ctx, codes + lo * input_stride(ctx, input_kind), -1, lo, hi, nullptr)) != DG_OK) return rc;
     }
     return dg_square_end(ctx);
 }
@@ -2169,10 +2299,10 @@ int dg_stream_push(dg_ctx* ctx, const uint8_t* codes, uint64_t n_batch, int inpu
     int rc = guarded(ctx, [&] {
         if (!ctx->streaming) fail(DG_ERR_STATE, "no stream session is open");
         if (!codes && n_batch) fail(DG_ERR_INVALID_ARG, "codes is NULL");
-        if (input_kind != DG_INPUT_PARADIS && input_kind != DG_INPUT_ASCII) fail(DG_ERR_INVALID_ARG, "bad input_kind");
+        if (!valid_input_kind(input_kind)) fail(DG_ERR_INVALID_ARG, "bad input_kind");
         for (uint64_t off = 0; off < n_batch; off += ctx->s_max_batch) {
             const uint64_t nb = std::min(ctx->s_max_batch, n_batch - off);
-            stream_push_one(ctx, codes + off * ctx->width, nb, input_kind,
+            stream_push_one(ctx, codes + off * input_stride(ctx, input_kind), nb, input_kind,
                             acgt_counts ? acgt_counts + off * 4 : nullptr);
         }
     });

@@ -8,8 +8,10 @@
 //
 //   -t  = threads formatting TSV text (the reference's worker count; results never depended on it)
 //   -b  = accepted and validated, otherwise unused (the reference's pair batch size)
-//   DISTANCE_GPUS=<k> or DISTANCE_GPUS=0,2,3 chooses the devices (default: device 0); there is no flag
-//   for it so the CLI surface stays the reference's.
+//   Devices: every visible GPU by default, like the reference takes every core (lib.rs:252-264, num_cpus::get());
+//   small inputs take fewer (one GPU per 2e13 pair-sites, ~0.2 s of tensor work: a CUDA context costs more than that).
+//   DISTANCE_GPUS=<k> or DISTANCE_GPUS=0,2,3 restricts / chooses them; there is no flag for it so the CLI surface stays
+//   the reference's.
 #include <cerrno>
 #include <chrono>
 #include <cmath>
@@ -171,10 +173,17 @@ int measure_id(const std::string& m) {
     return -1;
 }
 
-std::vector<int> gpu_list() {
+// pair_sites: the work of the run (0 = unknown, e.g. a stream of unknown length: every visible device)
+std::vector<int> gpu_list(double pair_sites) {
     std::vector<int> ids;
     const char* e = std::getenv("DISTANCE_GPUS");
-    if (!e || !*e) return {0};
+    if (!e || !*e) {
+        const int visible = std::max(1, dg_device_count());
+        int k = visible;
+        if (pair_sites > 0) k = (int)std::min<double>(visible, std::max(1.0, std::ceil(pair_sites / 2e13)));
+        for (int i = 0; i < k; i++) ids.push_back(i);
+        return ids;
+    }
     std::string s = e;
     if (s.find(',') == std::string::npos) {
         const int k = std::atoi(s.c_str());
@@ -252,7 +261,13 @@ int run(const Args& a) {
     const uint64_t width = loaded[0].width;
     TsvWriter writer(out_fd, (int)std::min<uint64_t>(threads, 256));
     SinkState st{&writer, {}};
-    const std::vector<int> gpus = gpu_list();
+    double pair_sites = 0;   // stream mode: unknown length -> every device
+    if (stream_fd < 0) {
+        const double n0 = (double)loaded[0].n(), n1 = loaded.size() > 1 ? (double)loaded[1].n() : 0;
+        pair_sites = (loaded.size() > 1 ? n0 * n1 : n0 * (n0 - 1) / 2) * (double)width;
+    }
+    const std::vector<int> gpus = gpu_list(pair_sites);
+    if (trace) fprintf(stderr, "[distance] %zu GPU(s)\n", gpus.size());
     dg_ctx* ctx = nullptr;
     int rc = dg_create(gpus.data(), (int)gpus.size(), measure_id(a.measure), width, &ctx);
     if (rc != DG_OK) throw message_error(std::string("GPU engine: ") + dg_last_error(nullptr));

@@ -66,7 +66,9 @@ constexpr uint32_t SPIN_LIMIT = 1u << 22;  // mbarrier polls before the kernel t
 //   ACC_MOD16                 : the raw sum modulo 2^16 (accumulator 0 = 3 * DIFF with the repair pending, width <= 32767):
 //                               pp_correct adds its deltas modulo 2^16 and the combine pass recovers DIFF, because of the
 //                               two candidates x and x + 65536 (3 * DIFF < 2^17) exactly one is a multiple of 3
-enum AccOp { ACC_RAW_I32 = 0, ACC_RAW_I16 = 1, ACC_DIV3_U32 = 2, ACC_DIV3_U16 = 3, ACC_MOD16 = 4 };
+//   ACC_ADD_I32               : split-K launches (TcParams::ksplit > 1): every work item ADDS its partial sum into a zeroed
+//                               int32 scratch array (small problems: the K range of a tile is dealt to several CTA pairs)
+enum AccOp { ACC_RAW_I32 = 0, ACC_RAW_I16 = 1, ACC_DIV3_U32 = 2, ACC_DIV3_U16 = 3, ACC_MOD16 = 4, ACC_ADD_I32 = 5 };
 __host__ __device__ constexpr bool acc_op_16(int op) { return op == ACC_RAW_I16 || op == ACC_DIV3_U16 || op == ACC_MOD16; }
 __host__ __device__ constexpr bool acc_op_div3(int op) { return op == ACC_DIV3_U32 || op == ACC_DIV3_U16; }
 
@@ -344,7 +346,8 @@ __device__ __forceinline__ void load_codes16(const PackI8Params& p, const uint8_
         const uintptr_t a = reinterpret_cast<uintptr_t>(row + s0);
         const uint32_t* ap = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(a & 3) * 8;
-        const uint32_t x0 = __ldg(ap), x1 = __ldg(ap + 1), x2 = __ldg(ap + 2), x3 = __ldg(ap + 3), x4 = __ldg(ap + 4);
+        // streaming (evict-first) loads: the code bytes are read once and must not push the GEMM's operand tiles out of L2
+        const uint32_t x0 = __ldcs(ap), x1 = __ldcs(ap + 1), x2 = __ldcs(ap + 2), x3 = __ldcs(ap + 3), x4 = __ldcs(ap + 4);
         raw[0] = __funnelshift_r(x0, x1, sh); raw[1] = __funnelshift_r(x1, x2, sh);
         raw[2] = __funnelshift_r(x2, x3, sh); raw[3] = __funnelshift_r(x3, x4, sh);
     } else {                    // last groups of the row: byte loads, bounded by width
@@ -452,8 +455,8 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
 #pragma unroll
                 for (int pl = 0; pl < PL::N; pl++) {
                     const uint32_t id = PL::id(pl);
-                    *reinterpret_cast<uint4*>(base + pl * p.wp8) =
-                        make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id));
+                    __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
+                           make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id)));
                 }
             } else {
                 CodeBits b[4];
@@ -469,8 +472,8 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
 #pragma unroll
                 for (int pl = 0; pl < PL::N; pl++) {
                     const uint32_t id = PL::id(pl);
-                    *reinterpret_cast<uint4*>(base + pl * p.wp8) =
-                        make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id));
+                    __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
+                           make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id)));
                 }
             }
         }
@@ -488,6 +491,32 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
                 p.acgt[seq * 4 + threadIdx.x] = seq < p.n ? v : 0u;
             }
             __syncthreads();
+        }
+    }
+}
+
+// ---- DG_INPUT_NIBBLE: two sites per byte -> Paradis bytes -------------------------------------------------------------
+// byte = nibble << 4 | (8 if exactly one possibility bit: the base is known); nibble 0 -> 0 (invalid, reported by the
+// pack kernels).  One thread per 4 input bytes (8 sites); HBM-bound and tiny next to the PCIe time it saves.
+__global__ void nibble_unpack_kernel(const uint8_t* __restrict__ nib, uint8_t* __restrict__ codes, uint64_t n, uint64_t width,
+                                     uint64_t wb) {
+    const uint64_t per_row = (wb + 3) / 4;
+    const uint64_t total = n * per_row;
+    for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = u / per_row, k0 = (u - r * per_row) * 4;
+        const uint8_t* src = nib + r * wb + k0;
+        uint8_t* dst = codes + r * width + 2 * k0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (k0 + k >= wb) break;
+            const uint32_t b = src[k];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const uint64_t site = 2 * (k0 + k) + h;
+                if (site >= width) break;
+                const uint32_t m = (b >> (4 * h)) & 15u;
+                dst[2 * k + h] = (uint8_t)((m << 4) | (__popc(m) == 1 ? 8u : 0u));
+            }
         }
     }
 }
@@ -612,7 +641,7 @@ __device__ __forceinline__ int pp_corr(uint32_t ma, uint32_t mb) {
 // Add a repair delta to accumulator 0 of the pair at scratch index idx: int32 sums take an atomicAdd; 16-bit sums
 // (ACC_MOD16: the value modulo 2^16) a wrap-around add through a CAS on the containing word.
 __device__ __forceinline__ void pp_add(void* out, int op, uint64_t idx, int c) {
-    if (op == ACC_RAW_I32) {
+    if (op == ACC_RAW_I32 || op == ACC_ADD_I32) {
         atomicAdd(reinterpret_cast<int*>(out) + idx, c);
     } else {
         uint32_t* w = reinterpret_cast<uint32_t*>(out) + (idx >> 1);
@@ -776,6 +805,7 @@ struct TcParams {
     // 32-column chunk of every tile row starts 32-byte aligned and an epilogue lane stores its row's chunk straight from
     // registers with 128-bit stores).  s_pitch == 0: `out` holds the final n / n_high counts in the reference's order.
     uint32_t s_pitch, s_colbase;
+    uint32_t ksplit;       // >= 1: work items = accumulators x tiles x ksplit, item kc sums K blocks [kc, kc + 1) * KT / ksplit
     uint32_t stages;       // pipeline depth in use (<= STAGES; tuning knob)
     unsigned long long* probe;  // DG_CLOCK_PROBE (debug): [4] += SM clocks, [5] += ns of this launch (CTA 0); or NULL
 };
@@ -853,24 +883,31 @@ __device__ __forceinline__ void epi_drain_scratch(const TcParams& p, uint8_t* ou
                 v[j] = (uint32_t)x;
             }
             const bool whole = TNX % 32 == 0 || c + 1 < NCH;   // the last chunk of a 240-column tile holds 16 columns
-            if (rv) {
+            if (OP == ACC_ADD_I32) {
+                if (rv) {
+                    int* d = reinterpret_cast<int*>(rowp + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if (whole || j < TNX % 32) atomicAdd(d + j, (int)v[j]);
+                }
+            } else if (rv) {
                 uint4* d = reinterpret_cast<uint4*>(rowp + c * 32);
                 if (sizeof(T) == 2) {
                     uint32_t w[16];
 #pragma unroll
                     for (int k = 0; k < 16; k++) w[k] = (v[2 * k] & 0xFFFFu) | (v[2 * k + 1] << 16);
-                    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-                    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    __stcs(d + 0, make_uint4(w[0], w[1], w[2], w[3]));   // streaming stores: scratch is re-read once, much later
+                    __stcs(d + 1, make_uint4(w[4], w[5], w[6], w[7]));
                     if (whole) {
-                        d[2] = make_uint4(w[8], w[9], w[10], w[11]);
-                        d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+                        __stcs(d + 2, make_uint4(w[8], w[9], w[10], w[11]));
+                        __stcs(d + 3, make_uint4(w[12], w[13], w[14], w[15]));
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) d[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                    for (int k = 0; k < 4; k++) __stcs(d + k, make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
                     if (whole) {
 #pragma unroll
-                        for (int k = 4; k < 8; k++) d[k] = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+                        for (int k = 4; k < 8; k++) __stcs(d + k, make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]));
                     }
                 }
             }
@@ -965,7 +1002,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t ntiles = p.tile_list ? p.n_live : p.gx * p.gy;
-    const uint32_t nwork = ntiles * p.nacc;   // accumulator-major: concurrent tiles read the same planes (L2 reuse)
+    const uint32_t nwork = ntiles * p.nacc * p.ksplit;   // accumulator-major: concurrent tiles read the same planes (L2 reuse)
+    // work item w -> accumulator a, tile t, K blocks [k0, k1) of the accumulator's npairs[a] * nsb
+    auto decode = [&](uint32_t w, uint32_t& a, uint32_t& t, uint32_t& k0, uint32_t& k1) {
+        const uint32_t per = ntiles * p.ksplit;
+        a = w / per;
+        const uint32_t r = w - a * per;
+        t = r / p.ksplit;
+        const uint32_t kc = r - t * p.ksplit, KT = p.npairs[a] * p.nsb;
+        k0 = (uint32_t)((uint64_t)kc * KT / p.ksplit);
+        k1 = (uint32_t)((uint64_t)(kc + 1) * KT / p.ksplit);
+    };
     const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
     const uint32_t cid = blockIdx.x / CL, ncl = gridDim.x / CL;   // tiles are dealt to clusters
     constexpr uint16_t MC_MASK = (1u << CL) - 1;
@@ -1015,11 +1062,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
             for (uint32_t w = cid; w < nwork; w += ncl) {
-                const uint32_t a = w / ntiles, t = w - a * ntiles;
+                uint32_t a, t, k0, k1;
+                decode(w, a, t, k0, k1);
                 uint32_t rowA0, rowB0;
                 if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
-                const uint32_t KT = p.npairs[a] * p.nsb;
-                for (uint32_t kt = 0; kt < KT; kt++) {
+                for (uint32_t kt = k0; kt < k1; kt++) {
                     mbar_wait(empty + stage, phase ^ 1);
                     const uint32_t pr = kt / p.nsb, sb = kt - pr * p.nsb;
                     uint8_t* sa = smem + stage * STAGE_BYTES;
@@ -1055,16 +1102,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0 && (!PAIR || rank == 0)) {
             uint32_t stage = 0, phase = 0, it = 0;
             for (uint32_t w = cid; w < nwork; w += ncl) {
-                const uint32_t a = w / ntiles, t = w - a * ntiles;
+                uint32_t a, t, k0, k1;
+                decode(w, a, t, k0, k1);
                 uint32_t rowA0, rowB0;
                 if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
-                const uint32_t KT = p.npairs[a] * p.nsb;
                 // MT = 1: two accumulators of 256 columns alternate; MT = 2: both are used by every tile
                 const uint32_t ab = MT == 1 ? (it & 1) : 0, aphase = MT == 1 ? ((it >> 1) & 1) : (it & 1);
                 mbar_wait(tempty + ab, aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + ab * TN;
-                for (uint32_t kt = 0; kt < KT; kt++) {
+                for (uint32_t kt = k0; kt < k1; kt++) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -1073,10 +1120,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (uint32_t k4 = 0; k4 < KB / 32; k4++)
 #pragma unroll
                         for (int m = 0; m < MT; m++) {
-                            if (FP4) tc_mma_f4_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_F4_PAIR, (kt | k4) != 0,
+                            if (FP4) tc_mma_f4_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_F4_PAIR, (kt != k0) || (k4 != 0),
                                                     tmem_base + SF_COL, tmem_base + SF_COL + 8);
-                            else if (PAIR) tc_mma_i8_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8_PAIR, (kt | k4) != 0);
-                            else tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt | k4) != 0);
+                            else if (PAIR) tc_mma_i8_pair(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8_PAIR, (kt != k0) || (k4 != 0));
+                            else tc_mma_i8(d_tmem + m * TN, make_smem_desc(sa + m * A_BYTES) + 2 * k4, db + 2 * k4, IDESC_I8, (kt != k0) || (k4 != 0));
                         }
                     if (PAIR) tc_commit_pair(empty + stage, MC_MASK);   // frees the stage in both CTAs
                     else if (CL == 1) tc_commit(empty + stage);         // frees the smem stage when these MMAs retire
@@ -1094,7 +1141,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t* ebuf = reinterpret_cast<uint32_t*>(smem + 192 * 1024 + 256) + quad * (32 * EPI_PITCH);
         uint32_t it = 0;
         for (uint32_t w = cid; w < nwork; w += ncl) {
-            const uint32_t a = w / ntiles, t = w - a * ntiles;
+            uint32_t a, t, k0, k1;
+            decode(w, a, t, k0, k1);
             uint32_t rowA0, rowB0;
             if (!tile_live<CL, MT>(p, t, rank, rowA0, rowB0)) continue;
             uint8_t* const outb = reinterpret_cast<uint8_t*>(p.out) + p.acc_off[a];
@@ -1108,6 +1156,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 case ACC_RAW_I32: epi_drain_scratch<ACC_RAW_I32, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 case ACC_RAW_I16: epi_drain_scratch<ACC_RAW_I16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 case ACC_MOD16: epi_drain_scratch<ACC_MOD16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
+                case ACC_ADD_I32: epi_drain_scratch<ACC_ADD_I32, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 case ACC_DIV3_U32: epi_drain_scratch<ACC_DIV3_U32, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 default: epi_drain_scratch<ACC_DIV3_U16, FP4, TNX, MT>(p, outb, tacc, lane, rowQ0, rowB0); break;
                 }
@@ -1162,10 +1211,11 @@ struct CombineParams {
 __device__ __forceinline__ int load_acc(const CombineParams& p, int a, uint64_t idx) {
     const uint8_t* b = p.acc + p.acc_off[a];
     switch (p.acc_op[a]) {
-    case ACC_RAW_I32: return reinterpret_cast<const int*>(b)[idx];
-    case ACC_RAW_I16: return (int)reinterpret_cast<const int16_t*>(b)[idx];
-    case ACC_DIV3_U32: return (int)reinterpret_cast<const uint32_t*>(b)[idx];
-    default: return (int)reinterpret_cast<const uint16_t*>(b)[idx];   // ACC_DIV3_U16, ACC_MOD16
+    // streaming loads: every scratch value is read exactly once
+    case ACC_RAW_I32: case ACC_ADD_I32: return __ldcs(reinterpret_cast<const int*>(b) + idx);
+    case ACC_RAW_I16: return (int)__ldcs(reinterpret_cast<const short*>(b) + idx);
+    case ACC_DIV3_U32: return (int)__ldcs(reinterpret_cast<const unsigned int*>(b) + idx);
+    default: return (int)__ldcs(reinterpret_cast<const unsigned short*>(b) + idx);   // ACC_DIV3_U16, ACC_MOD16
     }
 }
 // accumulator 0 of n / n_high / raw / jc69 -> DIFF
@@ -1175,48 +1225,52 @@ __device__ __forceinline__ uint32_t diff_of(int op, int a0) {
     return (uint32_t)a0 / 3u;
 }
 
-// Grid: a FIXED number of CTAs (2 per SM), each walking virtual blocks (256-column strip x row phase).  A grid sized by the
-// work (thousands of small CTAs) would take every register of every SM the moment the previous GEMM drains, and the next
-// panel's persistent GEMM CTA (1 per SM, ~24 K registers + 211 KB of shared memory) would find no room until the whole
-// combine pass is over: the f64 pass and the tensor pass would run back to back instead of side by side (measured: no
-// overlap at all).  Two resident CTAs per SM leave the GEMM its place.
-__global__ void __launch_bounds__(256, 2) tc_combine_kernel(CombineParams p, uint32_t gx, uint32_t gy) {
-    for (uint32_t vb = blockIdx.x; vb < gx * gy; vb += gridDim.x) {
-    const uint32_t bx = vb % gx, by = vb / gx;
-    const uint32_t col = p.col0 + bx * blockDim.x + threadIdx.x;
-    if (col >= p.n_b) continue;
-    for (uint32_t row = p.row0 + by; row < p.row_end; row += gy) {
-        if (p.square && col <= row) continue;
-        const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
-                                      : (uint64_t)(row - p.row0) * p.n_b + col;
-        const uint64_t sidx = (uint64_t)(row - p.row0) * p.s_pitch + (col - p.s_colbase);
-        const int a0 = load_acc(p, 0, sidx);
-        const int a1 = p.fam != FAM_SNP ? load_acc(p, 1, sidx) : 0;
-        uint4 cnt = make_uint4(0, 0, 0, 0);
-        if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
-            cnt = make_uint4(diff_of(p.acc_op[0], a0), (uint32_t)a1, 0, 0);  // {n, same}
-        } else if (p.fam == FAM_K80) {
-            const int tv = load_acc(p, 2, sidx);
-            const int same = (a0 + a1) >> 1, ts = (a0 - a1) >> 1;
-            cnt = make_uint4((uint32_t)same, (uint32_t)(ts + tv), (uint32_t)tv, 0);  // {same, ts + tv, tv}
-        } else {
-            const int yy = load_acc(p, 2, sidx), ww = load_acc(p, 3, sidx), zz = load_acc(p, 4, sidx);
-            const int sp = (a1 + ww) >> 1, p1 = (a1 - ww) >> 1, sy = (yy + zz) >> 1, p2 = (yy - zz) >> 1;
-            cnt = make_uint4((uint32_t)a0, (uint32_t)(a0 - sp - sy), (uint32_t)p1, (uint32_t)p2);  // {L, d, P1, P2}
-        }
-        if (p.result == RES_COUNTS) { reinterpret_cast<uint4*>(p.out)[idx] = cnt; continue; }
-        if (p.result == RES_U32) { reinterpret_cast<uint32_t*>(p.out)[idx] = cnt.x; continue; }
-        if (p.result == RES_U16) { reinterpret_cast<uint16_t*>(p.out)[idx] = (uint16_t)cnt.x; continue; }
-        double r;
-        if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
-        else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z, p.literal != 0);
-        else {
-            const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
-            const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
-            r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc, p.literal != 0);
-        }
-        reinterpret_cast<double*>(p.out)[idx] = r;
+// Grid: every CTA walks virtual blocks (256-column strip x row phase).  By default there is one CTA per virtual block;
+// DG_COMBINE_PER_SM bounds the grid to that many CTAs per SM (an experiment: a bounded grid leaves room for the next
+// panel's persistent GEMM CTA, but at 2 - 3 CTAs per SM the f64 chains run latency-bound and the pass gets slower than
+// what the overlap wins back: measured 6.4 ms unbounded vs 6.7 - 7.9 ms bounded on config 3).
+// One pair: the accumulators' sums at scratch index sidx -> the reference's counts -> the result at out index idx.
+__device__ __forceinline__ void combine_pair(const CombineParams& p, uint32_t row, uint32_t col) {
+    const uint64_t idx = p.square ? (uint64_t)row * (2 * p.n_total - row - 1) / 2 - p.out_base + (col - row - 1)
+                                  : (uint64_t)(row - p.row0) * p.n_b + col;
+    const uint64_t sidx = (uint64_t)(row - p.row0) * p.s_pitch + (col - p.s_colbase);
+    const int a0 = load_acc(p, 0, sidx);
+    const int a1 = p.fam != FAM_SNP ? load_acc(p, 1, sidx) : 0;
+    uint4 cnt = make_uint4(0, 0, 0, 0);
+    if (p.fam == FAM_SNP || p.fam == FAM_RAW) {
+        cnt = make_uint4(diff_of(p.acc_op[0], a0), (uint32_t)a1, 0, 0);  // {n, same}
+    } else if (p.fam == FAM_K80) {
+        const int tv = load_acc(p, 2, sidx);
+        const int same = (a0 + a1) >> 1, ts = (a0 - a1) >> 1;
+        cnt = make_uint4((uint32_t)same, (uint32_t)(ts + tv), (uint32_t)tv, 0);  // {same, ts + tv, tv}
+    } else {
+        const int yy = load_acc(p, 2, sidx), ww = load_acc(p, 3, sidx), zz = load_acc(p, 4, sidx);
+        const int sp = (a1 + ww) >> 1, p1 = (a1 - ww) >> 1, sy = (yy + zz) >> 1, p2 = (yy - zz) >> 1;
+        cnt = make_uint4((uint32_t)a0, (uint32_t)(a0 - sp - sy), (uint32_t)p1, (uint32_t)p2);  // {L, d, P1, P2}
     }
+    if (p.result == RES_COUNTS) { reinterpret_cast<uint4*>(p.out)[idx] = cnt; return; }
+    if (p.result == RES_U32) { __stcs(reinterpret_cast<uint32_t*>(p.out) + idx, cnt.x); return; }
+    if (p.result == RES_U16) { __stcs(reinterpret_cast<unsigned short*>(p.out) + idx, (unsigned short)cnt.x); return; }
+    double r;
+    if (p.fam == FAM_RAW) r = p.measure == 2 ? epi_raw(cnt.x, cnt.y) : epi_jc69(cnt.x, cnt.y);
+    else if (p.fam == FAM_K80) r = epi_k80(cnt.x, cnt.y, cnt.z, p.literal != 0);
+    else {
+        const uint4 rc = *reinterpret_cast<const uint4*>(p.a_acgt + 4 * (uint64_t)row);
+        const uint4 cc = *reinterpret_cast<const uint4*>(p.b_acgt + 4 * (uint64_t)col);
+        r = epi_tn93(cnt.x, cnt.y, cnt.z, cnt.w, p.swap_roles ? cc : rc, p.swap_roles ? rc : cc, p.literal != 0);
+    }
+    __stcs(reinterpret_cast<double*>(p.out) + idx, r);
+}
+
+__global__ void __launch_bounds__(256, 4) tc_combine_kernel(CombineParams p, uint32_t gx, uint32_t gy) {
+    for (uint32_t vb = blockIdx.x; vb < gx * gy; vb += gridDim.x) {
+        const uint32_t bx = vb % gx, by = vb / gx;
+        const uint32_t col = p.col0 + bx * blockDim.x + threadIdx.x;
+        if (col >= p.n_b) continue;
+        for (uint32_t row = p.row0 + by; row < p.row_end; row += gy) {
+            if (p.square && col <= row) continue;
+            combine_pair(p, row, col);
+        }
     }
 }
 

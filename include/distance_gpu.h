@@ -74,7 +74,12 @@ typedef enum {
 /* What the `codes` buffers hold. */
 typedef enum {
     DG_INPUT_PARADIS = 0, /* EncodedFastaRecord.seq bytes (src/fastaio.rs:16) */
-    DG_INPUT_ASCII = 1    /* raw FASTA sequence bytes; the LUT of src/encoding.rs:4-41 runs on device */
+    DG_INPUT_ASCII = 1,   /* raw FASTA sequence bytes; the LUT of src/encoding.rs:4-41 runs on device */
+    DG_INPUT_NIBBLE = 2   /* ABI 2: two sites per byte (site 2k in the low nibble of byte k, site 2k+1 in the high one), a row is
+                             (width + 1) / 2 bytes.  A nibble = the possibility bits of the Paradis code (its high nibble:
+                             A = 8, G = 4, C = 2, T = 1, R = 12 ... N = 15); "known" is implied by a single bit, and N, '-' and
+                             '?' (which no measure tells apart: src/measures.rs:17, 60-62, 158) all travel as 15.  Nibble 0 is
+                             invalid.  Half the bytes over PCIe for a parser that packs while it validates. */
 } dg_input_kind;
 
 typedef enum {

@@ -97,3 +97,14 @@ def test_two_rank_sharding_over_gloo(api):
     assert out[0][3] == 20.0 and out[1][3] == 20.0
     n_panels = len(api.plan_panels("n_high", 0, 20000, 20000, panel_bytes=16 << 20))
     assert out[0][1] + out[1][1] == n_panels and abs(out[0][1] - out[1][1]) <= 1
+
+
+def test_pack_nibbles_layout():
+    """DG_INPUT_NIBBLE rows: site 2k in the low nibble of byte k, site 2k + 1 in the high one, possibility bits of the
+    Paradis code (encoding.rs:7-38); odd widths pad with N (15)."""
+    import numpy as np
+    from distance_b200 import api
+    codes = np.array([[136, 72, 40, 24, 192], [240, 244, 242, 112, 48]], dtype=np.uint8)   # A G C T R / N - ? B Y
+    nib = api.pack_nibbles(codes)
+    assert nib.shape == (2, 3)
+    assert nib.tolist() == [[0x48, 0x12, 0xFC], [0xFF, 0x7F, 0xF3]]

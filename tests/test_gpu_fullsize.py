@@ -234,3 +234,43 @@ def test_fast_epilogues_match_the_literal_ones(dg, oracle, measure, monkeypatch)
             assert e.timings()["engine"] == 3
     assert np.array_equal(res[False].view(np.uint64), res[True].view(np.uint64))
     check(measure, res[False], oracle_run(oracle, measure, "square", codes))
+
+
+@pytest.mark.parametrize("measure", ["n_high", "jc69", "k80", "tn93"])
+@pytest.mark.parametrize("width", [1, 2, 301, 3000])
+def test_nibble_input_matches_byte_input(dg, oracle, measure, width):
+    """DG_INPUT_NIBBLE (two sites per byte, the possibility half of the Paradis code) through every entry point: resident
+    load, the pipelined session, two files and the stream give the same results as the byte codes (and the oracle)."""
+    from distance_b200 import api, synth
+    rng = np.random.default_rng(width * 7 + len(measure))
+    n = 300
+    codes = synth.random_codes(rng, n, width, p_ambig=0.08)
+    nib = api.pack_nibbles(codes)
+    assert nib.shape == (n, (width + 1) // 2)
+    want = oracle_run(oracle, measure, "square", codes)
+    with dg.Engine(measure, width) as e:
+        e.load(0, nib, input_kind=api.DG_INPUT_NIBBLE)
+        check(measure, e.run_square(), want)
+        e.set_option(api.DG_OPT_PIPE_CHUNK_BYTES, 128 * width)
+        got, _ = e.square_pipelined(nib, input_kind=api.DG_INPUT_NIBBLE)
+        check(measure, got, want)
+        a, b = codes[:130], codes[130:]
+        e.load(1, api.pack_nibbles(b), input_kind=api.DG_INPUT_NIBBLE)
+        got, _ = e.rect_pipelined(api.pack_nibbles(a), input_kind=api.DG_INPUT_NIBBLE)
+        check(measure, got, oracle_run(oracle, measure, "rect", a, b))
+        e.load(0, api.pack_nibbles(a), input_kind=api.DG_INPUT_NIBBLE)
+        got = e.stream([api.pack_nibbles(b[i:i + 50]) for i in range(0, 170, 50)], input_kind=api.DG_INPUT_NIBBLE, max_batch=64)
+        check(measure, got, oracle_run(oracle, measure, "stream", a, b))
+
+
+def test_nibble_zero_is_reported_as_invalid(dg):
+    from distance_b200 import api, synth
+    rng = np.random.default_rng(5)
+    codes = synth.random_codes(rng, 40, 100)
+    nib = api.pack_nibbles(codes)
+    nib[17, 21] &= 0x0F                       # site 43 of record 17 -> nibble 0: no base possible
+    with dg.Engine("n_high", 100) as e:
+        with pytest.raises(api.DistanceGpuError) as ei:
+            e.load(0, nib, input_kind=api.DG_INPUT_NIBBLE)
+        assert ei.value.code == -4            # DG_ERR_INVALID_CODE
+        assert e.invalid_site()[:2] == (17, 43)

@@ -13,12 +13,17 @@ REL_TOL = 1e-12  # BASELINE.json north_star: "raw/jc69/k80/tn93 must agree withi
 ALL = ["n", "n_high", "raw", "jc69", "k80", "tn93"]
 
 
-@pytest.fixture(autouse=True, params=["lop3", "tc", "fp4", "auto"])
+@pytest.fixture(autouse=True, params=["lop3", "tc", "fp4", "auto", "fp4_nosplit"])
 def engine(request, monkeypatch):
     """Every test runs on every count engine and on the automatic choice: DG_ENGINE overrides DG_OPT_ENGINE at
     dg_create (1 = LOP3+POPC bit-plane tiles, 2 = tcgen05 kind::i8 GEMM, 3 = tcgen05 kind::mxf4 GEMM with unit
-    scales, 0 = auto)."""
-    monkeypatch.setenv("DG_ENGINE", {"lop3": "1", "tc": "2", "fp4": "3", "auto": "0"}[request.param])
+    scales, 0 = auto).  Small launches of the tensor engines split the K range over several CTA pairs (partial sums
+    added into a zeroed scratch); "fp4_nosplit" (DG_KSPLIT=1) keeps these small cases on the one-pass epilogues that the
+    large configs use (16-bit / modulo-2^16 scratch, direct counts)."""
+    monkeypatch.setenv("DG_ENGINE", {"lop3": "1", "tc": "2", "fp4": "3", "auto": "0", "fp4_nosplit": "3"}[request.param])
+    if request.param == "fp4_nosplit":
+        monkeypatch.setenv("DG_KSPLIT", "1")
+        return "fp4"
     return request.param
 
 
