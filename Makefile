@@ -13,7 +13,7 @@ lib: $(LIB)
 
 $(LIB): $(CSRC)/dg_api.cu $(CSRC)/kernels.cuh $(CSRC)/tc_engine.cuh include/distance_gpu.h
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) $(PTXAS_V) -shared -o $@ $(CSRC)/dg_api.cu
+	$(NVCC) $(NVFLAGS) $(PTXAS_V) -shared -o $@.tmp $(CSRC)/dg_api.cu && mv -f $@.tmp $@
 
 # The `distance` command line (C++ host over the C ABI; the image has no Rust toolchain).
 CXX ?= g++
@@ -23,9 +23,9 @@ HOST := $(CSRC)/host
 
 cli: $(CLI)
 
-$(CLI): $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp $(HOST)/fasta.hpp $(HOST)/tsv.hpp include/distance_gpu.h $(LIB)
+$(CLI): $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp $(HOST)/fasta.hpp $(HOST)/tsv.hpp $(HOST)/measures.hpp include/distance_gpu.h $(LIB)
 	@mkdir -p $(BINDIR)
-	$(CXX) -O2 -std=c++17 -Wall -Wextra -pthread -o $@ $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp \
+	$(CXX) -O2 -std=c++17 -ffp-contract=off -Wall -Wextra -pthread -o $@ $(HOST)/main.cpp $(HOST)/fasta.cpp $(HOST)/tsv.cpp \
 		-L$(LIBDIR) -ldistance_gpu -Wl,-rpath,'$$ORIGIN/../_lib'
 
 oracle:
@@ -37,7 +37,7 @@ tools: $(TOOLS)
 tools/ubench_%: tools/ubench_%.cu
 	$(NVCC) $(ARCH) -O3 -lineinfo -o $@ $< -lcuda -ldl
 tools/tsv_bench: tools/tsv_bench.cpp $(HOST)/tsv.cpp $(HOST)/fasta.cpp $(HOST)/tsv.hpp $(HOST)/fasta.hpp
-	$(CXX) -O2 -std=c++17 -pthread -o $@ tools/tsv_bench.cpp $(HOST)/tsv.cpp $(HOST)/fasta.cpp
+	$(CXX) -O2 -std=c++17 -ffp-contract=off -pthread -o $@ tools/tsv_bench.cpp $(HOST)/tsv.cpp $(HOST)/fasta.cpp
 
 clean:
 	rm -rf $(LIBDIR) $(BINDIR) && $(MAKE) -C oracle clean

@@ -250,6 +250,9 @@ class RowGrabber:
         r0, r1 = int(p.row_begin), int(p.row_end)
         self.pairs += int(p.n_results)
         isz = self.dtype.itemsize
+        whole = None
+        if int(p.result_kind) == self.api.DG_RESULT_U8:   # uint8 + overflow list: widen the panel once, slice below
+            whole = self.api.panel_values(p)
         for r in self.rows:
             if r0 <= r < r1:
                 if self.mode == self.api.DG_MODE_SQUARE:
@@ -257,7 +260,9 @@ class RowGrabber:
                     ln = self.n - 1 - r
                 else:
                     off, ln = (r - r0) * self.n_cols, self.n_cols
-                if ln:
+                if ln and whole is not None:
+                    self.rows[r] = whole[off:off + ln].copy()
+                elif ln:
                     buf = (C.c_uint8 * (ln * isz)).from_address(p.data + off * isz)
                     self.rows[r] = np.frombuffer(buf, dtype=self.dtype, count=ln).copy()
                 else:
@@ -351,6 +356,7 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
     eng.set_option(api.DG_OPT_KEEP_CODES, 1)
     if is_int:
         eng.set_option(api.DG_OPT_RESULT_U16, 1)
+        eng.set_option(api.DG_OPT_RESULT_U8, 1)
         eng.set_option(api.DG_OPT_PANEL_BYTES, 128 << 20)
     pa = pinned_copy(api, a_asc)
     pb = None if b_asc is None else pinned_copy(api, b_asc)
@@ -404,6 +410,9 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
     d.barrier()
     e2e_ms = d.max(1e3 * (time.time() - t0) / args.cfg_e2e_steps)
     e2e_pairs = int(d.sum(got_n))
+    eng.reset_timings()
+    e2e_step()
+    e2e_d2h = int(eng.timings()["d2h_bytes"])   # counted by the library from the copies it issued
     # sampled oracle check through the in-order path (dg_load_resident + dg_run_part): resident again after the session
     rng = np.random.default_rng(1000 + cfg_id * 10 + rank)
     eng.load(0, pa, input_kind=api.DG_INPUT_ASCII)
@@ -419,16 +428,15 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
     n_chk, hits = check_rows(measure, mode_name, grab, lambda r: lut[a_asc[r]], lambda c: lut[cols_asc[c]], n_cols, rng,
                              max(64, 2400 // max(1, len(rows))), label)
     n_chk = int(d.sum(n_chk))
-    hits = {k: int(d.sum(v)) for k, v in sorted(hits.items())} if hits else {}
+    hits = {k: int(d.sum(hits.get(k, 0))) for k in ("inf", "nan", "zero")}   # the same collectives on every rank
     eng.close()
-    elem = 2 if is_int else 8
     return {"id": cfg_id, "workload": label, "measure": measure, "mode": mode_name, "pairs": pairs,
             "kernel_ms": k_ms, "pairs_per_s": pairs / (k_ms * 1e-3), "pair_sites_per_s": pairs * WIDTH / (k_ms * 1e-3),
             "roofline_frac": tensor_frac(measure, pairs, k_ms, world, engine), "engine": ENGINE_NAME.get(engine, "?"),
             "sm_mhz_in_kernel": tm.get("sm_mhz"),
             "e2e_ms": e2e_ms, "e2e_pairs_per_s": e2e_pairs / (e2e_ms * 1e-3),
-            "h2d_bytes_per_step": int(na.nbytes + (0 if nb_ is None else nb_.nbytes)), "d2h_bytes_per_step": int(my_pairs * elem),
-            "e2e_input_kind": "DG_INPUT_NIBBLE",
+            "h2d_bytes_per_step": int(na.nbytes + (0 if nb_ is None else nb_.nbytes)), "d2h_bytes_per_step": e2e_d2h,
+            "e2e_input_kind": "DG_INPUT_NIBBLE", "e2e_result_kind": "u8 + overflow list" if is_int else "f64",
             "parity_sampled": "ok", "parity_pairs": n_chk, "special_values_hit": hits,
             "part": f"rank r runs part r of {parts}" if world > 1 or parts > 1 else "whole job"}
 
@@ -437,7 +445,7 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
     """BASELINE config 4: 1,000 resident records against 1,000,000 streamed ones (every rank streams 1/N of them) in
     pinned double-buffered batches.  The two staging buffers of the ring are filled once with two different chunks of a
     synthetic pool (a parser would write the next batch there: dg_stream_buffer) and pushed over and over, so a step
-    moves 29.9 GB / N over PCIe without a host-side copy in the way."""
+    moves 15 GB / N (two sites per byte) up and 8 GB / N of f64 results down over PCIe without a host-side copy in the way."""
     rank, world = d.rank, d.world
     lut = synth.ascii_lut()
     rng = np.random.default_rng(1000 + cfg_id * 10 + rank)
@@ -445,6 +453,8 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
     res_asc = spike(synth.make_alignment(1000, seed=20251018 + 4, ambiguity=True, root=root), rng)
     batch = 4096
     pool_asc = spike(synth.make_alignment(2 * batch, seed=20251018 + 44 + rank, ambiguity=True, root=root), rng)
+    pool_nib = api.pack_nibbles(lut[pool_asc])   # the streamed batches travel as DG_INPUT_NIBBLE rows (two sites per byte)
+    nibw = pool_nib.shape[1]
     total = args.stream_records // world
     eng = dg.Engine(measure, WIDTH, gpus=[d.local_rank])
     eng.load(0, res_asc, input_kind=api.DG_INPUT_ASCII)
@@ -472,8 +482,8 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
             nb = min(batch, n_records - done)
             eng._check(L.dg_stream_buffer(eng.h, C.byref(buf), C.byref(cap)))
             if fill and k < 2:   # the ring has two staging buffers per device: slot k % 2 keeps pool chunk k % 2
-                C.memmove(buf.value, pool_asc[k * batch:(k + 1) * batch].ctypes.data, batch * WIDTH)
-            eng._check(L.dg_stream_push(eng.h, buf, nb, api.DG_INPUT_ASCII, None))
+                C.memmove(buf.value, pool_nib[k * batch:(k + 1) * batch].ctypes.data, batch * nibw)
+            eng._check(L.dg_stream_push(eng.h, buf, nb, api.DG_INPUT_NIBBLE, None))
             done += nb
             k += 1
         eng._check(L.dg_stream_end(eng.h))
@@ -509,7 +519,7 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
             hits = merge_hits(hits, compare_sample(measure, vals.reshape(rows_in, 1000)[r, cols], want, f"{label} batch {k} row {r}"))
             n_chk += int(cols.size)
     n_chk = int(d.sum(n_chk))
-    hits = {k: int(d.sum(v)) for k, v in sorted(hits.items())}
+    hits = {k: int(d.sum(hits.get(k, 0))) for k in ("inf", "nan", "zero")}   # the same collectives on every rank
     eng.close()
     return {"id": cfg_id, "workload": label, "measure": measure, "mode": "stream", "pairs": pairs,
             "kernel_ms": dev_ms, "pairs_per_s": pairs / (dev_ms * 1e-3), "pair_sites_per_s": pairs * WIDTH / (dev_ms * 1e-3),
@@ -517,8 +527,9 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
             "roofline_frac": tensor_frac(measure, pairs, dev_ms, world, engine), "engine": ENGINE_NAME.get(engine, "?"),
             "sm_mhz_in_kernel": tm.get("sm_mhz"),
             "e2e_ms": wall_ms, "e2e_pairs_per_s": pairs / (wall_ms * 1e-3),
-            "h2d_bytes_per_step": int(total * WIDTH), "d2h_bytes_per_step": int(total * 1000 * 8),
-            "h2d_gbs": total * WIDTH / (wall_ms * 1e-3) / 1e9,
+            "h2d_bytes_per_step": int(total * nibw), "d2h_bytes_per_step": int(total * 1000 * 8),
+            "h2d_gbs": total * nibw / (wall_ms * 1e-3) / 1e9, "d2h_gbs": total * 8000 / (wall_ms * 1e-3) / 1e9,
+            "e2e_input_kind": "DG_INPUT_NIBBLE",
             "streamed_records": total * world, "batch": batch,
             "parity_sampled": "ok", "parity_pairs": n_chk, "special_values_hit": hits,
             "part": f"every rank streams {total} records" if world > 1 else "whole job"}
@@ -586,6 +597,8 @@ def run_ours(args):
     eng.set_option(api.DG_OPT_KEEP_CODES, 1)
     if args.is_int and not args.u32_results:
         eng.set_option(api.DG_OPT_RESULT_U16, 1)   # counts <= width < 65536: lossless, half the D2H bytes
+        if not args.u16_results:
+            eng.set_option(api.DG_OPT_RESULT_U8, 1)   # e2e panels as uint8 + an overflow list for the counts >= 255
     if args.tile_variant:
         eng.set_option(api.DG_OPT_TILE_VARIANT, args.tile_variant)
     if args.engine:
@@ -739,6 +752,9 @@ def run_ours(args):
         sync_all()
     e2e_step_ms = d.max(1e3 * (t1 - t0) / args.steps)
     e2e_value = total_pairs / (e2e_step_ms * 1e-3)
+    eng.reset_timings()
+    e2e_step()
+    e2e_d2h_bytes = int(d.sum(eng.timings()["d2h_bytes"]))   # counted by the library from the copies it issued (all ranks)
 
     # the in-order path (dg_load_resident, then dg_run_part: panels reach the sink in the reference's output order)
     e2e_inorder_ms = None
@@ -900,8 +916,9 @@ def run_ours(args):
                                       "panels reach the sink in completion order (descending rows)",
                     "in_order_ms_per_step": e2e_inorder_ms,
                     "in_order_note": "dg_load_resident + dg_run_square: same bytes, panels in the reference's output order (no overlap of upload and tiles)",
-                    "d2h_bytes_per_step": int(total_pairs * (8 if not args.is_int else (4 if args.u32_results else 2))),
-                    "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else "u16 (DG_OPT_RESULT_U16)")},
+                    "d2h_bytes_per_step": e2e_d2h_bytes,
+                    "result_type": "f64" if not args.is_int else ("u32" if args.u32_results else ("u16 (DG_OPT_RESULT_U16)" if args.u16_results else
+                                   "u8 + overflow list for counts >= 255 (DG_OPT_RESULT_U8; a panel with > 16,384 such pairs arrives as u16)"))},
             "gpu_launches": launches, "engine": ENGINE_NAME.get(engine_id, "?"),
             "parity_sampled": "ok", "parity_pairs": head_chk,
             "roofline": roofline, "roofline_pack": roofline_pack, "cpu_baseline": cpu, "clocks": clocks,
@@ -935,7 +952,8 @@ def main():
     ap.add_argument("--watchdog", type=int, default=900, help="seconds after which a stuck run dumps its stacks and exits")
     ap.add_argument("--trace-e2e", action="store_true", help="after the timed steps, print rank 0's device timeline of one e2e session (DG_TRACE)")
     ap.add_argument("--no-repack-overlap", action="store_true", help="pack every operand plane before the first tile (DG_OPT_REPACK_OVERLAP=0)")
-    ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint16)")
+    ap.add_argument("--u32-results", action="store_true", help="keep n / n_high panels as uint32 (default: uint8 + overflow list)")
+    ap.add_argument("--u16-results", action="store_true", help="deliver n / n_high panels as uint16 (default: uint8 + overflow list)")
     ap.add_argument("--measure", default="n_high", choices=sorted(OPS_PER_PAIR_SITE),
                     help="default n_high = BASELINE config 2 (the driver's workload); jc69 + --n 100000 = config 5")
     ap.add_argument("--configs", default="1,2,3,4,5", help="BASELINE configs measured next to the headline (\"\" = none)")

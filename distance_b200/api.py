@@ -21,6 +21,10 @@ DG_RUN_DEVICE_ONLY, DG_RUN_REPACK = 1, 2
 DG_OPT_PANEL_BYTES, DG_OPT_KEEP_CODES, DG_OPT_TILE_VARIANT, DG_OPT_ENGINE, DG_OPT_RESULT_U16, DG_OPT_PIPE_PANELS = 1, 2, 3, 4, 5, 6
 DG_OPT_PIPE_CHUNK_BYTES = 7
 DG_OPT_REPACK_OVERLAP = 8
+DG_OPT_RESULT_U8 = 9
+DG_OPT_RESULT_COUNTS = 10
+DG_RESULT_U8 = 3
+DG_RESULT_COUNTS16 = 4
 DG_SQUARE_LOOKAHEAD = 3
 DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
@@ -53,7 +57,29 @@ class Panel(C.Structure):
         ("n_cols", C.c_uint64),
         ("n_results", C.c_uint64),
         ("data", C.c_void_p),
+        ("overflow", C.c_void_p),
+        ("n_overflow", C.c_uint64),
     ]
+
+
+def panel_values(p) -> np.ndarray:
+    """The results of one dg_panel as a numpy array (a copy): uint32 / uint16 / float64 per result_kind; DG_RESULT_U8
+    panels are widened to uint16 with their overflow list applied."""
+    n = int(p.n_results)
+    kind = int(p.result_kind)
+    if kind == DG_RESULT_U8:
+        v = np.frombuffer((C.c_uint8 * max(n, 1)).from_address(p.data), dtype=np.uint8, count=n).astype(np.uint16)
+        k = int(p.n_overflow)
+        if k:
+            e = np.frombuffer((C.c_uint32 * (2 * k)).from_address(p.overflow), dtype=np.uint32, count=2 * k).reshape(k, 2)
+            assert np.all(v[e[:, 0]] == 255)
+            v[e[:, 0]] = e[:, 1].astype(np.uint16)
+        return v
+    if kind == DG_RESULT_COUNTS16:   # four uint16 counts per pair
+        return np.frombuffer((C.c_uint8 * max(n * 8, 1)).from_address(p.data), dtype=np.uint16, count=4 * n).reshape(n, 4).copy()
+    dtype = {DG_RESULT_U32: np.uint32, DG_RESULT_U16: np.uint16, DG_RESULT_F64: np.float64}[kind]
+    isz = np.dtype(dtype).itemsize
+    return np.frombuffer((C.c_uint8 * max(n * isz, 1)).from_address(p.data), dtype=dtype, count=n).copy()
 
 
 class Timings(C.Structure):
@@ -211,6 +237,7 @@ class Engine:
         self.h = h
         self.is_int = measure in ("n", "n_high")
         self.u16 = False
+        self.u8 = False
         self._n = [0, 0]
 
     # -- plumbing --------------------------------------------------------------------------------
@@ -239,10 +266,12 @@ class Engine:
         self._check(self.L.dg_set_option(self.h, key, value))
         if key == DG_OPT_RESULT_U16:
             self.u16 = bool(value) and self.is_int
+        if key == DG_OPT_RESULT_U8:
+            self.u8 = bool(value) and self.is_int
 
     def _dtype(self):
         """element type of the result panels (dg_panel.result_kind)"""
-        return (np.uint16 if self.u16 else np.uint32) if self.is_int else np.float64
+        return (np.uint16 if (self.u16 or self.u8) else np.uint32) if self.is_int else np.float64
 
     # -- inputs ----------------------------------------------------------------------------------
     def load(self, which: int, codes: np.ndarray, input_kind: int = DG_INPUT_PARADIS, acgt=None):
@@ -283,8 +312,7 @@ class Engine:
         def sink(user, pp):
             p = pp.contents
             n = int(p.n_results)
-            src = np.frombuffer((C.c_uint8 * (n * out.itemsize)).from_address(p.data), dtype=dtype, count=n)
-            out[state["pos"]:state["pos"] + n] = src
+            out[state["pos"]:state["pos"] + n] = panel_values(p)
             state["pos"] += n
             state["panels"].append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), n))
             return 0
@@ -298,6 +326,20 @@ class Engine:
         assert st["pos"] == out.shape[0], (st["pos"], out.shape)
         self.last_panels = st["panels"]
         return out
+
+    def run_square_counts(self):
+        """dg_run_square with DG_OPT_RESULT_COUNTS set: the (pairs, 4) uint16 count tuples of every panel, in output order
+        (panels that arrive as f64 -- LOP3 engine, wide alignments -- raise)."""
+        chunks = []
+
+        def sink(user, pp):
+            p = pp.contents
+            assert int(p.result_kind) == DG_RESULT_COUNTS16, int(p.result_kind)
+            chunks.append(panel_values(p))
+            return 0
+
+        self._check(self.L.dg_run_square(self.h, SINK_FN(sink), None, 0))
+        return np.concatenate(chunks) if chunks else np.zeros((0, 4), np.uint16)
 
     def run_rect(self, flags: int = 0):
         out, st, cb = self._collect(self._n[0] * self._n[1])
@@ -313,10 +355,7 @@ class Engine:
 
         def sink(user, pp):
             p = pp.contents
-            n = int(p.n_results)
-            src = np.frombuffer((C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(p.data),
-                                dtype=dtype, count=n)
-            got.append((int(p.row_begin), int(p.row_end), src.copy()))
+            got.append((int(p.row_begin), int(p.row_end), panel_values(p).astype(dtype)))
             return 0
 
         self._check(self.L.dg_run_part(self.h, mode, part, n_parts, SINK_FN(sink), None, flags))
@@ -359,8 +398,7 @@ class Engine:
             cnt = int(p.n_results)
             r0 = int(p.row_begin)
             base = r0 * (2 * n - r0 - 1) // 2
-            src = np.frombuffer((C.c_uint8 * (cnt * out.itemsize)).from_address(p.data), dtype=dtype, count=cnt)
-            out[base:base + cnt] = src
+            out[base:base + cnt] = panel_values(p)
             panels.append((int(p.mode), r0, int(p.row_end), int(p.n_cols), cnt))
             return 0
 
@@ -399,8 +437,7 @@ class Engine:
         def sink(user, pp):
             p = pp.contents
             cnt = int(p.n_results)
-            src = np.frombuffer((C.c_uint8 * (cnt * np.dtype(dtype).itemsize)).from_address(p.data), dtype=dtype, count=cnt)
-            chunks.append(src.copy())
+            chunks.append(panel_values(p).astype(dtype))
             panels.append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), cnt))
             return 0
 
@@ -473,9 +510,7 @@ class Engine:
         def sink(user, pp):
             p = pp.contents
             n = int(p.n_results)
-            src = np.frombuffer((C.c_uint8 * (n * np.dtype(dtype).itemsize)).from_address(p.data),
-                                dtype=dtype, count=n)
-            chunks.append(src.copy())
+            chunks.append(panel_values(p).astype(dtype))
             panels.append((int(p.mode), int(p.row_begin), int(p.row_end), int(p.n_cols), n))
             return 0
 

@@ -117,6 +117,11 @@ struct Slot {  // one stage of the result ring (and of the stream-input ring)
     void* h_out = nullptr;
     int* d_scratch = nullptr;       // tcgen05 engine: raw int32 sums, [accumulator][panel pair]
     size_t scratch_cap = 0;
+    int kind = -1;                  // dg_result_kind of the panel in flight when it differs from the context's default (-1)
+    uint8_t* d_out8 = nullptr;      // DG_OPT_RESULT_U8: the panel narrowed to uint8 ...
+    size_t out8_cap = 0;
+    uint32_t* d_ovf = nullptr;      // ... and {count, -, entries {index, value} x OVF_CAP}
+    uint32_t* h_ovf = nullptr;      // pinned mirror
     uint32_t* d_tiles = nullptr;    // tcgen05 engine, square panels: live-tile list of this slot's launch
     uint32_t* h_tiles = nullptr;    // pinned staging of the same
     size_t tiles_cap = 0;
@@ -264,8 +269,13 @@ struct dg_ctx {
     uint64_t plan_tn() const { return want_fp4() ? 240 : 256; }
     uint64_t plan_items() const { static const uint64_t it[4] = {1, 2, 3, 5}; return it[fam]; }
     bool result_u16 = false;  // DG_OPT_RESULT_U16: n / n_high panels hold uint16 counts (needs width <= 65535)
-    bool u16() const { return measure <= 1 && result_u16; }
+    bool result_u8 = false;   // DG_OPT_RESULT_U8: ... delivered as uint8 + overflow list (the device still computes uint16)
+    bool u16() const { return measure <= 1 && (result_u16 || result_u8); }
+    bool u8() const { return measure <= 1 && result_u8; }
     size_t elem_bytes() const { return measure <= 1 ? (u16() ? 2 : 4) : 8; }
+    bool result_counts = false;   // DG_OPT_RESULT_COUNTS
+    // float measures on the tensor engines (resident panels / sessions): count tuples instead of the f64 (same 8 bytes)
+    bool counts16() const { return measure >= 2 && result_counts && width <= 65535; }
     int result_kind() const { return measure <= 1 ? (u16() ? DG_RESULT_U16 : DG_RESULT_U32) : DG_RESULT_F64; }
 };
 
@@ -342,13 +352,77 @@ void ensure_out_ring(dg_ctx* c, Device& d, size_t bytes) {
         s.d_out = s.h_out = nullptr;
     }
     d.out_cap = 0;
-    for (auto& s : d.slot) {
-        CUDA_CHECK(cudaMalloc(&s.d_out, bytes));
-        CUDA_CHECK(cudaHostAlloc(&s.h_out, bytes, cudaHostAllocDefault));
+    try {
+        for (auto& s : d.slot) {
+            CUDA_CHECK(cudaMalloc(&s.d_out, bytes));
+            CUDA_CHECK(cudaHostAlloc(&s.h_out, bytes, cudaHostAllocDefault));
+        }
+    } catch (const DgError& e) {
+        // a panel is never smaller than 512 rows x every column (the tensor engine's block height), whatever
+        // DG_OPT_PANEL_BYTES asks for: with millions of columns that minimum may not fit
+        fail(e.code, "the result ring needs %d x %zu bytes of device and of page-locked host memory (one panel = at least 512 rows x "
+                     "every column, DG_OPT_PANEL_BYTES = %zu): %s", Device::NSLOT, bytes, c->panel_bytes, e.msg.c_str());
     }
     d.out_cap = bytes;
 }
 
+
+// ---- DG_OPT_RESULT_U8 --------------------------------------------------------------------------------------------------
+constexpr uint32_t OVF_CAP = 16384;                       // overflow entries a uint8 panel may carry
+constexpr size_t OVF_WORDS = 2 + 2 * (size_t)OVF_CAP;     // {count, pad, entries}
+void ensure_narrow(Slot& s, size_t n_results) {
+    if (!s.d_ovf) {
+        CUDA_CHECK(cudaMalloc(&s.d_ovf, OVF_WORDS * 4));
+        CUDA_CHECK(cudaHostAlloc(&s.h_ovf, OVF_WORDS * 4, cudaHostAllocDefault));
+    }
+    if (s.out8_cap >= n_results) return;
+    if (s.d_out8) cudaFree(s.d_out8);
+    s.d_out8 = nullptr; s.out8_cap = 0;
+    CUDA_CHECK(cudaMalloc(&s.d_out8, n_results + 64));
+    s.out8_cap = n_results;
+}
+void free_narrow(Slot& s) {
+    if (s.d_out8) cudaFree(s.d_out8);
+    if (s.d_ovf) cudaFree(s.d_ovf);
+    if (s.h_ovf) cudaFreeHost(s.h_ovf);
+    s.d_out8 = nullptr; s.d_ovf = s.h_ovf = nullptr; s.out8_cap = 0;
+}
+// after the panel's kernels, on their stream: uint16 d_out -> uint8 d_out8 + overflow list
+void enqueue_narrow(dg_ctx* c, Slot& s, uint64_t n_results, cudaStream_t st) {
+    CUDA_CHECK(cudaMemsetAsync(s.d_ovf, 0, 8, st));
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_results / 16 + 256) / 256, 148 * 16);
+    tc::narrow_u8_kernel<<<std::max(1u, grid), 256, 0, st>>>(reinterpret_cast<const uint16_t*>(s.d_out), s.d_out8, n_results, s.d_ovf, OVF_CAP);
+    CUDA_CHECK(cudaGetLastError());
+    c->tm.count_launches++;
+}
+// D2H of a finished panel on the copy stream (after `k_stop`)
+void enqueue_panel_d2h(dg_ctx* c, Device& d, Slot& s, uint64_t n_results) {
+    if (c->u8()) {
+        CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out8, (size_t)n_results, cudaMemcpyDeviceToHost, d.copy));
+        CUDA_CHECK(cudaMemcpyAsync(s.h_ovf, s.d_ovf, OVF_WORDS * 4, cudaMemcpyDeviceToHost, d.copy));
+    } else {
+        CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)n_results * c->elem_bytes(), cudaMemcpyDeviceToHost, d.copy));
+    }
+}
+// fill the result fields of a panel descriptor once its copy has landed; a uint8 panel with too many overflows is
+// fetched again as uint16 (the slot's d_out still holds it)
+void finish_panel_desc(dg_ctx* c, Device& d, Slot& s, dg_panel& desc) {
+    desc.result_kind = s.kind >= 0 ? s.kind : c->result_kind();
+    desc.data = s.h_out;
+    desc.overflow = nullptr; desc.n_overflow = 0;
+    if (!c->u8()) { c->tm.d2h_bytes += desc.n_results * c->elem_bytes(); return; }
+    const uint32_t count = s.h_ovf[0];
+    if (count <= OVF_CAP) {
+        desc.result_kind = DG_RESULT_U8;
+        desc.overflow = reinterpret_cast<const dg_overflow*>(s.h_ovf + 2);
+        desc.n_overflow = count;
+        c->tm.d2h_bytes += desc.n_results + OVF_WORDS * 4;
+    } else {
+        CUDA_CHECK(cudaSetDevice(d.id));
+        CUDA_CHECK(cudaMemcpy(s.h_out, s.d_out, (size_t)desc.n_results * 2, cudaMemcpyDeviceToHost));
+        c->tm.d2h_bytes += desc.n_results * 3 + OVF_WORDS * 4;
+    }
+}
 
 // ---- tcgen05 engine: host side ------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -431,9 +505,11 @@ void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
 
 // Enqueue (no sync) the int8 operand planes (and, with count_acgt, the per-record A,T,G,C counts) of rows
 // [row0, row0 + n) of the set; the chunk's padding rows up to a multiple of 128 are zero-filled.
+// b_side_only: store only the planes the B (column) operand of the family's schedule reads (records that are columns of
+// this rank's panels but rows of nobody's here: a rank of a multi-process run packs U planes for its own rows only).
 void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, bool count_acgt,
                      cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr, bool upper_ascii = false,
-                     Device* pp_dev = nullptr) {
+                     Device* pp_dev = nullptr, bool b_side_only = false) {
     const TcSchedule& sch = tc_schedule(c->fam);
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     tc::PackI8Params pp{};
@@ -449,6 +525,12 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     pp.ascii = input_kind == DG_INPUT_ASCII;
     pp.nplanes = sch.nplanes;
     for (int i = 0; i < sch.nplanes; i++) pp.plane_id[i] = sch.plane_id[i];
+    pp.plane_mask = 0xFFFFFFFFu;
+    if (b_side_only) {
+        pp.plane_mask = 0;
+        for (int a = 0; a < sch.nacc; a++)
+            for (int i = 0; i < sch.npairs[a]; i++) pp.plane_mask |= 1u << sch.pb[a][i];
+    }
     const unsigned grid = (unsigned)std::min<uint64_t>(n_pad, 148 * 8);
     auto launch = [&](auto fp4, auto fam) {
         static_assert(tc::PackPlanes<decltype(fam)::value>::N <= tc::MAX_PLANES, "plane list too long");
@@ -736,7 +818,7 @@ bool tc_pp_pending(const dg_ctx* c, const PlaneSet& A, const PlaneSet& B, bool a
 // Raw int32 sums of every accumulator (scratch[accumulator][panel pair]) -> the reference's counts -> the result
 // (uint16 / uint32 count, f64 distance through the epi_* epilogues, or the debug counts).
 void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, int mode, const Panel& p, void* d_out,
-                    int* scratch, const AccPlan& plan, bool swap_roles, bool counts, cudaStream_t st) {
+                    int* scratch, const AccPlan& plan, bool swap_roles, bool counts, cudaStream_t st, bool counts16 = false) {
     tc::CombineParams cp{};
     cp.acc = reinterpret_cast<const uint8_t*>(scratch);
     for (uint32_t a = 0; a < plan.nacc; a++) { cp.acc_off[a] = plan.off[a]; cp.acc_op[a] = plan.op[a]; }
@@ -747,7 +829,7 @@ void launch_combine(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     cp.square = mode == DG_MODE_SQUARE ? 1 : 0;
     cp.col0 = cp.square ? (uint32_t)((p.row0 + 1) / 256 * 256) : 0;
     cp.swap_roles = swap_roles ? 1 : 0; cp.measure = c->measure; cp.fam = c->fam;
-    cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : tc::RES_F64);
+    cp.result = counts ? tc::RES_COUNTS : (c->measure <= 1 ? (c->u16() ? tc::RES_U16 : tc::RES_U32) : (counts16 ? tc::RES_COUNTS16 : tc::RES_F64));
     cp.n_total = A.n; cp.out_base = p.out_base; cp.out = d_out;
     // virtual blocks: 256-column strips x row phases (~16 per SM)
     const unsigned gx = (unsigned)((B.n - cp.col0 + 255) / 256);
@@ -828,7 +910,9 @@ cudaStream_t enqueue_panel_tc(dg_ctx* c, Device& d, const PlaneSet& A, const Pla
         CUDA_CHECK(cudaGetLastError());
         c->tm.count_launches++;
     }
-    if (!skip_combine) launch_combine(c, d, A, B, mode, p, d_out, scratch, plan, swap_roles, counts, st);
+    const bool c16 = !counts && !a_is_batch && ws && c->counts16();   // resident panels only
+    if (ws) ws->kind = c16 ? DG_RESULT_COUNTS16 : -1;
+    if (!skip_combine) launch_combine(c, d, A, B, mode, p, d_out, scratch, plan, swap_roles, counts, st, c16);
     return st;
 }
 
@@ -1119,6 +1203,8 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
     for (auto& d : c->devs) {
         CUDA_CHECK(cudaSetDevice(d.id));
         ensure_out_ring(c, d, std::max<size_t>(max_bytes, 256));
+        if (c->u8() && !device_only)
+            for (auto& sl : d.slot) ensure_narrow(sl, max_bytes / c->elem_bytes());
         bool any_split = false;
         if (tc_run)
             for (auto& p : mine) any_split = any_split || choose_ksplit(c, d.set[0], d.set[wb], mode, p) > 1;
@@ -1155,13 +1241,11 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
             if (!device_only) {
                 dg_panel desc{};
                 desc.mode = mode;
-                desc.result_kind = c->result_kind();
                 desc.row_begin = p.row0;
                 desc.row_end = p.row1;
                 desc.n_cols = mode == DG_MODE_SQUARE ? A0.n : B0.n;
                 desc.n_results = p.n_results;
-                desc.data = s.h_out;
-                c->tm.d2h_bytes += p.n_results * c->elem_bytes();
+                finish_panel_desc(c, d, s, desc);
                 if (sink(user, &desc) != 0) {
                     for (auto& dd : c->devs) { cudaSetDevice(dd.id); cudaDeviceSynchronize(); }
                     fail(DG_ERR_SINK, "sink aborted the run at panel %d", h);
@@ -1177,9 +1261,14 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
             if (repack_descending) {
                 uint64_t& lo = packed_lo[k % ndev];
                 if (p.row0 < lo) {
+                    // this panel's own rows get every plane; the records between it and what is already packed (other
+                    // ranks' panels) only serve as columns here: B-side planes (chunk boundaries: multiples of 128 records)
                     PlaneSet& ps = d.set[0];
-                    enqueue_tc_pack(c, ps, ps.codes, lo - p.row0, ps.input_kind, !ps.acgt_from_host && c->fam == FAM_TN93, d.prep,
-                                    p.row0);
+                    const bool cnt = !ps.acgt_from_host && c->fam == FAM_TN93;
+                    const uint64_t own_end = std::min<uint64_t>(lo, (p.row1 + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN);
+                    enqueue_tc_pack(c, ps, ps.codes, own_end - p.row0, ps.input_kind, cnt, d.prep, p.row0);
+                    if (own_end < lo)
+                        enqueue_tc_pack(c, ps, ps.codes, lo - own_end, ps.input_kind, cnt, d.prep, own_end, nullptr, false, nullptr, true);
                     CUDA_CHECK(cudaEventRecord(d.sq_ready, d.prep));
                     lo = p.row0;
                 }
@@ -1188,15 +1277,16 @@ void run_panel_list(dg_ctx* c, int mode, const std::vector<Panel>& mine, bool tc
             CUDA_CHECK(cudaEventRecord(s.k_start, d.cs(si)));
             if (trace) CUDA_CHECK(cudaEventRecord(tr0[k], d.cs(si)));
             cudaStream_t last = d.cs(si);
+            s.kind = -1;
             if (tc_run) last = enqueue_panel_tc(c, d, d.set[0], d.set[wb], mode, p, s.d_out, s.d_scratch, false, false, d.cs(si), false, &s,
                                                 trace ? tr1[k] : nullptr, use_post ? d.post : nullptr);
             else enqueue_panel_kernel<false>(c, d, d.set[0], d.set[wb], mode, p, s.d_out, false, d.cs(si));
+            if (c->u8() && !device_only) enqueue_narrow(c, s, p.n_results, last);
             CUDA_CHECK(cudaEventRecord(s.k_stop, last));
             if (trace) CUDA_CHECK(cudaEventRecord(tr2[k], last));
             if (!device_only) {
                 CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
-                CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(),
-                                           cudaMemcpyDeviceToHost, d.copy));
+                enqueue_panel_d2h(c, d, s, p.n_results);
                 CUDA_CHECK(cudaEventRecord(s.copied, d.copy));
             }
         }
@@ -1264,8 +1354,7 @@ void sq_sink_front(dg_ctx* c) {
     CUDA_CHECK(cudaEventSynchronize(s.copied));
     harvest_kernel_time(c, s);
     c->tm.pairs += f.pairs;
-    c->tm.d2h_bytes += f.desc.n_results * c->elem_bytes();
-    f.desc.data = s.h_out;
+    finish_panel_desc(c, d, s, f.desc);
     c->sq_queue.erase(c->sq_queue.begin());
     if (c->sq_sink(c->sq_user, &f.desc) != 0) fail(DG_ERR_SINK, "sink aborted the session");
 }
@@ -1302,6 +1391,7 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
             while (v->size() <= li) { cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); v->push_back(e); }
         CUDA_CHECK(cudaEventRecord(d.tr_k0[li], st));
     }
+    s.kind = -1;
     const uint32_t n_entries = c->sq_base[c->sq_pumped];   // entries of every chunk pumped so far
     const bool repair = c->sq_needs_pp && n_entries != 0 && (!rect || B.pp.n_entries != 0);
     if (c->fam == FAM_SNP && !repair) {
@@ -1349,12 +1439,14 @@ void sq_launch_panel(dg_ctx* c, size_t k) {
                 c->tm.count_launches++;
             }
         }
-        launch_combine(c, d, S, B, c->sq_mode, p, s.d_out, s.d_scratch, plan, false, false, st);
+        s.kind = c->counts16() ? DG_RESULT_COUNTS16 : -1;
+        launch_combine(c, d, S, B, c->sq_mode, p, s.d_out, s.d_scratch, plan, false, false, st, c->counts16());
     }
+    if (c->u8()) enqueue_narrow(c, s, p.n_results, st);
     CUDA_CHECK(cudaEventRecord(s.k_stop, st));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_k1[li], st));
     CUDA_CHECK(cudaStreamWaitEvent(d.copy, s.k_stop, 0));
-    CUDA_CHECK(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)p.n_results * c->elem_bytes(), cudaMemcpyDeviceToHost, d.copy));
+    enqueue_panel_d2h(c, d, s, p.n_results);
     CUDA_CHECK(cudaEventRecord(s.copied, d.copy));
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_d2h[li], d.copy));
     InFlight f;
@@ -1481,6 +1573,8 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     c->sq_next = 0;
     size_t max_bytes = 256;
     for (auto& p : c->sq_panels) max_bytes = std::max(max_bytes, (size_t)p.n_results * c->elem_bytes());
+    if (want_tc && c->u8())
+        for (auto& sl : d.pslot) ensure_narrow(sl, max_bytes / c->elem_bytes());
     if (want_tc) {
         size_t sb = 0;
         if (c->fam != FAM_SNP || c->sq_needs_pp)
@@ -1837,6 +1931,7 @@ void destroy_device(Device& d) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_nib) cudaFree(s.d_nib);
         if (s.h_acgt) cudaFreeHost(s.h_acgt);
+        free_narrow(s);
         free_set(s.batch);
         for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.in_ready, s.p_start, s.p_stop, s.gemm_done})
             if (e) cudaEventDestroy(e);
@@ -1847,6 +1942,7 @@ void destroy_device(Device& d) {
         if (s.d_tiles) cudaFree(s.d_tiles);
         if (s.h_tiles) cudaFreeHost(s.h_tiles);
         if (s.h_out) cudaFreeHost(s.h_out);
+        free_narrow(s);
         for (cudaEvent_t e : {s.k_start, s.k_stop, s.copied, s.gemm_done})
             if (e) cudaEventDestroy(e);
     }
@@ -2035,6 +2131,11 @@ int dg_set_option(dg_ctx* ctx, int key, int64_t value) {
             if (value != 0 && ctx->width > 65535) fail(DG_ERR_INVALID_ARG, "uint16 results need width <= 65535");
             ctx->result_u16 = value != 0;
             break;
+        case DG_OPT_RESULT_U8:
+            if (value != 0 && ctx->width > 65535) fail(DG_ERR_INVALID_ARG, "uint8 results need width <= 65535");
+            ctx->result_u8 = value != 0;
+            break;
+        case DG_OPT_RESULT_COUNTS: ctx->result_counts = value != 0; break;
         case DG_OPT_PIPE_PANELS:
             if (value < 1 || value > 4096) fail(DG_ERR_INVALID_ARG, "pipe panels must be in [1, 4096]");
             ctx->pipe_panels = (int)value;

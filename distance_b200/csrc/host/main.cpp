@@ -274,6 +274,39 @@ int run(const Args& a) {
     struct Guard { dg_ctx* c; ~Guard() { if (c) dg_destroy(c); } } guard{ctx};
     if (trace) fprintf(stderr, "[distance] %.3f s: dg_create done (CUDA context, streams)\n", since());
     if (width <= 65535) dg_set_option(ctx, DG_OPT_RESULT_U16, 1);  // n / n_high: half the D2H bytes, same text
+    // raw / jc69 / k80 / tn93 over loaded files: the panels carry the integer counts and the writer's threads evaluate the
+    // f64 expressions of measures.rs with this host's libm, so the text is byte-identical to the reference's (CUDA's log
+    // may be an ulp off glibc's).  Streamed runs keep the device's fused f64 epilogue.  DISTANCE_DEVICE_F64=1 switches it off.
+    const int mid = measure_id(a.measure);
+    const bool host_f64 = mid >= 2 && stream_fd < 0 && width <= 65535 && !std::getenv("DISTANCE_DEVICE_F64");
+    std::vector<uint32_t> acgt[2];
+    if (host_f64) {
+        dg_set_option(ctx, DG_OPT_RESULT_COUNTS, 1);
+        if (mid == DG_MEASURE_TN93)   // count_bases (fastaio.rs:53-66): the codes of A / T / G / C, either case
+            for (size_t k = 0; k < loaded.size(); k++) {
+                acgt[k].assign(loaded[k].n() * 4, 0);
+                const uint8_t* base = loaded[k].data();
+                const uint64_t nrec = loaded[k].n();
+                const int T = (int)std::min<uint64_t>(threads, 64);
+                std::vector<std::thread> th;
+                for (int t = 0; t < T; t++)
+                    th.emplace_back([&, t] {
+                        for (uint64_t r = t; r < nrec; r += T) {
+                            const uint8_t* s = base + r * width;
+                            uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
+                            for (uint64_t i = 0; i < width; i++) {
+                                const uint8_t ch = s[i] | 0x20;   // lower-case the letter
+                                cA += ch == 'a'; cT += ch == 't'; cG += ch == 'g'; cC += ch == 'c';
+                            }
+                            uint32_t* o = acgt[k].data() + 4 * r;
+                            o[0] = cA; o[1] = cT; o[2] = cG; o[3] = cC;
+                        }
+                    });
+                for (auto& x : th) x.join();
+            }
+        writer.set_counts_measure(mid, acgt[0].empty() ? nullptr : acgt[0].data(),
+                                  loaded.size() > 1 ? (acgt[1].empty() ? nullptr : acgt[1].data()) : (acgt[0].empty() ? nullptr : acgt[0].data()));
+    }
     // 32 MiB result panels: the pinned ring (two panels per GPU) costs ~0.5 ms per MB to page-lock, and the writer
     // formats a panel far faster than the GPU produces it, so larger panels buy nothing here
     dg_set_option(ctx, DG_OPT_PANEL_BYTES, 32 << 20);

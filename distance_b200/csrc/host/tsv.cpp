@@ -1,4 +1,5 @@
 #include "tsv.hpp"
+#include "measures.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -234,6 +235,17 @@ inline char* copy_id(char* p, const char* src, uint32_t len) {
     return p + len;
 }
 
+// DG_RESULT_COUNTS16: four uint16 counts per pair -> the f64 of measures.rs with the host's libm (measures.hpp)
+inline double counts_value(int measure, const void* data, uint64_t k, const uint32_t* q_acgt, const uint32_t* t_acgt) {
+    const uint16_t* c = static_cast<const uint16_t*>(data) + 4 * k;
+    switch (measure) {
+    case DG_MEASURE_RAW: return raw_from_counts(c[0], c[1]);
+    case DG_MEASURE_JC69: return jc69_from_counts(c[0], c[1]);
+    case DG_MEASURE_K80: return k80_from_counts(c[0], c[1], c[2]);
+    default: return tn93_from_counts(c[0], c[1], c[2], c[3], q_acgt, t_acgt);
+    }
+}
+
 template <int KIND>
 inline char* put_value(char* p, const void* data, uint64_t k) {
     if (KIND == DG_RESULT_U16) {
@@ -261,8 +273,9 @@ inline char* put_value(char* p, const void* data, uint64_t k) {
 template <int KIND>
 size_t TsvWriter::format_chunk(const dg_panel& p, const std::vector<uint64_t>& row_start, uint64_t k0, uint64_t k1,
                                std::vector<char>& buf) {
-    const size_t line_max = ids1_tab_.max_len() + ids2_tab_.max_len() + (KIND == DG_RESULT_F64 ? 420 : 16) + 64;
-    const size_t typical = ids1_tab_.max_len() + ids2_tab_.max_len() + (KIND == DG_RESULT_F64 ? 24 : 8);
+    constexpr bool kFloat = KIND == DG_RESULT_F64 || KIND == DG_RESULT_COUNTS16;
+    const size_t line_max = ids1_tab_.max_len() + ids2_tab_.max_len() + (kFloat ? 420 : 16) + 64;
+    const size_t typical = ids1_tab_.max_len() + ids2_tab_.max_len() + (kFloat ? 24 : 8);
     if (buf.size() < (k1 - k0) * typical + line_max) buf.resize((k1 - k0) * typical + line_max);
     char* out = buf.data();
     char* limit = buf.data() + buf.size() - line_max;
@@ -300,7 +313,15 @@ size_t TsvWriter::format_chunk(const dg_panel& p, const std::vector<uint64_t>& r
                 if (q > limit) grow(q);
                 q = copy_id(q, a, al);
                 q = copy_id(q, cols.ptr(j), cols.len(j));
-                q = put_value<KIND>(q, p.data, k);
+                if (KIND == DG_RESULT_COUNTS16) {
+                    // row record = the reference's `query`, column record = `target` (lib.rs:430-434)
+                    const uint32_t* qa = acgt_rows_ ? acgt_rows_ + 4 * row : nullptr;
+                    const uint32_t* ta = acgt_cols_ ? acgt_cols_ + 4 * j : nullptr;
+                    q = put_float12(q, counts_value(counts_measure_, p.data, k, qa, ta));
+                    *q++ = '\n';
+                } else {
+                    q = put_value<KIND>(q, p.data, k);
+                }
             }
         }
     }
@@ -322,6 +343,7 @@ void TsvWriter::run_chunks() {
         try {
             if (p.result_kind == DG_RESULT_U16) n = format_chunk<DG_RESULT_U16>(p, P.row_start, k0, k1, buf);
             else if (p.result_kind == DG_RESULT_U32) n = format_chunk<DG_RESULT_U32>(p, P.row_start, k0, k1, buf);
+            else if (p.result_kind == DG_RESULT_COUNTS16) n = format_chunk<DG_RESULT_COUNTS16>(p, P.row_start, k0, k1, buf);
             else n = format_chunk<DG_RESULT_F64>(p, P.row_start, k0, k1, buf);
         } catch (const std::exception& e) {
             err = e.what();

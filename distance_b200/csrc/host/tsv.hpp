@@ -56,6 +56,11 @@ public:
         ids1_ = ids1; ids2_ = ids2;
         ids1_tab_.clear(); ids2_tab_.clear();
     }
+    // DG_RESULT_COUNTS16 panels (raw / jc69 / k80 / tn93 as integer counts): which measure to evaluate on the host, and for
+    // tn93 the A,T,G,C counts (4 per record) of the row / column alignment (fastaio.rs:53-66)
+    void set_counts_measure(int measure, const uint32_t* acgt_rows, const uint32_t* acgt_cols) {
+        counts_measure_ = measure; acgt_rows_ = acgt_rows; acgt_cols_ = acgt_cols;
+    }
     void write_panel(const dg_panel& p);  // throws DistanceError on an io error other than BrokenPipe
     void flush();
     uint64_t lines() const { return lines_; }
@@ -77,6 +82,9 @@ private:
     const std::vector<std::string>* ids1_ = nullptr;
     const std::vector<std::string>* ids2_ = nullptr;
     uint64_t lines_ = 0;
+    int counts_measure_ = -1;
+    const uint32_t* acgt_rows_ = nullptr;
+    const uint32_t* acgt_cols_ = nullptr;
 };
 
 }  // namespace host

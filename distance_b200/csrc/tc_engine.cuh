@@ -241,6 +241,7 @@ struct PackI8Params {
     int count_upper_ascii; // ASCII input: count raw 'A','T','G','C' only (fastaio.rs:139-142) instead of count_bases
     int nplanes;
     uint8_t plane_id[MAX_PLANES];
+    uint32_t plane_mask;   // bit pl set = store plane pl (records that only ever serve as COLUMNS need no A-side planes)
     unsigned long long* invalid;  // min over ((seq0 + record) << 32 | site) of invalid bytes; or NULL
     uint64_t seq0;                // global index of record 0 of this chunk
     // partial ambiguity codes (R Y M W S K V H D B) met while packing, for the both-partial repair index; or NULL:
@@ -304,13 +305,16 @@ __device__ __forceinline__ NibBits nib_bits(uint32_t wlo, uint32_t whi) {
     b.e0 = E & N1; b.e1 = (E >> 1) & N1;
     return b;
 }
+// Each bit of the E2M1 code of V_b = 3 b - E is a 3-input boolean function of (b, e0, e1), i.e. ONE LOP3 (the inputs
+// carry bits at the nibble LSB positions only and every function maps (0, 0, 0) to 0, so no masking is needed); the four
+// result bits are merged with multiply-adds, which issue on the FMA pipe instead of the ALU pipe this kernel is bound by.
+//   b = 1: E = 0 -> 3 (0101), 1 -> 2 (0100), 2 -> 1 (0010), 3 -> 0;   b = 0: E = 0 -> 0, 1 -> -1 (1010), 2 -> -2 (1100)
 __device__ __forceinline__ uint32_t nib_v(const NibBits& n, uint32_t b) {   // V_b = 3 b - E as E2M1
-    const uint32_t x = n.e1 & ~n.e0, y = n.e0 & ~n.e1, nz = n.e0 | n.e1;     // E == 2, E == 1, E != 0
-    const uint32_t b3 = nz & ~b;                       // negative: base impossible in an ambiguous code
-    const uint32_t b2 = (b & ~n.e1) | (~b & x);        // 3, 2 | -2
-    const uint32_t b1 = (b & x) | (~b & y);            // 1    | -1
-    const uint32_t b0 = b & ~nz;                       // 3
-    return (b0 & N1) | ((b1 & N1) << 1) | ((b2 & N1) << 2) | ((b3 & N1) << 3);
+    const uint32_t b0 = lop3<0x10>(b, n.e0, n.e1);   // b & ~e0 & ~e1
+    const uint32_t b1 = lop3<0x24>(b, n.e0, n.e1);   // (b & e1 & ~e0) | (~b & e0 & ~e1)
+    const uint32_t b2 = lop3<0x52>(b, n.e0, n.e1);   // (b & ~e1) | (~b & e1 & ~e0)
+    const uint32_t b3 = lop3<0x06>(b, n.e0, n.e1);   // ~b & (e0 ^ e1)
+    return b3 * 8u + b2 * 4u + b1 * 2u + b0;          // disjoint bits: the sums carry nothing
 }
 __device__ __forceinline__ uint32_t nib_pm(uint32_t pos, uint32_t neg) { return ((pos | neg) << 1) | (neg << 3); }  // +1 / -1
 // The eight E2M1 nibbles of plane `id`.
@@ -455,8 +459,9 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
 #pragma unroll
                 for (int pl = 0; pl < PL::N; pl++) {
                     const uint32_t id = PL::id(pl);
-                    __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
-                           make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id)));
+                    if ((p.plane_mask >> pl) & 1u)
+                        __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
+                               make_uint4(plane_nib8(nb[0], id), plane_nib8(nb[1], id), plane_nib8(nb[2], id), plane_nib8(nb[3], id)));
                 }
             } else {
                 CodeBits b[4];
@@ -472,8 +477,9 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
 #pragma unroll
                 for (int pl = 0; pl < PL::N; pl++) {
                     const uint32_t id = PL::id(pl);
-                    __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
-                           make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id)));
+                    if ((p.plane_mask >> pl) & 1u)
+                        __stcs(reinterpret_cast<uint4*>(base + pl * p.wp8),
+                               make_uint4(plane_word(b[0], id), plane_word(b[1], id), plane_word(b[2], id), plane_word(b[3], id)));
                 }
             }
         }
@@ -1195,7 +1201,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //   raw, jc69 : acc0 = 3 DIFF, acc1 = SAME
 //   k80       : acc0 = CS = SAME + ts, acc1 = X = SAME - ts, acc2 = tv
 //   tn93      : acc0 = L, acc1 = PP = SP + P1, acc2 = YY = SY + P2, acc3 = SP - P1, acc4 = SY - P2
-enum ResultKind { RES_U32 = 0, RES_F64 = 1, RES_U16 = 2, RES_COUNTS = 3 };
+enum ResultKind { RES_U32 = 0, RES_F64 = 1, RES_U16 = 2, RES_COUNTS = 3, RES_COUNTS16 = 4 };
 struct CombineParams {
     const uint8_t* acc;     // scratch: accumulator a's array starts at acc + acc_off[a] and holds acc_op[a] values,
     uint64_t acc_off[5];    // element (row, col) at (row - row0) * s_pitch + col - s_colbase (TcParams)
@@ -1249,6 +1255,10 @@ __device__ __forceinline__ void combine_pair(const CombineParams& p, uint32_t ro
         cnt = make_uint4((uint32_t)a0, (uint32_t)(a0 - sp - sy), (uint32_t)p1, (uint32_t)p2);  // {L, d, P1, P2}
     }
     if (p.result == RES_COUNTS) { reinterpret_cast<uint4*>(p.out)[idx] = cnt; return; }
+    if (p.result == RES_COUNTS16) {   // DG_OPT_RESULT_COUNTS: the host evaluates the f64 expressions with its libm
+        __stcs(reinterpret_cast<uint2*>(p.out) + idx, make_uint2(cnt.x | (cnt.y << 16), cnt.z | (cnt.w << 16)));
+        return;
+    }
     if (p.result == RES_U32) { __stcs(reinterpret_cast<uint32_t*>(p.out) + idx, cnt.x); return; }
     if (p.result == RES_U16) { __stcs(reinterpret_cast<unsigned short*>(p.out) + idx, (unsigned short)cnt.x); return; }
     double r;
@@ -1270,6 +1280,44 @@ __global__ void __launch_bounds__(256, 4) tc_combine_kernel(CombineParams p, uin
         for (uint32_t row = p.row0 + by; row < p.row_end; row += gy) {
             if (p.square && col <= row) continue;
             combine_pair(p, row, col);
+        }
+    }
+}
+
+// ---- DG_OPT_RESULT_U8: uint16 counts -> uint8 + overflow list ----------------------------------------------------------
+// ovf[0] = number of counts >= 255 met (may exceed cap: then the host takes the uint16 panel), entries {index, value}
+// from ovf[2].  One thread per 16 counts (two 128-bit loads, one 128-bit store); HBM-bound, 3 bytes per pair.
+__global__ void narrow_u8_kernel(const uint16_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t n, uint32_t* ovf, uint32_t cap) {
+    const uint64_t groups = n / 16;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= groups; g += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i0 = g * 16;
+        uint32_t w[8];
+        const uint32_t cnt = g < groups ? 16u : (uint32_t)(n - i0);   // the last group is the ragged tail
+        if (cnt == 0) break;
+        if (cnt == 16) {
+            const uint4 a = __ldcs(reinterpret_cast<const uint4*>(in + i0)), b = __ldcs(reinterpret_cast<const uint4*>(in + i0) + 1);
+            w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t lo = 2 * k < cnt ? in[i0 + 2 * k] : 0u, hi = 2 * k + 1 < cnt ? in[i0 + 2 * k + 1] : 0u;
+                w[k] = lo | (hi << 16);
+            }
+        }
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const uint32_t v = (w[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu;
+            if (v >= 255u) {
+                const uint32_t pos = atomicAdd(ovf, 1u);
+                if (pos < cap) { ovf[2 + 2 * pos] = (uint32_t)(i0 + k); ovf[3 + 2 * pos] = v; }
+            }
+            o[k >> 2] |= min(v, 255u) << ((k & 3) * 8);
+        }
+        if (cnt == 16) {
+            __stcs(reinterpret_cast<uint4*>(out + i0), make_uint4(o[0], o[1], o[2], o[3]));
+        } else {
+            for (uint32_t k = 0; k < cnt; k++) out[i0 + k] = (uint8_t)(o[k >> 2] >> ((k & 3) * 8));
         }
     }
 }

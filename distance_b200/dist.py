@@ -30,7 +30,9 @@ class Dist:
             os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29511")
-            td.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            import datetime
+            # a rank that dies (or a mismatched collective) must not hold the GPUs for NCCL's default 10 minutes
+            td.init_process_group(backend=backend, rank=self.rank, world_size=self.world, timeout=datetime.timedelta(seconds=240))
             self.pg = td
 
     def barrier(self):

@@ -85,8 +85,26 @@ typedef enum {
 typedef enum {
     DG_RESULT_U32 = 0, /* n / n_high: the count; FloatInt::Int, printed `{}`   (src/lib.rs:626-628) */
     DG_RESULT_F64 = 1, /* raw/jc69/k80/tn93: IEEE bits; FloatInt::Float `{:.12}` (src/lib.rs:630-632) */
-    DG_RESULT_U16 = 2  /* n / n_high with DG_OPT_RESULT_U16: the same count in 16 bits (halves the D2H bytes) */
+    DG_RESULT_U16 = 2, /* n / n_high with DG_OPT_RESULT_U16: the same count in 16 bits (halves the D2H bytes) */
+    DG_RESULT_U8 = 3   /* ABI 2, n / n_high with DG_OPT_RESULT_U8: the count in 8 bits; 255 = "255 or more: look the pair up in
+                          dg_panel.overflow" (closely related genomes differ at a few dozen sites: a quarter of the uint32 bytes) */
 } dg_result_kind;
+
+/* DG_RESULT_COUNTS16 (= 4, ABI 2; DG_OPT_RESULT_COUNTS): raw / jc69 / k80 / tn93 panels of resident runs and sessions hold,
+ * per pair, the four uint16 counts the distance is a function of instead of the f64 itself (same 8 bytes):
+ *   raw, jc69 : { n = #different, same, 0, 0 }                       d = n + same         (src/measures.rs:56-77)
+ *   k80       : { same, ts + tv, tv, 0 }                             L = same + ts + tv   (src/measures.rs:80-113)
+ *   tn93      : { count_L, count_d, count_P1, count_P2 }                                  (src/measures.rs:156-175)
+ * A host that evaluates measures.rs's f64 expressions on them with its own libm (Rust's f64::ln is the platform's log)
+ * prints text that is byte-identical to the reference's; the device's fused f64 epilogue (CUDA log: <= 1 ulp off) stays
+ * the default.  Streamed batches, the LOP3 engine and widths above 65,535 always deliver DG_RESULT_F64. */
+#define DG_RESULT_COUNTS16 4
+
+/* DG_RESULT_U8 panels: the pairs whose count does not fit 8 bits, in no particular order. */
+typedef struct {
+    uint32_t index; /* position in dg_panel.data */
+    uint32_t value; /* the count */
+} dg_overflow;
 
 typedef enum {
     DG_MODE_SQUARE = 0, /* one alignment, pairs i<j row-major: generate_pairs_square    src/lib.rs:502-547 */
@@ -108,7 +126,9 @@ typedef struct {
     uint64_t row_end;    /* one past the last major row */
     uint64_t n_cols;     /* RECT/STREAM: results per row; SQUARE: n (row i has n-1-i results) */
     uint64_t n_results;  /* total results in `data` */
-    const void *data;    /* uint32_t / double / uint16_t [n_results] per result_kind; pinned host memory */
+    const void *data;    /* uint32_t / double / uint16_t / uint8_t [n_results] per result_kind; pinned host memory */
+    const dg_overflow *overflow; /* ABI 2: DG_RESULT_U8 only, else NULL */
+    uint64_t n_overflow;
 } dg_panel;
 
 /* Return 0 to continue, non-zero to abort the run (-> DG_ERR_SINK). */
@@ -130,6 +150,13 @@ typedef struct dg_ctx dg_ctx;
                                 the MAC rate).  Set it before dg_load_resident: it decides which operands are built. */
 #define DG_OPT_RESULT_U16 5  /* 0/1: deliver n / n_high panels as uint16_t (DG_RESULT_U16).  A count never exceeds
                                 the width, so this is lossless for width <= 65535 (else DG_ERR_INVALID_ARG). */
+
+#define DG_OPT_RESULT_U8 9   /* 0/1: deliver n / n_high panels of dg_run_* and the dg_square_* / dg_rect_* sessions as uint8_t
+                                (DG_RESULT_U8) with an overflow list for the counts >= 255.  A panel with more than 16,384 such
+                                pairs arrives as DG_RESULT_U16 instead (check dg_panel.result_kind per panel).  Needs width <= 65535. */
+
+#define DG_OPT_RESULT_COUNTS 10 /* 0/1: raw / jc69 / k80 / tn93 panels carry DG_RESULT_COUNTS16 tuples where possible (check
+                                   dg_panel.result_kind per panel) */
 
 #define DG_OPT_PIPE_PANELS 6 /* dg_square_* sessions: how many result panels (per part) the triangle is cut into
                                 (default 24; smaller panels start the D2H stream earlier, larger ones fill the SMs better) */

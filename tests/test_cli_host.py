@@ -258,3 +258,32 @@ def test_parsers_fuzz_against_sequential_reader(tmp_path):
         p = subprocess.run([CLI, "--selftest-stream", str(f), str(width), str(batch), str(rnd.choice([1, 4]))],
                            capture_output=True, env=env, timeout=60)
         assert p.returncode == 0 and b"identical" in p.stdout, (case, batch, p.stdout, p.stderr)
+
+
+def test_fasta_tokenisation_choices(tmp_path):
+    """The cases tests/golden/README.md lists as parity-unpinned against rust-bio: each documented choice, checked on both
+    readers (`--selftest-parse` runs the parallel loader and the sequential reader and reports records / width / error)."""
+    recs = [(f"r{i}", "ACGTACGTAC") for i in range(6)]
+    out = _selftest_parse(tmp_path, _fasta(recs))
+    assert "records 6 width 10" in out
+    # '>' alone with sequence lines behind it is a record with the empty id
+    out = _selftest_parse(tmp_path, _fasta(recs[:2]) + ">\nACGTACGTAC\n" + _fasta(recs[2:]))
+    assert "records 7 width 10" in out
+    # '>' alone with nothing behind it ends the iteration: the records after it are never read
+    out = _selftest_parse(tmp_path, _fasta(recs[:2]) + ">\n\n" + _fasta(recs[2:]))
+    assert "records 2 width 10" in out
+    # header: the id ends at the first blank, the description is dropped; CRLF and trailing blanks are trimmed
+    out = _selftest_parse(tmp_path, ">a some text\r\nACGTA \t\r\nCGTAC\r\n>b\r\nACGTACGTAC\r\n")
+    assert "records 2 width 10" in out
+    # a blank line inside a record adds nothing
+    out = _selftest_parse(tmp_path, ">a\nACGTA\n\nCGTAC\n>b\nACGTACGTAC\n\n\n")
+    assert "records 2 width 10" in out
+    # blank line before the first '>'
+    out = _selftest_parse(tmp_path, "\n" + _fasta(recs))
+    assert "Expected > at record start." in out
+    # an inner blank is a sequence byte: invalid nucleotide
+    out = _selftest_parse(tmp_path, ">a\nACGTA CGTA\n")
+    assert "Invalid nucleotide character in record 'a': ' '" in out
+    # deviation from str::trim_end: U+00A0 at a line end is not trimmed, it is reported (as its first UTF-8 byte, Latin-1)
+    out = _selftest_parse(tmp_path, ">a\nACGTACGTAC \n")
+    assert "Invalid nucleotide character in record 'a'" in out

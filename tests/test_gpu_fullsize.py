@@ -274,3 +274,72 @@ def test_nibble_zero_is_reported_as_invalid(dg):
             e.load(0, nib, input_kind=api.DG_INPUT_NIBBLE)
         assert ei.value.code == -4            # DG_ERR_INVALID_CODE
         assert e.invalid_site()[:2] == (17, 43)
+
+
+@pytest.mark.parametrize("engine", [1, 3])
+def test_u8_results_with_overflow_list(dg, oracle, engine):
+    """DG_OPT_RESULT_U8: n / n_high panels as uint8 with an overflow list for the counts >= 255 (resident run, pipelined
+    session, two files); a panel with more overflows than the list holds arrives as uint16.  Values identical either way."""
+    from distance_b200 import api, synth
+    width = 2000
+    near = synth.encode_ascii(synth.make_alignment(900, width=width, seed=12, ambiguity=True, mu=2e-2))   # counts ~ 80
+    rng = np.random.default_rng(8)
+    far = synth.random_codes(rng, 3, width, p_ambig=0.02)                                                    # counts ~ 1,400
+    codes = np.concatenate([near[:500], far, near[500:]])
+    want = oracle_run(oracle, "n_high", "square", codes)
+    assert (want >= 255).sum() > 1000 and (want == 255).sum() >= 0
+    kinds = set()
+    with dg.Engine("n_high", width) as e:
+        e.set_option(api.DG_OPT_ENGINE, engine)
+        e.set_option(api.DG_OPT_RESULT_U8, 1)
+        e.set_option(api.DG_OPT_PANEL_BYTES, 1 << 20)
+        e.load(0, codes)
+        got = e.run_square()
+        kinds |= {k for k in getattr(e, "last_kinds", [])}
+        check("n_high", got, want)
+        got, _ = e.square_pipelined(codes)
+        check("n_high", got, want)
+        e.load(1, codes[400:])
+        got, _ = e.rect_pipelined(codes[:400])
+        check("n_high", got, oracle_run(oracle, "n_high", "rect", codes[:400], codes[400:]))
+    # a saturated alignment: every count is large, every panel falls back to uint16
+    sat = synth.random_codes(rng, 700, width, p_ambig=0.01)
+    with dg.Engine("n", width) as e:
+        e.set_option(api.DG_OPT_ENGINE, engine)
+        e.set_option(api.DG_OPT_RESULT_U8, 1)
+        e.load(0, sat)
+        seen = []
+
+        def sink(user, pp):
+            seen.append(int(pp.contents.result_kind))
+            return 0
+
+        e._check(e.L.dg_run_square(e.h, api.SINK_FN(sink), None, 0))
+        assert seen and all(k == api.DG_RESULT_U16 for k in seen)
+        check("n", e.run_square(), oracle_run(oracle, "n", "square", sat))
+
+
+@pytest.mark.parametrize("measure", ["raw", "jc69", "k80", "tn93"])
+def test_count_tuples_instead_of_f64(dg, oracle, measure):
+    """DG_OPT_RESULT_COUNTS: float measures deliver the integer counts (DG_RESULT_COUNTS16) the host evaluates with its own
+    libm; they equal the debug counts of the same engine, and the reference's expressions on them give the oracle's values
+    bit for bit (raw is checked here; the C++ host's text for jc69 / k80 / tn93 is compared in test_cli_gpu.py)."""
+    from distance_b200 import api, synth
+    rng = np.random.default_rng(44)
+    n, width = 700, 1500
+    codes = synth.random_codes(rng, n, width, p_ambig=0.1)
+    codes[:300] = synth.encode_ascii(synth.make_alignment(300, width=width, seed=3, ambiguity=True, mu=1e-2))
+    with dg.Engine(measure, width) as e:
+        e.set_option(api.DG_OPT_RESULT_COUNTS, 1)
+        e.set_option(api.DG_OPT_PANEL_BYTES, 1 << 20)
+        e.load(0, codes)
+        got = e.run_square_counts()
+        dbg = e.debug_counts(0, 0)
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(got.astype(np.uint32), dbg[iu])
+    if measure == "raw":
+        want = oracle_run(oracle, "raw", "square", codes)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mine = got[:, 0].astype(np.float64) / (got[:, 0].astype(np.float64) + got[:, 1].astype(np.float64))
+        assert np.array_equal(mine.view(np.uint64)[~np.isnan(want)], want.view(np.uint64)[~np.isnan(want)])
+        assert np.array_equal(np.isnan(mine), np.isnan(want))
