@@ -331,15 +331,20 @@ def pinned_copy(api, a):
 
 def pinned_nibbles(api, synth, asc):
     """ASCII alignment -> DG_INPUT_NIBBLE rows in pinned memory (what a parser that packs while it validates hands over),
-    in row blocks so that a 100,000-record alignment needs no multi-GB temporaries."""
+    in row blocks on a few threads so that a 100,000-record alignment needs neither multi-GB temporaries nor 20 s."""
+    from concurrent.futures import ThreadPoolExecutor
     n, w = asc.shape
     nlut = (synth.ascii_lut() >> 4).astype(np.uint8)
     out = api.pinned_array((n, (w + 1) // 2), np.uint8)
-    for r0 in range(0, n, 4096):
-        t = nlut[asc[r0:r0 + 4096]]
+
+    def block(r0):
+        t = nlut[asc[r0:r0 + 2048]]
         if w % 2:
             t = np.concatenate([t, np.full((t.shape[0], 1), 15, np.uint8)], axis=1)
         np.bitwise_or(t[:, 0::2], t[:, 1::2] << 4, out=out[r0:r0 + t.shape[0]])
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        list(ex.map(block, range(0, n, 2048)))
     return out
 
 
@@ -706,28 +711,45 @@ def run_ours(args):
     if world > 1:
         import torch
         import torch.distributed as td
-        # rank r owns records [r*per, (r+1)*per): one pinned host slice, one device slice, ONE all-gather per step
-        per = (n + world - 1) // world
-        lo_r, hi_r = min(n, rank * per), min(n, (rank + 1) * per)
-        host_slice = torch.full((per, NIBW), 255, dtype=torch.uint8).pin_memory()
-        host_slice[:hi_r - lo_r] = torch.from_numpy(np.ascontiguousarray(nib[lo_r:hi_r]))
-        dev_slice = torch.empty((per, NIBW), dtype=torch.uint8, device=d.device)
-        gathered = torch.empty((world * per, NIBW), dtype=torch.uint8, device=d.device)
+        # The session takes its chunks highest records first, so the alignment is cut into BANDS of whole chunks, top down;
+        # every rank uploads 1/N of each band from pinned host memory over its own PCIe link and one NCCL all-gather per
+        # band (NVLink) completes it on every GPU.  No host synchronisation: a CUDA event behind each all-gather is handed
+        # to dg_square_push (ready_event), so band b + 1 is uploaded and gathered while the tiles of band b run.
+        eng.square_begin(n, e2e_cb, rank, world, input_kind=api.DG_INPUT_NIBBLE)
+        chunks = eng.square_plan()                       # [(lo, hi)] in push order (descending)
+        for lo, hi in chunks:
+            eng.square_push(pinned_nib.ctypes.data + lo * NIBW, -1, lo, hi)   # finish this planning session (a warm-up step)
+        eng.square_end()
+        n_bands = max(1, min(args.e2e_bands, len(chunks)))
+        per_band = -(-len(chunks) // n_bands)
+        bands = []
+        for b0 in range(0, len(chunks), per_band):
+            grp = chunks[b0:b0 + per_band]
+            blo, bhi = grp[-1][0], grp[0][1]             # records [blo, bhi)
+            pb = -(-(bhi - blo) // world)                # records of one rank's piece
+            plo, phi = min(bhi, blo + rank * pb), min(bhi, blo + (rank + 1) * pb)
+            host_piece = torch.full((pb, NIBW), 255, dtype=torch.uint8).pin_memory()
+            host_piece[:phi - plo] = torch.from_numpy(np.ascontiguousarray(nib[plo:phi]))
+            bands.append({"chunks": grp, "blo": blo, "host": host_piece,
+                          "dev": torch.empty((pb, NIBW), dtype=torch.uint8, device=d.device),
+                          "gathered": torch.empty((world * pb, NIBW), dtype=torch.uint8, device=d.device),
+                          "ev": torch.cuda.Event()})
+        in_stream = torch.cuda.Stream(device=d.device)
 
         def e2e_step():
             e2e_state["n"] = 0
-            dev_slice.copy_(host_slice, non_blocking=True)          # 1/N of the code bytes over this rank's PCIe link
-            td.all_gather_into_tensor(gathered, dev_slice)          # the rest over NVLink
-            torch.cuda.synchronize()
-            # the session takes the chunks from the gathered device buffer (device-to-device copies): packing, tiles and
-            # the D2H of finished panels overlap as in the single-GPU path
+            with torch.cuda.stream(in_stream):
+                for bd in bands:
+                    bd["dev"].copy_(bd["host"], non_blocking=True)        # 1/N of the band over this rank's PCIe link
+                    td.all_gather_into_tensor(bd["gathered"], bd["dev"])  # the rest over NVLink
+                    bd["ev"].record(in_stream)
             eng.square_begin(n, e2e_cb, rank, world, input_kind=api.DG_INPUT_NIBBLE)
-            base = gathered.data_ptr()
-            while True:
-                lo, hi = eng.square_next()
-                if hi == lo:
-                    break
-                eng.square_push(base + lo * NIBW, d.local_rank, lo, hi)
+            for bd in bands:
+                base = bd["gathered"].data_ptr()
+                for lo, hi in bd["chunks"]:
+                    lo2, hi2 = eng.square_next()
+                    assert (lo2, hi2) == (lo, hi)
+                    eng.square_push(base + (lo - bd["blo"]) * NIBW, d.local_rank, lo, hi, ready_event=bd["ev"].cuda_event)
             eng.square_end()
             return e2e_state["n"]
     else:
@@ -910,8 +932,10 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(n * NIBW),
                     "input_kind": "DG_INPUT_NIBBLE: two sites per byte (the possibility half of the Paradis code), packed by the host before "
                                   "the timed region like a parser would; unpacked to code bytes on the device",
-                    "input_path": ("every rank uploads 1/N of the code bytes from pinned host memory, one NCCL all-gather over NVLink, then the "
-                                   "pipelined session (dg_square_*) takes its chunks from the gathered device buffer; panels in completion order")
+                    "input_path": ("the alignment goes up in %d bands of chunks, highest records first: every rank uploads 1/N of a band from pinned "
+                                   "host memory, one NCCL all-gather over NVLink completes it on every GPU, a CUDA event behind it releases the band's "
+                                   "chunks to the pipelined session (dg_square_push ready_event): no host synchronisation; panels in completion order"
+                                   % args.e2e_bands)
                     if world > 1 else "pipelined session (dg_run_square_host) from pinned host memory: upload, tiles and D2H overlap; "
                                       "panels reach the sink in completion order (descending rows)",
                     "in_order_ms_per_step": e2e_inorder_ms,
@@ -962,6 +986,7 @@ def main():
     ap.add_argument("--cfg-e2e-steps", type=int, default=2, help="e2e steps per extra config")
     ap.add_argument("--stream-records", type=int, default=1000000, help="config 4: streamed records per step (whole job)")
     ap.add_argument("--n5", type=int, default=100000, help="config 5: records of the all-vs-all")
+    ap.add_argument("--e2e-bands", type=int, default=4, help="N > 1: all-gathers per e2e step (bands of upload chunks, top down)")
     ap.add_argument("--sustained-s", type=float, default=3.0, help="seconds of back-to-back steps for the `sustained` record (0 = skip)")
     args = ap.parse_args()
     global MEASURE, WORKLOAD

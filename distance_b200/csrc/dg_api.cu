@@ -256,7 +256,7 @@ struct dg_ctx {
     void* sq_user = nullptr;
     std::vector<InFlight> sq_queue;
     double sq_t0 = 0;
-    int pipe_panels = 24;              // DG_OPT_PIPE_PANELS
+    int pipe_panels = 8;               // DG_OPT_PIPE_PANELS
     uint64_t pipe_chunk_bytes = 0;     // DG_OPT_PIPE_CHUNK_BYTES (0 = automatic)
     bool repack_overlap = true;        // DG_OPT_REPACK_OVERLAP
     bool sq_trace = false;
@@ -958,11 +958,16 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
         per = std::max<uint64_t>(quantum, per / quantum * quantum);
         uint64_t best_rows = per;
         if (r + per < rows_major) {
-            double best_fill = -1;
-            for (uint64_t cand = per; cand >= quantum && cand * 2 >= per; cand -= quantum) {
-                const uint64_t live = live_pair_tiles(mode, r, r + cand, n_cols, tn) * items;
-                const double fill = (double)live / (double)((live + SLOTS - 1) / SLOTS * SLOTS);
-                if (fill > best_fill + 1e-9) { best_fill = fill; best_rows = cand; }
+            // A panel of only a few rounds loses a large share of its last one (84 tiles = 1.14 rounds of 74 pairs run at 57 %),
+            // so small budgets may grow up to twice their size for a fuller last round (a small penalty keeps ties small).
+            const uint64_t live_per = live_pair_tiles(mode, r, r + per, n_cols, tn) * items;
+            const uint64_t hi = live_per < 8 * SLOTS ? std::min<uint64_t>(2 * per, (uint64_t)tm * 32768 / quantum * quantum) : per;
+            double best_score = -1;
+            for (uint64_t cand = hi; cand >= quantum && cand * 2 >= per; cand -= quantum) {
+                const uint64_t live = live_pair_tiles(mode, r, std::min(rows_major, r + cand), n_cols, tn) * items;
+                const double fill = live ? (double)live / (double)((live + SLOTS - 1) / SLOTS * SLOTS) : 0.0;
+                const double score = fill - (cand > per ? 0.04 * (double)(cand - per) / (double)per : 0.0);
+                if (score > best_score + 1e-9) { best_score = score; best_rows = cand; }
                 if (cand == quantum) break;
             }
         }

@@ -159,7 +159,7 @@ typedef struct dg_ctx dg_ctx;
                                    dg_panel.result_kind per panel) */
 
 #define DG_OPT_PIPE_PANELS 6 /* dg_square_* sessions: how many result panels (per part) the triangle is cut into
-                                (default 24; smaller panels start the D2H stream earlier, larger ones fill the SMs better) */
+                                (default 8; smaller panels start the D2H stream earlier, larger ones fill whole rounds of the CTA pairs better) */
 #define DG_OPT_PIPE_CHUNK_BYTES 7 /* dg_square_* sessions: target bytes of one upload chunk (0 = automatic:
                                      max(24 MiB, alignment bytes / 40)); chunks are whole multiples of 128 records */
 #define DG_OPT_REPACK_OVERLAP 8 /* 0/1 (default 1): kernel-only square runs with DG_RUN_REPACK re-pack the operand planes

@@ -108,3 +108,22 @@ def test_pack_nibbles_layout():
     nib = api.pack_nibbles(codes)
     assert nib.shape == (2, 3)
     assert nib.tolist() == [[0x48, 0x12, 0xFC], [0xFF, 0x7F, 0xF3]]
+
+
+def test_small_panels_fill_whole_rounds_of_the_cta_pairs():
+    """The pipelined session cuts the triangle into a dozen panels; each is ONE persistent launch over 74 CTA pairs, so a
+    panel of 84 tiles (1.14 rounds) would run at 57 %.  The planner grows small panels up to twice their budget for a
+    fuller last round: >= 90 % of the slots of all rounds are busy for config 2's session-sized panels."""
+    from distance_b200 import api
+    n = 20000
+    total_bytes = n * (n - 1) // 2 * 4
+    plan = api.plan_panels("n_high", api.DG_MODE_SQUARE, n, n, total_bytes // 8)
+    assert sum(p[2] for p in plan) == n * (n - 1) // 2
+
+    def live(r0, r1):   # 512 x 240 tiles right of the diagonal
+        blocks = (n + 239) // 240
+        return sum(max(0, blocks - (rs + 1) // 240) for rs in range(r0, r1, 512))
+
+    used = sum(live(a, b) for a, b, _ in plan)
+    slots = sum(-(-live(a, b) // 74) * 74 for a, b, _ in plan)
+    assert used / slots >= 0.90, (used / slots, [b - a for a, b, _ in plan])

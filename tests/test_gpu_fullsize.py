@@ -330,6 +330,7 @@ def test_count_tuples_instead_of_f64(dg, oracle, measure):
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     codes[:300] = synth.encode_ascii(synth.make_alignment(300, width=width, seed=3, ambiguity=True, mu=1e-2))
     with dg.Engine(measure, width) as e:
+        e.set_option(api.DG_OPT_ENGINE, 3)            # (auto would send this ambiguity-heavy input to the LOP3 tiles: f64 panels)
         e.set_option(api.DG_OPT_RESULT_COUNTS, 1)
         e.set_option(api.DG_OPT_PANEL_BYTES, 1 << 20)
         e.load(0, codes)

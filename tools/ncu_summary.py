@@ -19,6 +19,8 @@ KEYS = [
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe % (IMAD.IADD)"),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
     ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64 pipe %"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue slots busy %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
