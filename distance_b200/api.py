@@ -25,7 +25,7 @@ DG_OPT_RESULT_U8 = 9
 DG_OPT_RESULT_COUNTS = 10
 DG_RESULT_U8 = 3
 DG_RESULT_COUNTS16 = 4
-DG_SQUARE_LOOKAHEAD = 3
+DG_SQUARE_LOOKAHEAD = 8
 DG_RESULT_U32, DG_RESULT_F64, DG_RESULT_U16 = 0, 1, 2
 DG_ERR = {0: "DG_OK", -1: "DG_ERR_INVALID_ARG", -2: "DG_ERR_CUDA", -3: "DG_ERR_STATE",
           -4: "DG_ERR_INVALID_CODE", -5: "DG_ERR_SINK", -6: "DG_ERR_NOMEM"}

@@ -743,6 +743,10 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
     for (uint32_t a = 0; a < tp.nacc; a++) { tp.acc_off[a] = plan.off[a]; tp.acc_op[a] = plan.op[a]; }
     tp.s_pitch = plan.s_pitch; tp.s_colbase = plan.s_colbase;
     tp.ksplit = std::max<uint32_t>(1, plan.ksplit);
+    static const bool l2_hint = std::getenv("DG_TC_L2_HINT") != nullptr;
+    tp.l2_evict_last = l2_hint ? 1u : 0u;
+    static const uint32_t raster_env = std::getenv("DG_TC_RASTER") ? (uint32_t)std::max(1, std::atoi(std::getenv("DG_TC_RASTER"))) : 0u;
+    tp.raster_g = raster_env ? raster_env : tc::RASTER_G;
     if (plan.s_pitch && (plan.s_pitch != tp.gx * tp.tn || plan.s_colbase != tp.col_block0 * tp.tn))
         fail(DG_ERR_STATE, "internal: scratch geometry does not match the launch's tiles");
     tp.probe = d.clk_probe;
@@ -763,8 +767,8 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         }
         const uint32_t rows_per_block = (uint32_t)(tc::TM * cl * mt);
         uint32_t n_live = 0;
-        for (uint32_t band0 = 0; band0 < tp.gy; band0 += tc::RASTER_G) {
-            const uint32_t gb = std::min<uint32_t>(tc::RASTER_G, tp.gy - band0);
+        for (uint32_t band0 = 0; band0 < tp.gy; band0 += tp.raster_g) {
+            const uint32_t gb = std::min<uint32_t>(tp.raster_g, tp.gy - band0);
             for (uint32_t bx = 0; bx < tp.gx; bx++)
                 for (uint32_t by = band0; by < band0 + gb; by++) {
                     const uint64_t rowS0 = (uint64_t)tp.row0 + (uint64_t)by * rows_per_block;
@@ -775,7 +779,7 @@ void launch_tc_gemm(dg_ctx* c, Device& d, const PlaneSet& A, const PlaneSet& B, 
         }
         if (n_live == 0) return;
         if (tiles_on_device) {   // sessions: no small H2D copy behind the bulk uploads on the copy engine
-            tc::build_tile_list_kernel<<<1, 1024, 0, st>>>(tp.gx, tp.gy, tc::RASTER_G, tp.row0, tp.row_end, rows_per_block,
+            tc::build_tile_list_kernel<<<1, 1024, 0, st>>>(tp.gx, tp.gy, tp.raster_g, tp.row0, tp.row_end, rows_per_block,
                                                           tp.col_block0, tp.tn, ws->d_tiles);
             CUDA_CHECK(cudaGetLastError());
         } else {
@@ -961,7 +965,12 @@ std::vector<Panel> make_panels(size_t panel_bytes, size_t elem_bytes, int mode, 
             // A panel of only a few rounds loses a large share of its last one (84 tiles = 1.14 rounds of 74 pairs run at 57 %),
             // so small budgets may grow up to twice their size for a fuller last round (a small penalty keeps ties small).
             const uint64_t live_per = live_pair_tiles(mode, r, r + per, n_cols, tn) * items;
-            const uint64_t hi = live_per < 8 * SLOTS ? std::min<uint64_t>(2 * per, (uint64_t)tm * 32768 / quantum * quantum) : per;
+            // (launches of less than half a round are split along K instead: choose_ksplit); panels of up to 40 rounds may still
+            // grow by a quarter: 17.03 rounds (config 3: 1,260 work items) run as 18, 19.9 as 20.
+            const uint64_t cap = (uint64_t)tm * 32768 / quantum * quantum;
+            uint64_t hi = per;
+            if (live_per >= SLOTS / 2 && live_per < 3 * SLOTS) hi = std::min<uint64_t>(2 * per, cap);
+            else if (live_per >= 3 * SLOTS && live_per < 40 * SLOTS) hi = std::min<uint64_t>(per + std::max<uint64_t>(quantum, per / 4 / quantum * quantum), cap);
             double best_score = -1;
             for (uint64_t cand = hi; cand >= quantum && cand * 2 >= per; cand -= quantum) {
                 const uint64_t live = live_pair_tiles(mode, r, std::min(rows_major, r + cand), n_cols, tn) * items;
@@ -1050,7 +1059,7 @@ void ensure_nib(dg_ctx* c, PlaneSet& s, uint64_t n) {
 }
 void enqueue_nibble_unpack(dg_ctx* c, const uint8_t* d_nib, uint8_t* d_codes, uint64_t n, cudaStream_t st) {
     const uint64_t wb = input_stride(c, DG_INPUT_NIBBLE);
-    const uint64_t units = n * ((wb + 3) / 4);
+    const uint64_t units = n * ((wb + 7) / 8);
     const unsigned grid = (unsigned)std::min<uint64_t>((units + 255) / 256, 148 * 32);
     tc::nibble_unpack_kernel<<<std::max(1u, grid), 256, 0, st>>>(d_nib, d_codes, n, c->width, wb);
     CUDA_CHECK(cudaGetLastError());

@@ -113,6 +113,17 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y) : "memory");
 }
+// the same with an L2 cache policy (createpolicy): operand tiles are re-read by the other tiles of the raster band
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(x), "r"(y), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
 // arrive on the barrier at this offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
     asm volatile(
@@ -504,25 +515,54 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
 // ---- DG_INPUT_NIBBLE: two sites per byte -> Paradis bytes -------------------------------------------------------------
 // byte = nibble << 4 | (8 if exactly one possibility bit: the base is known); nibble 0 -> 0 (invalid, reported by the
 // pack kernels).  One thread per 4 input bytes (8 sites); HBM-bound and tiny next to the PCIe time it saves.
+__device__ __forceinline__ uint32_t nib_to_codes2(uint32_t b) {   // one nibble byte -> two Paradis bytes (low nibble first)
+    const uint32_t m0 = b & 15u, m1 = (b >> 4) & 15u;
+    const uint32_t c0 = (m0 << 4) | (__popc(m0) == 1 ? 8u : 0u), c1 = (m1 << 4) | (__popc(m1) == 1 ? 8u : 0u);
+    return c0 | (c1 << 8);
+}
+// One thread per 8 input bytes (16 sites).  Output rows are `width` bytes apart (29,903: no alignment), so a thread writes
+// the bytes up to its first 4-byte boundary singly, then three aligned words cut out of its 16 bytes with funnel shifts,
+// then the rest singly: 7 stores instead of 16.
 __global__ void nibble_unpack_kernel(const uint8_t* __restrict__ nib, uint8_t* __restrict__ codes, uint64_t n, uint64_t width,
                                      uint64_t wb) {
-    const uint64_t per_row = (wb + 3) / 4;
+    const uint64_t per_row = (wb + 7) / 8;
     const uint64_t total = n * per_row;
     for (uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; u < total; u += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t r = u / per_row, k0 = (u - r * per_row) * 4;
+        const uint64_t r = u / per_row, k0 = (u - r * per_row) * 8;
         const uint8_t* src = nib + r * wb + k0;
         uint8_t* dst = codes + r * width + 2 * k0;
+        const uint32_t n_in = (uint32_t)min((uint64_t)8, wb - k0);
+        const uint32_t n_out = (uint32_t)min((uint64_t)16, width - 2 * k0);
+        uint32_t w[5];
+        if (n_in == 8 && (reinterpret_cast<uintptr_t>(src) & 7) == 0) {
+            const uint2 v = __ldcs(reinterpret_cast<const uint2*>(src));
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (k0 + k >= wb) break;
-            const uint32_t b = src[k];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const uint64_t site = 2 * (k0 + k) + h;
-                if (site >= width) break;
-                const uint32_t m = (b >> (4 * h)) & 15u;
-                dst[2 * k + h] = (uint8_t)((m << 4) | (__popc(m) == 1 ? 8u : 0u));
+            for (int k = 0; k < 4; k++) {
+                const uint32_t x = k < 2 ? v.x : v.y;
+                const uint32_t b0 = (x >> (16 * (k & 1))) & 0xFFu, b1 = (x >> (16 * (k & 1) + 8)) & 0xFFu;
+                w[k] = nib_to_codes2(b0) | (nib_to_codes2(b1) << 16);
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t b0 = 2 * k < (int)n_in ? src[2 * k] : 0xFFu, b1 = 2 * k + 1 < (int)n_in ? src[2 * k + 1] : 0xFFu;
+                w[k] = nib_to_codes2(b0) | (nib_to_codes2(b1) << 16);
+            }
+        }
+        w[4] = 0;
+        const uint32_t head = (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+        if (n_out == 16) {
+            for (uint32_t i = 0; i < head; i++) dst[i] = (uint8_t)(w[0] >> (8 * i));
+            uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+#pragma unroll
+            for (int j = 0; j < 3; j++) dw[j] = __funnelshift_r(w[j], w[j + 1], 8 * head);
+            if (head == 0) {
+                dw[3] = w[3];
+            } else {
+                for (uint32_t i = head + 12; i < 16; i++) dst[i] = (uint8_t)(w[3] >> (8 * (i - 12)));
+            }
+        } else {   // the last sites of the row
+            for (uint32_t i = 0; i < n_out; i++) dst[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
         }
     }
 }
@@ -605,33 +645,82 @@ __global__ void publish_invalid_kernel(const unsigned long long* d_inv, unsigned
     *h_inv = *d_inv;
     __threadfence_system();
 }
-__global__ void pp_scan_chunk_kernel(const uint32_t* site_cnt, uint32_t* cum_cnt, uint64_t width, uint32_t* off,
-                                     uint32_t* total, uint32_t* h_total, double* h_work, const unsigned long long* d_inv,
-                                     unsigned long long* h_inv) {
-    __shared__ uint32_t part[1024];
-    __shared__ double wpart[1024];
+// One block of 1,024 threads; thread t owns the sites [t * per, (t + 1) * per).  This kernel sits on the critical path of
+// every upload chunk of a session (pack -> scan -> the host sizes the entry buffer), so it is written for latency: the
+// site counts are fetched in batches of 8 independent loads (round 1 walked them one dependent load at a time: ~100 us
+// per chunk, as long as the chunk's PCIe transfer) and the 1,024 partial sums are scanned with warp shuffles.
+__global__ void __launch_bounds__(1024) pp_scan_chunk_kernel(const uint32_t* __restrict__ site_cnt, uint32_t* __restrict__ cum_cnt,
+                                                             uint64_t width, uint32_t* __restrict__ off, uint32_t* total,
+                                                             uint32_t* h_total, double* h_work, const unsigned long long* d_inv,
+                                                             unsigned long long* h_inv) {
+    __shared__ uint32_t wsum[32];
+    __shared__ double wwork[32];
+    __shared__ uint32_t s_base;
+    const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const uint64_t per = (width + 1023) / 1024;
-    const uint64_t b = min(width, threadIdx.x * per), e = min(width, b + per);
+    const uint64_t b = min(width, (uint64_t)t * per), e = min(width, b + per);
     uint32_t s = 0; double w = 0;
-    for (uint64_t i = b; i < e; i++) {
-        s += site_cnt[i];
-        const uint32_t cc = cum_cnt[i] + site_cnt[i];
-        cum_cnt[i] = cc;
-        w += (double)cc * cc;
+    for (uint64_t i0 = b; i0 < e; i0 += 8) {
+        uint32_t c[8], q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const bool ok = i0 + k < e;
+            c[k] = ok ? site_cnt[i0 + k] : 0u;
+            q[k] = ok ? cum_cnt[i0 + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (i0 + k < e) {
+                const uint32_t cc = q[k] + c[k];
+                cum_cnt[i0 + k] = cc;
+                s += c[k];
+                w += (double)cc * cc;
+            }
+        }
     }
-    part[threadIdx.x] = s; wpart[threadIdx.x] = w;
+    // exclusive scan of the 1,024 partial sums (and the sum of the work terms)
+    uint32_t incl = s; double wt = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+    if (lane == 31) wsum[warp] = incl;
+    if (lane == 0) wwork[warp] = wt;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = *total; double tw = 0;
-        off[0] = run;
-        for (int i = 0; i < 1024; i++) { const uint32_t t = part[i]; part[i] = run; run += t; tw += wpart[i]; }
-        *total = run;
-        *h_total = run; *h_work = tw; *h_inv = *d_inv;
-        __threadfence_system();
+    if (warp == 0) {
+        uint32_t v = wsum[lane]; double ww = wwork[lane];
+        uint32_t iv = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
+            if (lane >= (uint32_t)o) iv += u;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ww += __shfl_xor_sync(0xffffffffu, ww, o);
+        wsum[lane] = iv - v;   // exclusive prefix of the warps
+        if (lane == 31) {
+            const uint32_t base = *total;
+            s_base = base;
+            off[0] = base;
+            const uint32_t run = base + iv;
+            *total = run;
+            *h_total = run; *h_work = ww; *h_inv = *d_inv;
+            __threadfence_system();
+        }
     }
     __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (uint64_t i = b; i < e; i++) { off[1 + i] = run; run += site_cnt[i]; }
+    uint32_t run = s_base + wsum[warp] + (incl - s);
+    for (uint64_t i0 = b; i0 < e; i0 += 8) {
+        uint32_t c[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) c[k] = i0 + k < e ? site_cnt[i0 + k] : 0u;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (i0 + k < e) { off[1 + i0 + k] = run; run += c[k]; }
+    }
 }
 
 // DIFF is computed as sum_b U_b(q) V_b(t) = 3 [Sq, St disjoint] whenever at least one code is a known base or
@@ -811,6 +900,8 @@ struct TcParams {
     // 32-column chunk of every tile row starts 32-byte aligned and an epilogue lane stores its row's chunk straight from
     // registers with 128-bit stores).  s_pitch == 0: `out` holds the final n / n_high counts in the reference's order.
     uint32_t s_pitch, s_colbase;
+    uint32_t raster_g;        // row blocks per raster band (RASTER_G; DG_TC_RASTER overrides for experiments)
+    uint32_t l2_evict_last;   // DG_TC_L2_HINT (experiment): operand TMA loads carry an evict-last L2 policy
     uint32_t ksplit;       // >= 1: work items = accumulators x tiles x ksplit, item kc sums K blocks [kc, kc + 1) * KT / ksplit
     uint32_t stages;       // pipeline depth in use (<= STAGES; tuning knob)
     unsigned long long* probe;  // DG_CLOCK_PROBE (debug): [4] += SM clocks, [5] += ns of this launch (CTA 0); or NULL
@@ -827,9 +918,10 @@ __device__ __forceinline__ bool tile_live(const TcParams& p, uint32_t t, uint32_
         const uint32_t code = __ldg(p.tile_list + t);
         bx = code & 0xFFFFFu; by = code >> 20;
     } else {
-        const uint32_t band = t / (RASTER_G * p.gx), r = t - band * (RASTER_G * p.gx);
-        const uint32_t gb = min(RASTER_G, p.gy - band * RASTER_G);  // row blocks in this band
-        bx = r / gb; by = band * RASTER_G + (r - bx * gb);
+        const uint32_t G = p.raster_g;
+        const uint32_t band = t / (G * p.gx), r = t - band * (G * p.gx);
+        const uint32_t gb = min(G, p.gy - band * G);  // row blocks in this band
+        bx = r / gb; by = band * G + (r - bx * gb);
     }
     const uint32_t rowS0 = p.row0 + by * (TM * MT * CL);
     rowB0 = (p.col_block0 + bx) * p.tn;
@@ -1067,6 +1159,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint64_t policy = p.l2_evict_last ? l2_policy_evict_last() : 0ull;
             for (uint32_t w = cid; w < nwork; w += ncl) {
                 uint32_t a, t, k0, k1;
                 decode(w, a, t, k0, k1);
@@ -1080,6 +1173,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (PAIR) {
                         // the leader's barrier counts the bytes of both CTAs
                         if (rank == 0) mbar_arrive_expect_tx(full + stage, 2 * (MT * A_BYTES + BH_BYTES));
+                        if (p.l2_evict_last) {
+#pragma unroll
+                            for (int m = 0; m < MT; m++)
+                                tma_load_2d_pair_hint(sa + m * A_BYTES, &tmA, (int)(p.pa[a][pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage, policy);
+                            tma_load_2d_pair_hint(sa + MT * A_BYTES, &tmB, xb, (int)(rowB0 + rank * (TNX / 2)), full + stage, policy);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                            continue;
+                        }
 #pragma unroll
                         for (int m = 0; m < MT; m++)
                             tma_load_2d_pair(sa + m * A_BYTES, &tmA, (int)(p.pa[a][pr] * p.wp8 + sb * KB), (int)(rowA0 + m * TM), full + stage);

@@ -262,7 +262,7 @@ DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t 
  * nucleotide byte fails the push / end call that notices it (DG_ERR_INVALID_CODE) before any panel that depends on
  * it is delivered; dg_invalid_site then names the lowest (record, site) among the chunks seen so far, which need
  * not be the first in file order. */
-#define DG_SQUARE_LOOKAHEAD 3
+#define DG_SQUARE_LOOKAHEAD 8
 DG_API int dg_square_begin(dg_ctx *ctx, uint64_t n, int input_kind, const uint64_t *acgt_counts, uint32_t part,
                            uint32_t n_parts, dg_sink_fn sink, void *user);
 DG_API int dg_square_next(dg_ctx *ctx, uint64_t *lo, uint64_t *hi);
