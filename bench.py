@@ -371,10 +371,14 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
     eng.load(0, pa, input_kind=api.DG_INPUT_ASCII)
     if pb is not None:
         eng.load(1, pb, input_kind=api.DG_INPUT_ASCII)
+    n_rows, n_cols = a_asc.shape[0], (a_asc.shape[0] if b_asc is None else b_asc.shape[0])
+    if parts > 1:
+        # panels are dealt to the parts round-robin: cut the job into >= 4 panels per part so that the shares are even
+        total_bytes = (n_rows * (n_rows - 1) // 2 if b_asc is None else n_rows * n_cols) * (2 if is_int else 8)
+        eng.set_option(api.DG_OPT_PANEL_BYTES, int(max(8 << 20, min((128 << 20) if is_int else (256 << 20), total_bytes // (4 * parts)))))
     plan = eng.plan(mode)
     mine = [p for k, p in enumerate(plan) if k % parts == part]
     my_pairs = sum(p[2] for p in mine)
-    n_rows, n_cols = a_asc.shape[0], (a_asc.shape[0] if b_asc is None else b_asc.shape[0])
     # kernel-only
     for _ in range(2):
         eng.run_device_only(mode, part, parts, repack=True)
@@ -871,6 +875,10 @@ def run_ours(args):
             "traffic": peaks.get("tc_kernel_dram_bytes_per_launch"),
             "ops_per_pair_site": I8_OPS_PER_PAIR_SITE[MEASURE], "peak_source": src8,
             "frac_in_survey_units": ach / pk8 * 10.0 / I8_OPS_PER_PAIR_SITE[MEASURE],
+            # the same achieved rate against the hardware limit AT THE CLOCK THE KERNEL SAW (148 SMs x 16,384 fp4 / 8,192 int8 MAC
+            # per clock): the chip runs at its power cap, and the clock it settles at varies by several percent between runs
+            "frac_of_hw_peak_at_in_kernel_clock": (ach * 1e12 / (148 * (16384 if engine_id == 3 else 8192) * 2 * sm_mhz_burst * 1e6))
+            if sm_mhz_burst else None,
             "padded_frac": ach / pk8 * (math.ceil(WIDTH / 128) * 128) / WIDTH,
             "avg_launch_ms": count_launch_ms, "count_ms_per_step": count_ms_step,
             "note": "achieved = executed algorithmic tensor ops (4 MAC per pair-site: DIFF as a rank-4 bilinear form, "

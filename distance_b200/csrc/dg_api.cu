@@ -1598,7 +1598,9 @@ void sq_begin(dg_ctx* c, int mode, uint64_t n, int input_kind, const uint64_t* a
     // chunks: the same for every part (a multi-rank launcher broadcasts them): <= ~40 pieces of >= 24 MB, descending,
     // every boundary but n itself a multiple of ROW_ALIGN (the pack kernel zero-fills whole 128-row groups)
     const uint64_t target = c->pipe_chunk_bytes ? c->pipe_chunk_bytes : std::max<uint64_t>(24ull << 20, n * c->width / 40);
-    const uint64_t rows = std::max<uint64_t>(ROW_ALIGN, target / c->width / ROW_ALIGN * ROW_ALIGN);
+    // the target is bytes ON THE WIRE: nibble rows carry twice the records per chunk (the per-chunk unpack / pack / scan
+    // launches are what falls behind the copies once GEMM CTAs share the SMs: profiles/e2e_timeline_r02.md)
+    const uint64_t rows = std::max<uint64_t>(ROW_ALIGN, target / input_stride(c, input_kind) / ROW_ALIGN * ROW_ALIGN);
     c->sq_chunks.clear();
     if (rect) {
         for (uint64_t lo = 0; lo < n;) {   // ascending

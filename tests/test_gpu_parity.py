@@ -452,7 +452,7 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
     if ndev < 2:
         pytest.skip("needs >= 2 GPUs")
     rng = np.random.default_rng(21)
-    n, width = max(2100, 1100 * ndev), 300   # >= 2 panels of >= 512 rows per device
+    n, width = max(2100, 1100 * ndev), 300   # more panels (of >= 512 rows) than devices: some device takes two
     codes = synth.random_codes(rng, n, width, p_ambig=0.1)
     for measure in ("n_high", "tn93"):
         want = oracle_run(oracle, measure, "square", codes)
@@ -460,7 +460,7 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
             e.set_option(api.DG_OPT_PANEL_BYTES, 512 * n * (4 if measure == "n_high" else 8))
             e.load(0, codes)
             got = e.run_square()
-            assert len(e.last_panels) >= 2 * ndev
+            assert len(e.last_panels) >= ndev + 1   # (the planner may merge small panels for fuller launches)
             check(measure, got, want)
             loaded, streamed = codes[:40], codes[40:400]
             e.load(0, loaded)

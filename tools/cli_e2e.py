@@ -13,6 +13,7 @@ ap.add_argument("--n", type=int, default=20000)
 ap.add_argument("--measure", default="n_high")
 ap.add_argument("--dir", default="/dev/shm")
 ap.add_argument("--seed", type=int, default=20251018 + 2)
+ap.add_argument("--null-only", action="store_true", help="TSV to /dev/null only (large runs: the text would not fit a tmpfs)")
 ap.add_argument("--stream", type=int, default=0,
                 help="config 4 instead: -m k80 -i <1,000 resident records> -s <this many streamed records> (a pool of 20,000 records repeated)")
 a = ap.parse_args()
@@ -57,7 +58,7 @@ gen_s = time.time() - t0
 pairs = a.n * (a.n - 1) // 2
 out = {"n": a.n, "measure": a.measure, "pairs": pairs, "fasta_bytes": os.path.getsize(fa), "cores": os.cpu_count(), "runs": []}
 tsv = os.path.join(a.dir, "dg_cli_e2e.tsv")
-for sink in ("/dev/null", tsv):
+for sink in (("/dev/null",) if a.null_only else ("/dev/null", tsv)):
     for rep in range(2):
         env = dict(os.environ, DG_TRACE="1")
         t0 = time.time()
