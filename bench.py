@@ -377,7 +377,8 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
         total_bytes = (n_rows * (n_rows - 1) // 2 if b_asc is None else n_rows * n_cols) * (2 if is_int else 8)
         eng.set_option(api.DG_OPT_PANEL_BYTES, int(max(8 << 20, min((128 << 20) if is_int else (256 << 20), total_bytes // (4 * parts)))))
     plan = eng.plan(mode)
-    mine = [p for k, p in enumerate(plan) if k % parts == part]
+    from distance_b200 import dist as _dist
+    mine = _dist.my_panels(plan, part, parts)
     my_pairs = sum(p[2] for p in mine)
     # kernel-only
     for _ in range(2):
@@ -460,7 +461,7 @@ def config_stream(cfg_id, label, measure, d, args, dg, api, synth):
     rng = np.random.default_rng(1000 + cfg_id * 10 + rank)
     root = synth.make_root(WIDTH, 20251018 + 4)
     res_asc = spike(synth.make_alignment(1000, seed=20251018 + 4, ambiguity=True, root=root), rng)
-    batch = 4096
+    batch = 7168   # 14 row blocks x 5 column blocks x 3 accumulators = 210 work items = 2.84 rounds of the 74 CTA pairs (4,096: 1.62)
     pool_asc = spike(synth.make_alignment(2 * batch, seed=20251018 + 44 + rank, ambiguity=True, root=root), rng)
     pool_nib = api.pack_nibbles(lut[pool_asc])   # the streamed batches travel as DG_INPUT_NIBBLE rows (two sites per byte)
     nibw = pool_nib.shape[1]
@@ -615,7 +616,7 @@ def run_ours(args):
     eng.load(0, pinned)
     plan = eng.plan(api.DG_MODE_SQUARE)
     if world > 1:
-        # ranks own panels k % world == rank: pick the panel size (<= the default) whose largest share is smallest
+        # ranks own the panels dg_plan_parts deals them: pick the panel size (<= the default) whose largest share is smallest
         best = None
         for pct in range(100, 59, -4):
             pb = args.panel_bytes * pct // 100

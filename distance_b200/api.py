@@ -37,7 +37,7 @@ ABI_SYMBOLS = [
     "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end", "dg_debug_counts", "dg_debug_planes",
     "dg_get_timings", "dg_reset_timings", "dg_alloc_pinned", "dg_free_pinned", "dg_plan_panels", "dg_plan_ctx",
     "dg_square_begin", "dg_square_next", "dg_square_plan", "dg_square_push", "dg_square_end", "dg_run_square_host",
-    "dg_rect_begin", "dg_run_rect_host",
+    "dg_rect_begin", "dg_run_rect_host", "dg_plan_parts",
 ]
 
 
@@ -162,6 +162,8 @@ def load_library():
     L.dg_plan_panels.restype = C.c_int64
     L.dg_plan_ctx.argtypes = [vp, i32, vp, vp, vp, u64]
     L.dg_plan_ctx.restype = C.c_int64
+    L.dg_plan_parts.argtypes = [vp, u64, C.c_uint32, vp]
+    L.dg_plan_parts.restype = i32
     for name in ("dg_create", "dg_set_option", "dg_load_resident", "dg_load_resident_device", "dg_invalid_site", "dg_run_square",
                  "dg_run_rect", "dg_run_part", "dg_stream_begin", "dg_stream_push", "dg_stream_buffer", "dg_stream_end",
                  "dg_debug_counts", "dg_debug_planes", "dg_get_timings", "dg_reset_timings", "dg_square_begin",
@@ -208,6 +210,17 @@ def pack_nibbles(codes: np.ndarray) -> np.ndarray:
 
 def input_stride(width: int, input_kind: int) -> int:
     return (width + 1) // 2 if input_kind == DG_INPUT_NIBBLE else width
+
+
+def plan_parts(plan, n_parts: int):
+    """dg_plan_parts: the part that owns each panel of a plan [(row_begin, row_end, n_results)] (host arithmetic only)."""
+    L = load_library()
+    sizes = np.array([p[2] for p in plan], dtype=np.uint64)
+    out = np.zeros(max(len(plan), 1), dtype=np.uint32)
+    rc = L.dg_plan_parts(sizes.ctypes.data_as(C.c_void_p), len(plan), n_parts, out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        raise DistanceGpuError(rc, "dg_plan_parts")
+    return [int(x) for x in out[:len(plan)]]
 
 
 def pinned_array(shape, dtype) -> np.ndarray:

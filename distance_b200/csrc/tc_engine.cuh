@@ -1373,7 +1373,8 @@ __device__ __forceinline__ void combine_pair(const CombineParams& p, uint32_t ro
     __stcs(reinterpret_cast<double*>(p.out) + idx, r);
 }
 
-__global__ void __launch_bounds__(256, 4) tc_combine_kernel(CombineParams p, uint32_t gx, uint32_t gy) {
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) tc_combine_kernel(CombineParams p, uint32_t gx, uint32_t gy) {
     for (uint32_t vb = blockIdx.x; vb < gx * gy; vb += gridDim.x) {
         const uint32_t bx = vb % gx, by = vb / gx;
         const uint32_t col = p.col0 + bx * blockDim.x + threadIdx.x;

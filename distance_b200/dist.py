@@ -68,5 +68,10 @@ class Dist:
 
 
 def my_panels(plan, rank: int, world: int):
-    """The panels dg_run_part(part=rank, n_parts=world) processes: index % world == rank."""
-    return [p for k, p in enumerate(plan) if k % world == rank]
+    """The panels dg_run_part(part=rank, n_parts=world) processes: those dg_plan_parts assigns to `rank` (largest panels
+    first, each to the least-loaded part)."""
+    if world <= 1:
+        return list(plan)
+    from . import api
+    part_of = api.plan_parts(plan, world)
+    return [p for k, p in enumerate(plan) if part_of[k] == rank]

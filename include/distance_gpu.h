@@ -220,7 +220,7 @@ DG_API int dg_invalid_site(const dg_ctx *ctx, uint64_t *record, uint64_t *site, 
 DG_API int dg_run_square(dg_ctx *ctx, dg_sink_fn sink, void *user, uint32_t flags);
 /* Alignment 0 x alignment 1 (replaces load() with two inputs, src/lib.rs:401-409). */
 DG_API int dg_run_rect(dg_ctx *ctx, dg_sink_fn sink, void *user, uint32_t flags);
-/* Multi-process sharding: run only the panels whose index % n_parts == part (mode SQUARE or RECT).
+/* Multi-process sharding: run only the panels that dg_plan_parts assigns to `part` (mode SQUARE or RECT).
  * Panels are independent, so ranks need no collective; each rank's sink sees its own panels in
  * increasing order. */
 DG_API int dg_run_part(dg_ctx *ctx, int mode, uint32_t part, uint32_t n_parts, dg_sink_fn sink, void *user,
@@ -229,7 +229,7 @@ DG_API int dg_run_part(dg_ctx *ctx, int mode, uint32_t part, uint32_t n_parts, d
 /* The panel plan dg_run_square / dg_run_rect / dg_run_part follow, without touching a device (pure
  * host arithmetic; lets a multi-process launcher and CPU tests see the sharding).  mode SQUARE:
  * n_rows = n_cols = n.  Writes up to `cap` panels (row_begin, row_end, n_results) and returns the
- * total number of panels, or a negative DG_ERR_*.  Panel k belongs to part k % n_parts.  Assumes the default
+ * total number of panels, or a negative DG_ERR_*.  Which part owns panel k: dg_plan_parts.  Assumes the default
  * result width (uint32 / double); with DG_OPT_RESULT_U16 use dg_plan_ctx. */
 DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n_cols, uint64_t panel_bytes,
                               int tile_variant, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
@@ -237,6 +237,11 @@ DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n
 
 /* The same plan for THIS context: its loaded alignments, panel bytes, tile variant and result width
  * (uint16 panels hold twice the rows of uint32 ones).  Returns the number of panels or a negative DG_ERR_*. */
+/* ABI 2: the part that owns each panel of a plan (n_results[k] = the panel's result count, as dg_plan_* report them):
+ * largest panels first, each to the part with the least work so far -- deterministic, so every rank derives the same
+ * shares.  (Round-robin dealing left the largest of 8 shares 12 - 20 % above the mean.) */
+DG_API int dg_plan_parts(const uint64_t *n_results, uint64_t count, uint32_t n_parts, uint32_t *part_of);
+
 DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
                            uint64_t cap);
 
@@ -244,8 +249,8 @@ DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t 
  * hands the alignment over in chunks, HIGHEST records first.  Row i of the upper triangle (src/lib.rs:512-513)
  * only needs the records j > i, so as soon as the records [lo, n) are on the device every result panel whose rows
  * start at or above lo runs: the PCIe upload, packing + tiles and the D2H of finished panels overlap.
- *   - dg_square_begin plans the session: this part's panels (panel k of the session's plan belongs to part
- *     k % n_parts, as in dg_run_part) and the chunk sequence, which is the same for every part.
+ *   - dg_square_begin plans the session: this part's panels (dealt by dg_plan_parts over the session's
+ *     plan, as in dg_run_part) and the chunk sequence, which is the same for every part.
  *   - dg_square_next returns the record range [*lo, *hi) the next dg_square_push must deliver (*lo == *hi: done).
  *   - dg_square_push takes that chunk: `codes` points at the first byte of record lo; src_device < 0 = host memory
  *     (pinned memory makes the copy asynchronous), otherwise the CUDA device that holds it (peer copy, e.g. a chunk

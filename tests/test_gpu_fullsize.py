@@ -119,7 +119,7 @@ def test_config4_k80_stream_full_size(dg, oracle):
 
 def test_config5_jc69_share_of_100k(dg, oracle):
     """BASELINE config 5 / the north-star target: jc69 all-vs-all over 100,000 x 29,903 records; ONE rank's share
-    (panels k % 8 == 0, what one of 8 B200s computes), rows sampled against the oracle (measures.rs:56-77)."""
+    (part 0 of 8, what one of 8 B200s computes), rows sampled against the oracle (measures.rs:56-77)."""
     from distance_b200 import api, synth
     rng = np.random.default_rng(5)
     n = 100000
@@ -128,7 +128,8 @@ def test_config5_jc69_share_of_100k(dg, oracle):
     with dg.Engine("jc69", W) as e:
         e.load(0, asc, input_kind=api.DG_INPUT_ASCII)
         plan = e.plan(api.DG_MODE_SQUARE)
-        mine = [p for k, p in enumerate(plan) if k % 8 == 0]
+        from distance_b200 import dist
+        mine = dist.my_panels(plan, 0, 8)
         sample_rows = {}
         for (r0, r1, _) in (mine[0], mine[len(mine) // 2], mine[-1]):
             for r in (r0, (r0 + r1) // 2, r1 - 1):

@@ -460,7 +460,7 @@ def test_multi_gpu_single_process_matches_oracle(dg, oracle, engine):
             e.set_option(api.DG_OPT_PANEL_BYTES, 512 * n * (4 if measure == "n_high" else 8))
             e.load(0, codes)
             got = e.run_square()
-            assert len(e.last_panels) >= ndev + 1   # (the planner may merge small panels for fuller launches)
+            assert len(e.last_panels) >= ndev       # every device takes a panel (the planner may merge small ones)
             check(measure, got, want)
             loaded, streamed = codes[:40], codes[40:400]
             e.load(0, loaded)

@@ -84,7 +84,8 @@ def main():
             e.load(1, pinned(b))
         part, parts = (0, args.parts) if cfg == 5 else (0, 1)
         plan = e.plan(mode)
-        pairs = sum(p[2] for k, p in enumerate(plan) if k % parts == part)
+        from distance_b200 import dist
+        pairs = sum(p[2] for p in dist.my_panels(plan, part, parts))
         for _ in range(args.warmup):
             e.run_device_only(mode, part, parts, repack=True)
         ms = []

@@ -72,7 +72,8 @@ def square_or_rect(cfg, measure, a, b, args, part=0, n_parts=1, u16=False):
     if elem == 2:
         e.set_option(api.DG_OPT_PANEL_BYTES, 128 << 20)
     plan = e.plan(mode)
-    pairs = sum(p[2] for k, p in enumerate(plan) if k % n_parts == part)
+    from distance_b200 import dist
+    pairs = sum(p[2] for p in dist.my_panels(plan, part, n_parts))
     for _ in range(2):
         e.run_device_only(mode, part, n_parts, repack=True)
     ms = []
