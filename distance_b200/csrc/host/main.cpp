@@ -173,6 +173,29 @@ int measure_id(const std::string& m) {
     return -1;
 }
 
+// GPUs the run can use, from the device files of the driver (no CUDA call: the point is to decide BEFORE the driver starts)
+int count_gpu_device_files() {
+    int n = 0;
+    char path[64];
+    for (int i = 0; i < 64; i++) {
+        snprintf(path, sizeof path, "/dev/nvidia%d", i);
+        if (access(path, F_OK) == 0) n++;
+    }
+    return n;
+}
+// A run that needs k of the box's GPUs hides the others from the driver before its first CUDA call: on an 8-GPU NVSwitch
+// box the start-up of the driver costs 8 - 10 s with every device visible (measured: dg_create done at 9.7 s for a 2-GPU
+// run) against ~1 s on a single-GPU box.  Respects an existing CUDA_VISIBLE_DEVICES / DISTANCE_GPUS.
+void limit_visible_devices(double pair_sites) {
+    if (std::getenv("CUDA_VISIBLE_DEVICES") || std::getenv("DISTANCE_GPUS") || pair_sites <= 0) return;
+    const int have = count_gpu_device_files();
+    const int want = (int)std::max(1.0, std::ceil(pair_sites / 2e13));
+    if (have <= 1 || want >= have) return;
+    std::string v;
+    for (int i = 0; i < want; i++) v += (i ? "," : "") + std::to_string(i);
+    setenv("CUDA_VISIBLE_DEVICES", v.c_str(), 1);
+}
+
 // pair_sites: the work of the run (0 = unknown, e.g. a stream of unknown length: every visible device)
 std::vector<int> gpu_list(double pair_sites) {
     std::vector<int> ids;
@@ -266,6 +289,7 @@ int run(const Args& a) {
         const double n0 = (double)loaded[0].n(), n1 = loaded.size() > 1 ? (double)loaded[1].n() : 0;
         pair_sites = (loaded.size() > 1 ? n0 * n1 : n0 * (n0 - 1) / 2) * (double)width;
     }
+    limit_visible_devices(pair_sites);
     const std::vector<int> gpus = gpu_list(pair_sites);
     if (trace) fprintf(stderr, "[distance] %zu GPU(s)\n", gpus.size());
     dg_ctx* ctx = nullptr;
