@@ -229,11 +229,16 @@ def spike(asc, rng):
     """Three planted records so that the sampled check meets the special values: an all-N record (no compared site:
     NaN), a copy of its neighbour (identical pair: -0.0 / 0.0), a random-base record (saturated distances)."""
     n, w = asc.shape
-    if n >= 8:
-        asc[3, :] = ord("N")
-        asc[5, :] = asc[4, :]
-        asc[7, :] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=w)]
+    if n >= 16:   # at both ends: as COLUMNS the last ones meet every sampled row of an all-vs-all, whichever part owns it
+        for base in (0, n - 8):
+            asc[base + 3, :] = ord("N")
+            asc[base + 5, :] = asc[base + 4, :]
+            asc[base + 7, :] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=w)]
     return asc
+
+
+def special_indices(n):
+    return [3, 4, 5, 7, n - 5, n - 4, n - 3, n - 1] if n >= 16 else []
 
 
 class RowGrabber:
@@ -298,7 +303,7 @@ def check_rows(measure, mode_name, grab, row_codes_of, col_codes_of, n_cols_tota
         k = min(per_row, avail)
         cols = np.unique(np.concatenate([rng.integers(first, n_cols_total, size=k), np.arange(first, min(n_cols_total, first + 24)),
                                          [n_cols_total - 1]]))
-        specials = [c for c in (3, 4, 5, 7) if first <= c < n_cols_total]
+        specials = [c for c in special_indices(n_cols_total) if first <= c < n_cols_total]
         cols = np.unique(np.concatenate([cols, np.array(specials, dtype=cols.dtype)])) if specials else cols
         want = oracle_pairs(measure, row_codes_of(r), [col_codes_of(int(c)) for c in cols], swap=swap)
         got = vals[cols - first]
@@ -428,7 +433,7 @@ def config_square_or_rect(cfg_id, label, measure, a_asc, b_asc, d, args, dg, api
     eng.load(0, pa, input_kind=api.DG_INPUT_ASCII)
     if pb is not None:
         eng.load(1, pb, input_kind=api.DG_INPUT_ASCII)
-    rows = sample_rows_of(mine, (3, 4, 5, 7), rng)
+    rows = sample_rows_of(mine, special_indices(n_rows), rng)
     dtype = (np.uint16 if is_int else np.float64)
     grab = RowGrabber(api, mode, n_rows, n_cols, dtype, rows)
     eng._check(eng.L.dg_run_part(eng.h, mode, part, parts, grab.cb, None, 0))
