@@ -160,6 +160,8 @@ struct Device {
     uint32_t* h_pp_total = nullptr; // pinned {entries}
     double* h_pp_work = nullptr;    // pinned
     cudaEvent_t chunk_ev[32] = {};
+    cudaStream_t unpack = nullptr;     // sessions fed with nibble rows: the unpacked copy is written here, off the critical path
+    cudaEvent_t unpack_ev[32] = {};    // chunk g's unpacked bytes are in place
     unsigned long long* d_invalid = nullptr;  // [3]: ring slot 0, ring slot 1, resident loads
     unsigned long long* h_invalid = nullptr;  // [3] pinned mirror
     // pipelined all-vs-all session (dg_square_*): a deeper result ring of small panels + the chunked index
@@ -509,11 +511,14 @@ void alloc_tc_operands(dg_ctx* c, PlaneSet& s) {
 // this rank's panels but rows of nobody's here: a rank of a multi-process run packs U planes for its own rows only).
 void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n, int input_kind, bool count_acgt,
                      cudaStream_t st, uint64_t row0 = 0, unsigned long long* d_inv = nullptr, bool upper_ascii = false,
-                     Device* pp_dev = nullptr, bool b_side_only = false) {
+                     Device* pp_dev = nullptr, bool b_side_only = false, bool nibble_rows = false) {
     const TcSchedule& sch = tc_schedule(c->fam);
     const uint64_t n_pad = (n + ROW_ALIGN - 1) / ROW_ALIGN * ROW_ALIGN;
     tc::PackI8Params pp{};
-    pp.codes = d_codes + row0 * c->width; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
+    // nibble_rows: d_codes holds DG_INPUT_NIBBLE rows; the kernel expands them in registers (no unpacked copy is read)
+    pp.nibble = nibble_rows ? 1 : 0;
+    pp.in_stride = nibble_rows ? (c->width + 1) / 2 : c->width;
+    pp.codes = d_codes + row0 * pp.in_stride; pp.n = n; pp.n_pad = n_pad; pp.width = c->width; pp.wp8 = s.tc_wp8;
     pp.ops = s.tc_ops + (size_t)row0 * sch.nplanes * s.tc_wp8;
     pp.acgt = count_acgt ? s.acgt + row0 * 4 : nullptr;
     pp.count_upper_ascii = upper_ascii && input_kind == DG_INPUT_ASCII ? 1 : 0;
@@ -534,7 +539,8 @@ void enqueue_tc_pack(dg_ctx* c, PlaneSet& s, const uint8_t* d_codes, uint64_t n,
     const unsigned grid = (unsigned)std::min<uint64_t>(n_pad, 148 * 8);
     auto launch = [&](auto fp4, auto fam) {
         static_assert(tc::PackPlanes<decltype(fam)::value>::N <= tc::MAX_PLANES, "plane list too long");
-        tc::pack_ops_kernel<decltype(fp4)::value, decltype(fam)::value><<<grid, 256, 0, st>>>(pp);
+        if (nibble_rows) tc::pack_ops_kernel<decltype(fp4)::value, decltype(fam)::value, true><<<grid, 256, 0, st>>>(pp);
+        else tc::pack_ops_kernel<decltype(fp4)::value, decltype(fam)::value, false><<<grid, 256, 0, st>>>(pp);
     };
     auto by_fam = [&](auto fp4) {
         switch (c->fam) {
@@ -610,6 +616,10 @@ void set_side_kernel_carveouts() {
     prefer_max_carveout(tc::pack_ops_kernel<true, FAM_RAW>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_RAW>);
     prefer_max_carveout(tc::pack_ops_kernel<true, FAM_K80>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_K80>);
     prefer_max_carveout(tc::pack_ops_kernel<true, FAM_TN93>); prefer_max_carveout(tc::pack_ops_kernel<false, FAM_TN93>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_SNP, true>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_SNP, true>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_RAW, true>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_RAW, true>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_K80, true>);  prefer_max_carveout(tc::pack_ops_kernel<false, FAM_K80, true>);
+    prefer_max_carveout(tc::pack_ops_kernel<true, FAM_TN93, true>); prefer_max_carveout(tc::pack_ops_kernel<false, FAM_TN93, true>);
     prefer_max_carveout(tc::pp_correct_kernel);
     prefer_max_carveout(tc::pp_correct_chunks_kernel);
     prefer_max_carveout(tc::pp_correct_scan_kernel<true>);
@@ -1417,6 +1427,7 @@ void sq_report_invalid(dg_ctx* c, Device& d, unsigned long long key) {
     c->inv_record = key >> 32;
     c->inv_site = key & 0xffffffffull;
     c->inv_byte = 0;
+    if (c->sq_nibble) CUDA_CHECK(cudaStreamSynchronize(d.unpack));   // the unpacked copy of that chunk
     CUDA_CHECK(cudaMemcpy(&c->inv_byte, d.set[0].codes + c->inv_record * c->width + c->inv_site, 1, cudaMemcpyDeviceToHost));
     fail(DG_ERR_INVALID_CODE, "invalid nucleotide byte 0x%02x in record %llu at site %llu", c->inv_byte,
          (unsigned long long)c->inv_record, (unsigned long long)c->inv_site);
@@ -1541,6 +1552,7 @@ void sq_pump(dg_ctx* c, size_t g) {
         } else if (total > c->sq_base[g]) {   // hit buffer overflowed: rescan the chunk's codes
             const uint64_t nr = ch.hi - ch.lo;
             const unsigned gb = (unsigned)std::min<uint64_t>((nr * c->width + 255) / 256, 148 * 32);
+            if (c->sq_nibble && c->sq_tc) CUDA_CHECK(cudaStreamWaitEvent(d.fill, d.unpack_ev[g & 31], 0));   // the unpacked copy
             tc::pp_fill_kernel<<<gb, 256, 0, d.fill>>>(S.codes + ch.lo * c->width, nr, c->width, c->sq_input_kind == DG_INPUT_ASCII,
                                                       cursor, d.sq_entries, ch.lo);
             CUDA_CHECK(cudaGetLastError());
@@ -1719,11 +1731,20 @@ void sq_push(dg_ctx* c, const uint8_t* codes, int src_dev, uint64_t lo, uint64_t
     if (c->sq_trace) CUDA_CHECK(cudaEventRecord(d.tr_copy[g], d.copy_in));
     // packing + index scan of this chunk: enqueued now, runs as soon as the copy has landed
     CUDA_CHECK(cudaStreamWaitEvent(d.prep, ev, 0));
-    if (c->sq_nibble) enqueue_nibble_unpack(c, dst, S.codes + lo * c->width, nr, d.prep);
+    // Nibble rows: the tensor-core pack reads them directly, so the unpacked copy (kept for what runs on the resident
+    // alignment later: the LOP3 engine, a rescan of the partial codes, re-packing) is written off the critical path.
+    const bool fused_nibble = c->sq_nibble && c->sq_tc;
+    if (fused_nibble) {
+        CUDA_CHECK(cudaStreamWaitEvent(d.unpack, ev, 0));
+        enqueue_nibble_unpack(c, dst, S.codes + lo * c->width, nr, d.unpack);
+        CUDA_CHECK(cudaEventRecord(d.unpack_ev[g & 31], d.unpack));
+    } else if (c->sq_nibble) {
+        enqueue_nibble_unpack(c, dst, S.codes + lo * c->width, nr, d.prep);
+    }
     if (c->sq_tc) {
         if (c->sq_needs_pp) CUDA_CHECK(cudaMemsetAsync(d.pp_cnt, 0, (size_t)c->width * 4, d.prep));
-        enqueue_tc_pack(c, S, S.codes, nr, c->sq_input_kind, !S.acgt_from_host && c->fam == FAM_TN93, d.prep, lo,
-                        d.d_invalid + 2, false, c->sq_needs_pp ? &d : nullptr);
+        enqueue_tc_pack(c, S, fused_nibble ? S.nib : S.codes, nr, c->sq_input_kind, !S.acgt_from_host && c->fam == FAM_TN93, d.prep, lo,
+                        d.d_invalid + 2, false, c->sq_needs_pp ? &d : nullptr, false, fused_nibble);
         if (c->sq_needs_pp) {
             tc::pp_scan_chunk_kernel<<<1, 1024, 0, d.prep>>>(d.pp_cnt, d.sq_cum, c->width, d.sq_off + g * (size_t)(c->width + 1),
                                                              d.sq_total, d.h_sq_total + g, d.h_sq_work + g, d.d_invalid + 2,
@@ -1753,6 +1774,7 @@ void sq_end(dg_ctx* c) {
     CUDA_CHECK(cudaSetDevice(d.id));
     while (c->sq_pumped < c->sq_pushed) sq_pump(c, c->sq_pumped);
     while (!c->sq_queue.empty()) sq_sink_front(c);
+    if (c->sq_nibble) CUDA_CHECK(cudaStreamSynchronize(d.unpack));   // the resident code bytes are complete from here on
     if (c->sq_trace) {
         CUDA_CHECK(cudaDeviceSynchronize());
         auto at = [&](cudaEvent_t e) { float ms = 0; cudaEventElapsedTime(&ms, d.tr_base, e); return ms; };
@@ -1908,11 +1930,13 @@ void stream_push_one(dg_ctx* c, const uint8_t* codes, uint64_t nb, int input_kin
     CUDA_CHECK(cudaStreamWaitEvent(cst, s.in_ready, 0));
     s.batch.n = nb;
     CUDA_CHECK(cudaEventRecord(s.p_start, cst));
-    if (nibble) enqueue_nibble_unpack(c, s.d_nib, s.d_in, nb, cst);
+    // tensor-core engine: the pack kernel reads the nibble rows itself (a batch's codes are not needed again: its partial
+    // codes are found by scanning its V planes); the LOP3 engine packs from unpacked bytes
+    if (nibble && !c->s_tc) enqueue_nibble_unpack(c, s.d_nib, s.d_in, nb, cst);
     s.batch.input_kind = nibble ? DG_INPUT_NIBBLE : input_kind;
     // fastaio.rs:250-254: the streamed tn93 records count raw upper-case chars only (:139-142)
-    if (c->s_tc) enqueue_tc_pack(c, s.batch, s.d_in, nb, input_kind, !host_counts && c->fam == FAM_TN93, cst, 0,
-                                 d.d_invalid + si, true);
+    if (c->s_tc) enqueue_tc_pack(c, s.batch, nibble ? s.d_nib : s.d_in, nb, input_kind, !host_counts && c->fam == FAM_TN93, cst, 0,
+                                 d.d_invalid + si, true, nullptr, false, nibble);
     else enqueue_pack(c, d.d_invalid + si, s.batch, s.d_in, nb, input_kind, !host_counts, input_kind == DG_INPUT_ASCII, cst);
     CUDA_CHECK(cudaEventRecord(s.p_stop, cst));
     Panel p;
@@ -2020,6 +2044,8 @@ void destroy_device(Device& d) {
     if (d.h_pp_total) cudaFreeHost(d.h_pp_total);
     if (d.h_pp_work) cudaFreeHost(d.h_pp_work);
     for (auto& e : d.chunk_ev) if (e) cudaEventDestroy(e);
+    for (auto& e : d.unpack_ev) if (e) cudaEventDestroy(e);
+    if (d.unpack) cudaStreamDestroy(d.unpack);
     if (d.run_start) cudaEventDestroy(d.run_start);
     if (d.run_stop) cudaEventDestroy(d.run_stop);
     if (d.d_invalid) cudaFree(d.d_invalid);
@@ -2119,6 +2145,7 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
                 CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
                 CUDA_CHECK(cudaStreamCreateWithPriority(&d.prep, cudaStreamNonBlocking, hi_pri));
                 CUDA_CHECK(cudaStreamCreateWithPriority(&d.fill, cudaStreamNonBlocking, hi_pri));
+                CUDA_CHECK(cudaStreamCreateWithPriority(&d.unpack, cudaStreamNonBlocking, lo_pri));
                 CUDA_CHECK(cudaEventCreateWithFlags(&d.sq_ready, cudaEventDisableTiming));
             }
             for (auto& s : d.slot)
@@ -2135,6 +2162,7 @@ int dg_create(const int* gpu_ids, int n_gpus, int measure, uint64_t width, dg_ct
             CUDA_CHECK(cudaHostAlloc(&d.h_pp_total, 4, cudaHostAllocDefault));
             CUDA_CHECK(cudaHostAlloc(&d.h_pp_work, 8, cudaHostAllocDefault));
             for (auto& e : d.chunk_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            for (auto& e : d.unpack_ev) CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             set_side_kernel_carveouts();
             CUDA_CHECK(cudaMemcpyToSymbol(c_ascii_lut, lut, 256));
             CUDA_CHECK(cudaMemcpyToSymbol(c_valid_code, valid, 32));

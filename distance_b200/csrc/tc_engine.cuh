@@ -249,6 +249,8 @@ struct PackI8Params {
     int8_t* ops;           // n_pad x nplanes x wp8
     uint32_t* acgt;        // n_pad x 4 (A,T,G,C) written per record, or NULL
     int ascii;
+    int nibble;            // `codes` holds DG_INPUT_NIBBLE rows (two sites per byte, low nibble first) of in_stride bytes
+    uint64_t in_stride;    // bytes between the input rows: width, or (width + 1) / 2 for nibble rows
     int count_upper_ascii; // ASCII input: count raw 'A','T','G','C' only (fastaio.rs:139-142) instead of count_bases
     int nplanes;
     uint8_t plane_id[MAX_PLANES];
@@ -353,11 +355,46 @@ __device__ __forceinline__ uint32_t plane_nib8(const NibBits& n, uint32_t id) {
     }
 }
 
+// Four possibility nibbles (one per byte, 0 .. 15) -> four Paradis codes: nibble << 4 | 8 if exactly one bit is set (the base
+// is known); nibble 0 -> 0, which the validation below reports as an invalid byte.
+__device__ __forceinline__ uint32_t nib4_to_codes(uint32_t m) {
+    const uint32_t t = m & ((m | 0x10101010u) - M1);             // m & (m - 1) per byte: no borrow leaves a byte
+    const uint32_t many = (t + 0x7F7F7F7Fu) & 0x80808080u;       // 0x80 where two or more bits are set
+    const uint32_t some = (m + 0x7F7F7F7Fu) & 0x80808080u;       // 0x80 where the nibble is not 0
+    return (m << 4) | ((some & ~many) >> 4);
+}
+// Four nibble bytes (8 sites, low nibble = the even site) -> two words of Paradis codes.
+__device__ __forceinline__ void nib_word_to_codes(uint32_t x, uint32_t& c0, uint32_t& c1) {
+    const uint32_t lo = x & 0x0F0F0F0Fu, hi = (x >> 4) & 0x0F0F0F0Fu;
+    c0 = nib4_to_codes(__byte_perm(lo, hi, 0x5140));
+    c1 = nib4_to_codes(__byte_perm(lo, hi, 0x7362));
+}
+
 // 16 code bytes of `row` starting at site s0 -> four words of valid Paradis codes (invalid bytes reported and
 // replaced by N; sites >= width are N).  raw[] = the untranslated bytes (for the upper-case ASCII count quirk).
+template <bool NIB>
 __device__ __forceinline__ void load_codes16(const PackI8Params& p, const uint8_t* row, uint64_t seq, uint64_t s0,
                                              const uint8_t* lut, uint32_t (&w)[4], uint32_t (&raw)[4]) {
-    if (s0 + 20 <= p.width) {   // the aligned window [a & ~3, +20) stays inside this row
+    if (NIB) {             // `row` holds nibble rows: sites [s0, s0 + 16) are its bytes [s0 / 2, s0 / 2 + 8)
+        const uint8_t* src = row + (s0 >> 1);
+        if (s0 + 16 <= p.width && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+            const uint32_t* sp = reinterpret_cast<const uint32_t*>(src);
+            nib_word_to_codes(__ldcs(sp), raw[0], raw[1]);
+            nib_word_to_codes(__ldcs(sp + 1), raw[2], raw[3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint64_t st = s0 + 4 * k + j;
+                    const uint32_t nb = st < p.width ? ((uint32_t)row[st >> 1] >> (4 * (st & 1))) & 15u : 15u;
+                    m |= nb << (8 * j);
+                }
+                raw[k] = nib4_to_codes(m);
+            }
+        }
+    } else if (s0 + 20 <= p.width) {   // the aligned window [a & ~3, +20) stays inside this row
         const uintptr_t a = reinterpret_cast<uintptr_t>(row + s0);
         const uint32_t* ap = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
         const uint32_t sh = (uint32_t)(a & 3) * 8;
@@ -400,7 +437,7 @@ __device__ __forceinline__ void load_codes16(const PackI8Params& p, const uint8_
 // so they are not 16-byte aligned), translated through a 256-entry LUT in shared memory (ASCII -> Paradis,
 // encoding.rs:4-41; or Paradis -> itself if legal) and expanded to every stored plane with byte-SIMD arithmetic.
 // Per-record A,T,G,C counts (count_bases, fastaio.rs:53-66) are reduced in the CTA: no atomics.
-template <bool FP4, int FAM>
+template <bool FP4, int FAM, bool NIB = false>
 __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
     using PL = PackPlanes<FAM>;
     __shared__ uint8_t lut[256];
@@ -416,7 +453,7 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (uint64_t seq = blockIdx.x; seq < p.n_pad; seq += gridDim.x) {
         uint32_t cA = 0, cT = 0, cG = 0, cC = 0;
-        const uint8_t* row = p.codes + seq * p.width;
+        const uint8_t* row = p.codes + seq * p.in_stride;
         for (uint32_t g = threadIdx.x; g < groups; g += blockDim.x) {
             const uint64_t s0 = (uint64_t)g * SITES;
             uint32_t w[4 * H];
@@ -425,7 +462,7 @@ __global__ void __launch_bounds__(256, 3) pack_ops_kernel(PackI8Params p) {
                 uint32_t wh[4] = {0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u, 0xF0F0F0F0u};   // N-like padding
                 if (seq < p.n && s0 + 16 * h < p.width) {
                     uint32_t raw[4];
-                    load_codes16(p, row, seq, s0 + 16 * h, lut, wh, raw);
+                    load_codes16<NIB>(p, row, seq, s0 + 16 * h, lut, wh, raw);
                     if (p.pp_site_cnt) {
                         // partial code <=> "known" bit clear and possibility nibble != 1111 (0.1 % of real data: rare path)
 #pragma unroll
@@ -645,81 +682,99 @@ __global__ void publish_invalid_kernel(const unsigned long long* d_inv, unsigned
     *h_inv = *d_inv;
     __threadfence_system();
 }
-// One block of 1,024 threads; thread t owns the sites [t * per, (t + 1) * per).  This kernel sits on the critical path of
-// every upload chunk of a session (pack -> scan -> the host sizes the entry buffer), so it is written for latency: the
-// site counts are fetched in batches of 8 independent loads (round 1 walked them one dependent load at a time: ~100 us
-// per chunk, as long as the chunk's PCIe transfer) and the 1,024 partial sums are scanned with warp shuffles.
+// One block of 1,024 threads.  This kernel sits on the critical path of every upload chunk of a session (pack -> scan ->
+// the host sizes the entry buffer), so it is written for latency.
 __global__ void __launch_bounds__(1024) pp_scan_chunk_kernel(const uint32_t* __restrict__ site_cnt, uint32_t* __restrict__ cum_cnt,
                                                              uint64_t width, uint32_t* __restrict__ off, uint32_t* total,
                                                              uint32_t* h_total, double* h_work, const unsigned long long* d_inv,
                                                              unsigned long long* h_inv) {
-    __shared__ uint32_t wsum[32];
+    // One CTA, every global access coalesced: the sites are walked in segments of 16 x 1,024; inside a segment warp w owns
+    // the 32-site groups k * 32 + w (k < 16), scans each with shuffles, and the 512 group totals are scanned in two more
+    // shuffle levels.  (Thread-contiguous runs made every load its own L1 wavefront: ~100 us on the one SM.)
+    constexpr int G = 16;               // 2 G live registers per thread: 1,024 threads leave 64
+    __shared__ uint32_t gsum[G * 32];   // group totals -> exclusive prefix inside their block of 32 groups
+    __shared__ uint32_t wtot[32];       // totals of the blocks of 32 groups -> exclusive prefix
     __shared__ double wwork[32];
-    __shared__ uint32_t s_base;
+    __shared__ uint32_t s_run;          // offset of the segment's first site
     const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint64_t per = (width + 1023) / 1024;
-    const uint64_t b = min(width, (uint64_t)t * per), e = min(width, b + per);
-    uint32_t s = 0; double w = 0;
-    for (uint64_t i0 = b; i0 < e; i0 += 8) {
-        uint32_t c[8], q[8];
+    if (t == 0) { const uint32_t base = *total; s_run = base; off[0] = base; }
+    double w = 0;
+    for (uint64_t seg0 = 0; seg0 < width; seg0 += (uint64_t)G * 1024) {
+        uint32_t c[G], q[G];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const bool ok = i0 + k < e;
-            c[k] = ok ? site_cnt[i0 + k] : 0u;
-            q[k] = ok ? cum_cnt[i0 + k] : 0u;
+        for (int k = 0; k < G; k++) {
+            const uint64_t i = seg0 + (uint64_t)(k * 32 + warp) * 32 + lane;
+            const bool ok = i < width;
+            c[k] = ok ? site_cnt[i] : 0u;
+            q[k] = ok ? cum_cnt[i] : 0u;
         }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            if (i0 + k < e) {
+        for (int k = 0; k < G; k++) {
+            const uint64_t i = seg0 + (uint64_t)(k * 32 + warp) * 32 + lane;
+            if (i < width) {
                 const uint32_t cc = q[k] + c[k];
-                cum_cnt[i0 + k] = cc;
-                s += c[k];
-                w += (double)cc * cc;
+                cum_cnt[i] = cc;
+                w += (double)cc * cc;   // integers: the order of the sum does not matter
             }
+            uint32_t incl = c[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += v;
+            }
+            q[k] = incl - c[k];         // exclusive prefix inside the group
+            if (lane == 31) gsum[k * 32 + warp] = incl;
         }
-    }
-    // exclusive scan of the 1,024 partial sums (and the sum of the work terms)
-    uint32_t incl = s; double wt = w;
+        __syncthreads();
+        if (warp < G) {   // warp w scans group totals [32 w, 32 w + 32)
+            const uint32_t v = gsum[warp * 32 + lane];
+            uint32_t incl = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += u;
+            }
+            gsum[warp * 32 + lane] = incl - v;
+            if (lane == 31) wtot[warp] = incl;
+        }
+        __syncthreads();
+        uint32_t seg_total = 0;
+        if (warp == 0) {
+            const uint32_t v = lane < G ? wtot[lane] : 0u;
+            uint32_t incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= (uint32_t)o) incl += u;
+            }
+            if (lane < G) wtot[lane] = incl - v;
+            seg_total = __shfl_sync(0xffffffffu, incl, 31);
+        }
+        __syncthreads();
+        const uint32_t run0 = s_run;
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const uint64_t i = seg0 + (uint64_t)(k * 32 + warp) * 32 + lane;
+            if (i < width) off[1 + i] = run0 + wtot[k] + gsum[k * 32 + warp] + q[k];
+        }
+        __syncthreads();
+        if (t == 0) s_run = run0 + seg_total;
+        __syncthreads();
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-    if (lane == 31) wsum[warp] = incl;
-    if (lane == 0) wwork[warp] = wt;
+    for (int o = 16; o; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) wwork[warp] = w;
     __syncthreads();
     if (warp == 0) {
-        uint32_t v = wsum[lane]; double ww = wwork[lane];
-        uint32_t iv = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, iv, o);
-            if (lane >= (uint32_t)o) iv += u;
-        }
+        double ww = wwork[lane];
 #pragma unroll
         for (int o = 16; o; o >>= 1) ww += __shfl_xor_sync(0xffffffffu, ww, o);
-        wsum[lane] = iv - v;   // exclusive prefix of the warps
-        if (lane == 31) {
-            const uint32_t base = *total;
-            s_base = base;
-            off[0] = base;
-            const uint32_t run = base + iv;
+        if (lane == 0) {
+            const uint32_t run = s_run;
             *total = run;
             *h_total = run; *h_work = ww; *h_inv = *d_inv;
             __threadfence_system();
         }
-    }
-    __syncthreads();
-    uint32_t run = s_base + wsum[warp] + (incl - s);
-    for (uint64_t i0 = b; i0 < e; i0 += 8) {
-        uint32_t c[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) c[k] = i0 + k < e ? site_cnt[i0 + k] : 0u;
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (i0 + k < e) { off[1 + i0 + k] = run; run += c[k]; }
     }
 }
 

@@ -275,6 +275,18 @@ def test_nibble_zero_is_reported_as_invalid(dg):
             e.load(0, nib, input_kind=api.DG_INPUT_NIBBLE)
         assert ei.value.code == -4            # DG_ERR_INVALID_CODE
         assert e.invalid_site()[:2] == (17, 43)
+    # the pipelined session and the stream pack straight from the nibble rows: same report
+    with dg.Engine("n_high", 100) as e:
+        with pytest.raises(api.DistanceGpuError) as ei:
+            e.square_pipelined(nib, input_kind=api.DG_INPUT_NIBBLE)
+        assert ei.value.code == -4 and e.invalid_site() == (17, 43, 0)
+        got, _ = e.square_pipelined(api.pack_nibbles(codes), input_kind=api.DG_INPUT_NIBBLE)   # the context is usable again
+        assert got.shape == (40 * 39 // 2,)
+    with dg.Engine("k80", 100) as e:
+        e.load(0, codes)
+        with pytest.raises(api.DistanceGpuError) as ei:
+            e.stream([nib], input_kind=api.DG_INPUT_NIBBLE, max_batch=64)
+        assert ei.value.code == -4
 
 
 @pytest.mark.parametrize("engine", [1, 3])
