@@ -129,7 +129,7 @@ bool FastaReader::fill() {
     }
 }
 
-bool FastaReader::read_line() {
+bool FastaReader::read_line_raw() {
     line_.clear();
     bool got = false;
     for (;;) {
@@ -147,13 +147,73 @@ bool FastaReader::read_line() {
     }
 }
 
-static size_t trimmed_len(const std::string& s) {
+// rust-bio 1.6.0 (io/fasta.rs, Reader::read) reads every line into a String -- so a line that is not valid UTF-8 fails with
+// io::ErrorKind::InvalidData --, trims it with str::trim_end() and splits the header at the first char::is_whitespace.  Both
+// use the Unicode White_Space property: U+0009..000D, U+0020, U+0085, U+00A0, U+1680, U+2000..200A, U+2028, U+2029,
+// U+202F, U+205F, U+3000.
+static size_t ws3(unsigned char a, unsigned char b, unsigned char c) {   // a three-byte white-space character?
+    if (a == 0xE1) return (b == 0x9A && c == 0x80) ? 3 : 0;                                   // U+1680
+    if (a == 0xE3) return (b == 0x80 && c == 0x80) ? 3 : 0;                                   // U+3000
+    if (a != 0xE2) return 0;
+    if (b == 0x80) return (c >= 0x80 && c <= 0x8A) || c == 0xA8 || c == 0xA9 || c == 0xAF ? 3 : 0;   // U+2000..200A, 2028, 2029, 202F
+    return (b == 0x81 && c == 0x9F) ? 3 : 0;                                                  // U+205F
+}
+static bool ascii_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+// bytes of the white-space character that starts at p[0] (n bytes are readable), or 0
+static size_t ws_at_start(const char* p, size_t n) {
+    const unsigned char a = (unsigned char)p[0];
+    if (a < 0x80) return ascii_ws(a) ? 1 : 0;
+    if (a == 0xC2) return n >= 2 && ((unsigned char)p[1] == 0x85 || (unsigned char)p[1] == 0xA0) ? 2 : 0;   // U+0085, U+00A0
+    return n >= 3 ? ws3(a, (unsigned char)p[1], (unsigned char)p[2]) : 0;
+}
+// bytes of the white-space character that ends at p[n - 1], or 0
+static size_t ws_at_end(const char* p, size_t n) {
+    const unsigned char z = (unsigned char)p[n - 1];
+    if (z < 0x80) return ascii_ws(z) ? 1 : 0;
+    if (n >= 2 && (unsigned char)p[n - 2] == 0xC2) return z == 0x85 || z == 0xA0 ? 2 : 0;
+    return n >= 3 ? ws3((unsigned char)p[n - 3], (unsigned char)p[n - 2], z) : 0;
+}
+static size_t trimmed_len(const std::string& s) {   // str::trim_end
     size_t n = s.size();
     while (n > 0) {
-        unsigned char c = (unsigned char)s[n - 1];
-        if (c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f') n--; else break;
+        const size_t k = ws_at_end(s.data(), n);
+        if (k == 0) break;
+        n -= k;
     }
     return n;
+}
+// core::str::from_utf8: no overlong forms, no surrogates, nothing above U+10FFFF
+static bool valid_utf8(const char* p, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        const unsigned char a = (unsigned char)p[i];
+        if (a < 0x80) { i++; continue; }
+        auto cont = [&](size_t k, unsigned char lo = 0x80, unsigned char hi = 0xBF) {
+            return i + k < n && (unsigned char)p[i + k] >= lo && (unsigned char)p[i + k] <= hi;
+        };
+        if (a >= 0xC2 && a <= 0xDF) { if (!cont(1)) return false; i += 2; }
+        else if (a == 0xE0) { if (!cont(1, 0xA0, 0xBF) || !cont(2)) return false; i += 3; }
+        else if ((a >= 0xE1 && a <= 0xEC) || a == 0xEE || a == 0xEF) { if (!cont(1) || !cont(2)) return false; i += 3; }
+        else if (a == 0xED) { if (!cont(1, 0x80, 0x9F) || !cont(2)) return false; i += 3; }
+        else if (a == 0xF0) { if (!cont(1, 0x90, 0xBF) || !cont(2) || !cont(3)) return false; i += 4; }
+        else if (a >= 0xF1 && a <= 0xF3) { if (!cont(1) || !cont(2) || !cont(3)) return false; i += 4; }
+        else if (a == 0xF4) { if (!cont(1, 0x80, 0x8F) || !cont(2) || !cont(3)) return false; i += 4; }
+        else return false;
+    }
+    return true;
+}
+static bool has_high_byte(const char* p, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if ((unsigned char)p[i] >= 0x80) return true;
+    return false;
+}
+
+bool FastaReader::read_line() {
+    const bool got = read_line_raw();
+    // BufRead::read_line: io::Error::INVALID_UTF8, a SimpleMessage (its Debug form is `Error { kind, message }`)
+    if (got && has_high_byte(line_.data(), line_.size()) && !valid_utf8(line_.data(), line_.size()))
+        throw DistanceError("IOError(Error { kind: InvalidData, message: \"stream did not contain valid UTF-8\" })");
+    return got;
 }
 
 bool FastaReader::next(std::string& id, std::vector<uint8_t>& seq) {
@@ -164,7 +224,7 @@ bool FastaReader::next(std::string& id, std::vector<uint8_t>& seq) {
     if (line_.empty() || line_[0] != '>') throw io_error_custom("Expected > at record start.");
     const size_t hl = trimmed_len(line_);
     size_t sp = 1;
-    while (sp < hl && !std::isspace((unsigned char)line_[sp])) sp++;
+    while (sp < hl && ws_at_start(line_.data() + sp, hl - sp) == 0) sp++;   // splitn(2, char::is_whitespace)
     id.assign(line_, 1, sp - 1);
     const bool has_desc = sp < hl;
     const size_t seq0 = seq.size();
@@ -173,9 +233,10 @@ bool FastaReader::next(std::string& id, std::vector<uint8_t>& seq) {
         if (!read_line()) break;
         if (!line_.empty() && line_[0] == '>') { have_line_ = true; break; }
         const size_t n = trimmed_len(line_);
-        if (validate_) validate_record(id, (const uint8_t*)line_.data(), n);  // fastaio.rs:111-113
         seq.insert(seq.end(), line_.begin(), line_.begin() + n);
     }
+    // fastaio.rs:111-113 runs on the complete record: an unreadable line (of this record or the next header) is reported first
+    if (validate_) validate_record(id, seq.data() + seq0, seq.size() - seq0);
     if (id.empty() && !has_desc && seq.size() == seq0) return false;  // rust-bio: an empty record ends the iteration
     return true;
 }
@@ -253,6 +314,7 @@ inline const char* walk_record(const char* p, const char* end, const char*& id0,
     const char* q = p + 1;
     while (q < t && !std::isspace((unsigned char)*q)) q++;
     id0 = p + 1; id_len = (size_t)(q - (p + 1)); has_desc = q < t;
+    if (has_high_byte(p, (size_t)(hend - p))) id_len = 0;   // Unicode white space / UTF-8 validity: the sequential reader decides
     p = nl ? nl + 1 : end;
     while (p < end && *p != '>') {
         nl = static_cast<const char*>(std::memchr(p, '\n', (size_t)(end - p)));

@@ -61,7 +61,8 @@ public:
     bool at_end() const { return eof_ && pos_ == end_ && !have_line_; }
 
 private:
-    bool read_line();  // fills line_ (without the '\n'); false at EOF with nothing read
+    bool read_line();      // fills line_ (without the '\n'); false at EOF with nothing read; throws on invalid UTF-8
+    bool read_line_raw();
     bool fill();
     int fd_;
     const char* mem_ = nullptr;   // in-memory source (fd_ < 0)

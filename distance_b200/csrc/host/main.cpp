@@ -455,6 +455,9 @@ int selftest_parse(const char* path, int threads) {
     printf("selftest-parse: %s; records %llu width %llu; parallel loader %.3f s (%s), sequential reader %.3f s; error '%s'\n",
            same ? "identical" : "MISMATCH", (unsigned long long)slow.n(), (unsigned long long)slow.width, tf,
            fast.fast_ ? "parallel pass" : "fell back to the sequential reader", ts, es.c_str());
+    if (std::getenv("DG_SELFTEST_DUMP"))   // tests: what the reader made of the file, one "id<TAB>sequence" line per record
+        for (uint64_t r = 0; r < slow.n(); r++)
+            printf("%s\t%.*s\n", slow.ids[r].c_str(), (int)slow.width, (const char*)slow.data() + r * slow.width);
     return same ? 0 : 1;
 }
 

@@ -284,6 +284,63 @@ def test_fasta_tokenisation_choices(tmp_path):
     # an inner blank is a sequence byte: invalid nucleotide
     out = _selftest_parse(tmp_path, ">a\nACGTA CGTA\n")
     assert "Invalid nucleotide character in record 'a': ' '" in out
-    # deviation from str::trim_end: U+00A0 at a line end is not trimmed, it is reported (as its first UTF-8 byte, Latin-1)
-    out = _selftest_parse(tmp_path, ">a\nACGTACGTAC \n")
-    assert "Invalid nucleotide character in record 'a'" in out
+    # str::trim_end strips Unicode White_Space: U+00A0 at a line end is trimmed like a blank
+    out = _selftest_parse(tmp_path, ">a\nACGTACGTAC\u00a0\n")
+    assert "records 1 width 10" in out and "error ''" in out
+
+
+def _dump(tmp_path, data, threads=4):
+    f = tmp_path / "u.fa"
+    f.write_bytes(data)
+    p = subprocess.run([CLI, "--selftest-parse", str(f), str(threads)], capture_output=True, timeout=60,
+                       env=dict(os.environ, DG_SELFTEST_DUMP="1"))
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    lines = p.stdout.decode("utf-8", "replace").split("\n")
+    assert "identical" in lines[0], lines[0]
+    return lines[0], [tuple(x.split("\t")) for x in lines[1:] if x]
+
+
+def test_unicode_white_space_and_utf8_like_rust_bio(tmp_path):
+    """rust-bio 1.6.0 reads lines into a String (invalid UTF-8 = io::ErrorKind::InvalidData), trims them with str::trim_end and
+    splits the header at the first char::is_whitespace: all three use Unicode White_Space, not the ASCII blanks."""
+    ws = ["\u0085", "\u00a0", "\u1680", "\u2000", "\u2003", "\u200a", "\u2028", "\u2029", "\u202f", "\u205f", "\u3000", "\x0b", "\x0c"]
+    # every White_Space character is trimmed from the end of a sequence line and of a header, and ends an id
+    for k, w in enumerate(ws):
+        text = f">id{k}{w}a description{w}{w}\nACGTA{w}\nCGTAC{w} \t{w}\n>next\nACGTACGTAC\n"
+        head, recs = _dump(tmp_path, text.encode("utf-8"))
+        assert "records 2 width 10" in head and "error ''" in head, (w.encode("unicode_escape"), head)
+        assert recs == [(f"id{k}", "ACGTACGTAC"), ("next", "ACGTACGTAC")], (w.encode("unicode_escape"), recs)
+    # not white space: U+200B (zero width space), U+180E, U+FEFF stay -- in an id as bytes of the id, in a sequence as an invalid byte
+    for w in ["\u200b", "\u180e", "\ufeff"]:
+        head, recs = _dump(tmp_path, f">a{w}b c\nACGT\n".encode("utf-8"))
+        assert recs == [(f"a{w}b", "ACGT")], recs
+        head, _ = _dump(tmp_path, f">a\nACGT{w}\n".encode("utf-8"))
+        assert "Invalid nucleotide character in record 'a': '" in head
+    # a non-ASCII letter in a sequence: the first byte of its UTF-8 form, shown as the Latin-1 character (`*nuc as char`)
+    head, _ = _dump(tmp_path, ">a\nAC\u00e9GT\n".encode("utf-8"))
+    assert "Invalid nucleotide character in record 'a': '\u00c3'" in head
+    # invalid UTF-8 anywhere in a line is BufRead::read_line's error, whatever else is wrong with the record ...
+    bad_utf8 = 'IOError(Error { kind: InvalidData, message: "stream did not contain valid UTF-8" })'
+    for data in [b">a\nACGT\xff\n", b">a \xc3\x28 desc\nACGT\n", b">a\nACXT\nAC\xe2\x80\n", b">a\nACGT\n>b\xed\xa0\x80\nACGT\n",
+                 b">a\nACGT\n>b\nAC\xc0\xafGT\n", b"\xf5>a\nACGT\n", b">a\nACGT\xf4\x90\x80\x80\n"]:
+        head, _ = _dump(tmp_path, data)
+        assert bad_utf8 in head, (data, head)
+    # ... read while its record is read: the header of the NEXT record is read with this record's lines, before encode() runs
+    head, _ = _dump(tmp_path, b">a\nACXT\n>b\xff\nACGT\n")
+    assert bad_utf8 in head
+    # but an invalid nucleotide in an EARLIER record is met first
+    head, _ = _dump(tmp_path, b">a\nACXT\n>b\nACGT\n>c\xff\nACGT\n")
+    assert "Invalid nucleotide character in record 'a': 'X'" in head
+    # the block parser of the streamed file hands such records to the same sequential reader
+    recs = [(f"q{i}", "ACGTACGTACGT") for i in range(400)]
+    text = _fasta(recs[:100]) + ">odd\u2003id\u00a0\nACGTAC\u3000\nGTACGT\n" + _fasta(recs[100:])
+    assert "records 401 (block parser 401)" in _selftest_stream(tmp_path, text, 12, 64)
+    f = tmp_path / "s.fa"
+    f.write_bytes(_fasta(recs[:100]).encode() + b">x\nACGTAC\xffTACGT\n" + _fasta(recs[100:]).encode())
+    rc, out, err = run(["--selftest-stream", str(f), "12", "64", "4"])
+    assert rc == 0 and "stream did not contain valid UTF-8" in out, (out, err)
+    # through the whole CLI: the reference's `Error: {:?}` line and exit code 1
+    f = tmp_path / "bad.fa"
+    f.write_bytes(b">a\nACGT\n>b\nAC\xffT\n")
+    rc, out, err = run(["-i", str(f)])
+    assert rc == 1 and out == "" and err.strip() == "Error: " + bad_utf8
