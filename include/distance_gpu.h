@@ -235,13 +235,13 @@ DG_API int64_t dg_plan_panels(int measure, int mode, uint64_t n_rows, uint64_t n
                               int tile_variant, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
                               uint64_t cap);
 
-/* The same plan for THIS context: its loaded alignments, panel bytes, tile variant and result width
- * (uint16 panels hold twice the rows of uint32 ones).  Returns the number of panels or a negative DG_ERR_*. */
 /* ABI 2: the part that owns each panel of a plan (n_results[k] = the panel's result count, as dg_plan_* report them):
  * largest panels first, each to the part with the least work so far -- deterministic, so every rank derives the same
  * shares.  (Round-robin dealing left the largest of 8 shares 12 - 20 % above the mean.) */
 DG_API int dg_plan_parts(const uint64_t *n_results, uint64_t count, uint32_t n_parts, uint32_t *part_of);
 
+/* The same plan for THIS context: its loaded alignments, panel bytes, tile variant and result width
+ * (uint16 panels hold twice the rows of uint32 ones).  Returns the number of panels or a negative DG_ERR_*. */
 DG_API int64_t dg_plan_ctx(dg_ctx *ctx, int mode, uint64_t *row_begin, uint64_t *row_end, uint64_t *n_results,
                            uint64_t cap);
 
